@@ -1,0 +1,887 @@
+// enc_engine.cuh -- the serial half of the libcsc encode path, one stream per warp.
+//
+// What runs here is everything that SURVEY.md H1 proves serially dependent
+// inside one stream: dynamic block typing + run merging
+// (csc_encoder_main.cpp:85-146), the state-aware filtering of the parallel
+// match-finder precomputation so that it reproduces the reference tables
+// exactly (csc_mf.cpp:134-495), the lazy parser (csc_lz.cpp:156-199), the
+// price-optimal parser (csc_lz.cpp:207-362), the packet grammar
+// (csc_model.cpp) and the range / raw-bit coder (csc_coder.{h,cpp}).
+//
+// It is NOT a translation of the reference's data structures: the 6-byte hash
+// table does not exist here.  The parallel kernels (mf_kernels.cu) produce, for
+// every position p, the K nearest earlier positions with the same 6-byte hash
+// (row P6[p]) and their forward match lengths (L6[p]).  The reference bucket
+// at any moment equals "the first W entries along that chain that are still
+// alive", where a position is NOT alive if it was skipped by SlidePos' long-
+// match rule (csc_mf.cpp:145), sampled out by SlidePosFast (csc_mf.cpp:215),
+// or overwritten by the run de-duplication rule (csc_mf.cpp:147-157).  The
+// engine keeps one bit per position (D6) for that and walks rows.
+// The tiny 2-/3-byte single-slot tables are emulated directly (320 KiB).
+#pragma once
+#include "csc_defs.h"
+#include "warp.h"
+
+namespace cscb {
+
+CSC_HD u32 ilog2(u32 v) {
+#if defined(__CUDA_ARCH__)
+    return 31u - (u32)__clz((int)v);
+#else
+    return 31u - (u32)__builtin_clz(v);
+#endif
+}
+
+// distance slot: largest s with dist_table_[s] <= d (csc_model.cpp:45-55,331-342);
+// the table is {0,1,2, 2^(s-2)+1 ...} so the search has a closed form.
+CSC_HD u32 dist_slot(u32 d) { return d < 3 ? d : 2u + ilog2(d - 1); }
+
+CSC_HD u32 rev4(u32 v) { return ((v & 1) << 3) | ((v & 2) << 1) | ((v & 4) >> 1) | ((v & 8) >> 3); }
+
+struct Encoder {
+    const EncStream &S;
+    ModelSmall &M;
+    // range coder (csc_coder.h:44-50)
+    u64 low;
+    u32 range, cachesize, cache;
+    u32 bc_bits, bc_val;
+    u32 rc_n, rc_blk, bc_n, bc_blk, ev_n;
+    // model (csc_model.h)
+    u32 state, ctx, lp_rebuild;
+    // LZ (csc_lz.h:22)
+    u32 rep[4];
+    i32 err;
+    u32 tr_n;
+    u32 vld, W, K, good;
+
+    CSC_HD Encoder(const EncStream &s, ModelSmall &m) : S(s), M(m) {}
+
+    // ------------------------------------------------------------------ output
+    CSC_HD void event(u32 kind) {
+        if (ev_n < S.ev_cap) S.events[ev_n] = (u8)kind; else err = kErrOverflow;
+        ev_n++;
+    }
+    CSC_HD void put_rc(u32 b) {
+        if (rc_n < S.rc_cap) S.rc_out[rc_n] = (u8)b; else err = kErrOverflow;
+        rc_n++;
+        if (++rc_blk == S.cfg.csc_blocksize) { event(1); rc_blk = 0; }   // csc_coder.cpp:97-104
+    }
+    CSC_HD void put_bc(u32 b) {
+        if (bc_n < S.bc_cap) S.bc_out[bc_n] = (u8)b; else err = kErrOverflow;
+        bc_n++;
+        if (++bc_blk == S.cfg.csc_blocksize) { event(0); bc_blk = 0; }   // BCWCheckBound
+    }
+    CSC_HD void trace(u32 k, u32 a, u32 b) {
+        if (S.trace) {
+            if (tr_n < S.trace_cap) { S.trace[tr_n * 3] = k; S.trace[tr_n * 3 + 1] = a; S.trace[tr_n * 3 + 2] = b; }
+            tr_n++;
+        }
+    }
+
+    // ------------------------------------------------------------- range coder
+    CSC_HD void coder_reset() {
+        low = 0; range = 0xFFFFFFFFu; cachesize = 1; cache = 0;
+        bc_bits = 0; bc_val = 0; rc_blk = 0; bc_blk = 0;
+    }
+    CSC_HD void shift_low() {   // csc_coder.cpp:89-112
+        if ((u32)low < 0xFF000000u || (u32)(low >> 32) != 0) {
+            u32 t = cache;
+            u32 carry = (u32)(low >> 32);
+            do {
+                put_rc((t + carry) & 0xFF);
+                t = 0xFF;
+            } while (--cachesize != 0);
+            cache = ((u32)low >> 24) & 0xFF;
+        }
+        cachesize++;
+        low = (u64)((u32)low << 8);
+    }
+    CSC_HD void enc_bit(u16 &pr, u32 bit) {   // csc_coder.h:67-81
+        u32 p = pr;
+        u32 bound = (range >> 12) * p;
+        if (bit) { range = bound; p += (0xFFFu - p) >> 5; }
+        else { low += bound; range -= bound; p -= p >> 5; }
+        pr = (u16)p;
+        if (range < (1u << 24)) { range <<= 8; shift_low(); }
+    }
+    CSC_HD void direct16(u32 val, u32 len) {   // csc_coder.cpp:76-87
+        bc_val = (bc_val << len) | val;
+        bc_bits += len;
+        while (bc_bits >= 8) {
+            put_bc((bc_val >> (bc_bits - 8)) & 0xFF);
+            bc_bits -= 8;
+        }
+    }
+    CSC_HD void direct(u32 val, u32 len) {     // csc_coder.h:83-88
+        if (len <= 16) direct16(val, len);
+        else { direct16(val >> 16, len - 16); direct16(val & 0xFFFF, 16); }
+    }
+    CSC_HD void flush_segment(u32 seg, u32 rc0, u32 bc0, u32 ev0) {   // csc_coder.cpp:40-74
+        for (int i = 0; i < 5; i++) shift_low();
+        // one byte is skipped, not stored (H3): the host substitutes the stale ring byte
+        if (rc_n < S.rc_cap) S.rc_out[rc_n] = 0; else err = kErrOverflow;
+        rc_n++; rc_blk++;
+        put_bc((bc_val << (8 - bc_bits)) & 0xFF);
+        put_bc(0);
+        SegOut so;
+        so.rc_off = rc0; so.rc_len = rc_n - rc0;
+        so.bc_off = bc0; so.bc_len = bc_n - bc0;
+        so.ev_off = ev0; so.ev_len = ev_n - ev0;
+        S.segout[seg] = so;
+        coder_reset();
+    }
+
+    // ------------------------------------------------------------------- model
+    CSC_HD void model_reset() {   // csc_model.cpp:88-111
+        for (u32 i = CSC_LANE; i < 64 * 3; i += CSC_NLANES) { M.p_state[i] = 2048; M.p_repdist[i] = 2048; }
+        for (u32 i = CSC_LANE; i < 8 + 16 * 2 + 32 * 4; i += CSC_NLANES) M.p_dist[i] = 2048;
+        for (u32 i = CSC_LANE; i < 128; i += CSC_NLANES) M.p_matchlen_extra3[i] = 2048;
+        for (u32 i = CSC_LANE; i < 29 * 16; i += CSC_NLANES) M.p_matchdist_extra[i] = 2048;
+        for (u32 i = CSC_LANE; i < 8; i += CSC_NLANES) { M.p_matchlen_extra1[i] = 2048; M.p_matchlen_extra2[i] = 2048; }
+        if (CSC_LANE == 0) {
+            M.p_matchlen_slot[0] = M.p_matchlen_slot[1] = 2048;
+            M.p_longlen = 2048; M.p_rle_flag = 2048;
+        }
+        for (u32 i = CSC_LANE; i < 32; i += CSC_NLANES) M.len_price[i] = 0;
+        w_sync();
+        state = 0; ctx = 0; lp_rebuild = 0;
+    }
+
+    CSC_HD void lit_bits(u16 *row, u32 c) {
+        // the 8 tree nodes are known up front: load, code, store (csc_model.cpp:176-182)
+        u32 cc = c | 0x100;
+        u16 pv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) pv[k] = row[cc >> (8 - k)];
+#pragma unroll
+        for (int k = 0; k < 8; k++) enc_bit(pv[k], (cc >> (7 - k)) & 1);
+#pragma unroll
+        for (int k = 0; k < 8; k++) row[cc >> (8 - k)] = pv[k];
+    }
+    CSC_HD void encode_literal(u32 c) {   // csc_model.cpp:169-183
+        trace(0, c, 0);
+        enc_bit(M.p_state[state * 3 + 0], 0);
+        state = (state * 4) & 0x3F;
+        u16 *row = S.p_lit + ctx * 256;
+        ctx = c;
+        lit_bits(row, c);
+    }
+    CSC_HD void encode_matchlen_1(u32 len) {   // csc_model.cpp:113-145
+        if (len < 16) {
+            u16 *p;
+            if (len < 8) {
+                enc_bit(M.p_matchlen_slot[0], 0);
+                p = M.p_matchlen_extra1;
+            } else {
+                enc_bit(M.p_matchlen_slot[0], 1);
+                enc_bit(M.p_matchlen_slot[1], 0);
+                len -= 8;
+                p = M.p_matchlen_extra2;
+            }
+            u32 c = len | 8;
+            do { enc_bit(p[c >> 3], (c >> 2) & 1); c <<= 1; } while (c < 0x40);
+        } else {
+            enc_bit(M.p_matchlen_slot[0], 1);
+            enc_bit(M.p_matchlen_slot[1], 1);
+            u32 c = (len - 16) | 0x80;
+            do { enc_bit(M.p_matchlen_extra3[c >> 7], (c >> 6) & 1); c <<= 1; } while (c < 0x4000);
+        }
+    }
+    CSC_HD void encode_matchlen_2(u32 len) {   // csc_model.cpp:147-159
+        if (len >= 143) {
+            encode_matchlen_1(143);
+            len -= 143;
+            while (len >= 143) { len -= 143; enc_bit(M.p_longlen, 0); }
+            enc_bit(M.p_longlen, 1);
+        }
+        encode_matchlen_1(len);
+    }
+    CSC_HD void encode_rep0len1() {   // csc_model.cpp:198-207
+        trace(2, 0, 0);
+        enc_bit(M.p_state[state * 3 + 0], 1);
+        enc_bit(M.p_state[state * 3 + 1], 0);
+        enc_bit(M.p_state[state * 3 + 2], 0);
+        ctx = 0;
+        state = (state * 4 + 2) & 0x3F;
+    }
+    CSC_HD void encode_rep(u32 idx, u32 lencode) {   // csc_model.cpp:218-232
+        trace(3, lencode, idx);
+        enc_bit(M.p_state[state * 3 + 0], 1);
+        enc_bit(M.p_state[state * 3 + 1], 0);
+        enc_bit(M.p_state[state * 3 + 2], 1);
+        u32 b1 = (idx >> 1) & 1, b0 = idx & 1;
+        enc_bit(M.p_repdist[state * 3 + 0], b1);
+        enc_bit(M.p_repdist[state * 3 + 1 + b1], b0);
+        encode_matchlen_2(lencode);
+        state = (state * 4 + 3) & 0x3F;
+    }
+    CSC_HD void encode_match(u32 dist, u32 lencode) {   // csc_model.cpp:301-366
+        trace(1, lencode, dist);
+        enc_bit(M.p_state[state * 3 + 0], 1);
+        enc_bit(M.p_state[state * 3 + 1], 1);
+        encode_matchlen_2(lencode);
+        u32 base, sbits;
+        if (lencode == 0) { base = 0; sbits = 3; }
+        else if (lencode <= 2) { base = 16 * (lencode - 1) + 8; sbits = 4; }
+        else if (lencode <= 5) { base = 32 * (lencode - 3) + 8 + 32; sbits = 5; }
+        else { base = 32 * 3 + 8 + 32; sbits = 5; }
+        u32 slot = dist_slot(dist);
+        u16 *p = M.p_dist + base;
+        u32 c = slot | (1u << sbits);
+        do { enc_bit(p[c >> sbits], (c >> (sbits - 1)) & 1); c <<= 1; } while (c < (1u << (sbits * 2)));
+        if (slot > 2) {
+            u32 ebits = slot - 2;
+            u32 elen = dist - (1u << ebits) - 1;
+            if (ebits > 4) direct(elen >> 4, ebits - 4);
+            c = rev4(elen & 0x0F) | 0x10;
+            p = M.p_matchdist_extra + (ebits - 1) * 16;
+            do { enc_bit(p[c >> 4], (c >> 3) & 1); c <<= 1; } while (c < 0x100);
+        }
+        state = (state * 4 + 1) & 0x3F;
+    }
+    CSC_HD void encode_int(u32 num) {   // csc_model.cpp:389-414
+        u32 slot = num ? ilog2(num) : 0;
+        direct(slot, 5);
+        if (slot == 0) direct(num, 1);
+        else direct(num - (1u << slot), slot);
+    }
+
+    // ------------------------------------------------------------------ prices
+    CSC_HD u32 bitprice(u32 p, u32 bit) const { return M.p2bits[(bit ? p : 4096u - p) >> 3]; }
+    CSC_HD u32 literal_price(u32 fstate, u32 fctx, u32 c) const {   // csc_model.cpp:185-196
+        u32 r = bitprice(M.p_state[fstate * 3], 0);
+        const u16 *row = S.p_lit + fctx * 256;
+        u32 cc = c | 0x100;
+#pragma unroll
+        for (int k = 0; k < 8; k++) r += bitprice(row[cc >> (8 - k)], (cc >> (7 - k)) & 1);
+        return r;
+    }
+    CSC_HD u32 rep0len1_price(u32 fs) const {   // csc_model.cpp:209-216
+        return bitprice(M.p_state[fs * 3], 1) + bitprice(M.p_state[fs * 3 + 1], 0) + bitprice(M.p_state[fs * 3 + 2], 0);
+    }
+    CSC_HD u32 repdist_price(u32 fs, u32 idx) const {   // csc_model.cpp:273-284
+        u32 r = bitprice(M.p_state[fs * 3], 1) + bitprice(M.p_state[fs * 3 + 1], 0) + bitprice(M.p_state[fs * 3 + 2], 1);
+        u32 b1 = (idx >> 1) & 1, b0 = idx & 1;
+        r += bitprice(M.p_repdist[fs * 3 + 0], b1);
+        r += bitprice(M.p_repdist[fs * 3 + 1 + b1], b0);
+        return r;
+    }
+    CSC_HD u32 matchdist_price(u32 fs, u32 dist) const {   // csc_model.cpp:368-387
+        u32 r = bitprice(M.p_state[fs * 3], 1) + bitprice(M.p_state[fs * 3 + 1], 1);
+        u32 s = dist_slot(dist);
+        return r + (s > 2 ? s + 2 : 2) * 128;
+    }
+    CSC_HD u32 len_price_one(u32 len) const {   // body of len_price_rebuild, csc_model.cpp:234-270
+        u32 r = 0;
+        if (len < 16) {
+            const u16 *p;
+            if (len < 8) { r += bitprice(M.p_matchlen_slot[0], 0); p = M.p_matchlen_extra1; }
+            else { r += bitprice(M.p_matchlen_slot[0], 1) + bitprice(M.p_matchlen_slot[1], 0); len -= 8; p = M.p_matchlen_extra2; }
+            u32 c = len | 8;
+            do { r += bitprice(p[c >> 3], (c >> 2) & 1); c <<= 1; } while (c < 0x40);
+        } else {
+            r += bitprice(M.p_matchlen_slot[0], 1) + bitprice(M.p_matchlen_slot[1], 1);
+            u32 c = (len - 16) | 0x80;
+            do { r += bitprice(M.p_matchlen_extra3[c >> 7], (c >> 6) & 1); c <<= 1; } while (c < 0x4000);
+        }
+        return r;
+    }
+    CSC_HD u32 matchlen_price(u32 lencode) {   // csc_model.cpp:286-299
+        if (lencode >= 32) return 128 * 6;
+        if (lp_rebuild-- == 0) {
+            w_sync();
+            for (u32 i = CSC_LANE; i < 32; i += CSC_NLANES) M.len_price[i] = len_price_one(i);
+            w_sync();
+            lp_rebuild = 4096;
+        }
+        return M.len_price[lencode];
+    }
+
+    // ----------------------------------------------------- match finder (state)
+    CSC_HD u32 hash2_at(u32 x, u32 sb_end) const {   // HASH2, csc_mf.cpp:23-28; unwritten window bytes are 0
+        u32 b0 = S.lz[x], b1 = (x + 1 < sb_end) ? S.lz[x + 1] : 0;
+        return ((b0 | (b1 << 8)) * 65521u) & 0x3FFF;
+    }
+    CSC_HD u32 hash3_at(u32 x, u32 sb_end) const {   // HASH3, csc_mf.cpp:30-33
+        u32 b0 = S.lz[x], b1 = (x + 1 < sb_end) ? S.lz[x + 1] : 0, b2 = (x + 2 < sb_end) ? S.lz[x + 2] : 0;
+        return (b0 << 8) ^ (b1 << 5) ^ b2;
+    }
+    CSC_HD bool dead6(u32 e) const { return bit_get(S.D6, e); }
+    CSC_HD void kill6(u32 e) { g_or(&S.D6[e >> 5], 1u << (e & 31)); }
+
+    // newest position < bound on the 6-byte chain of x that is still in the table
+    // (= slot 0 of the reference bucket at the time the window ended at `bound`)
+    CSC_HD u32 newest_alive6(u32 x, u32 bound) const {
+        u32 src = x, k = 0;
+        for (;;) {
+            u32 e = S.P6[(size_t)src * K + k];
+            if (e == kNone) return kNone;
+            if (++k == K) { src = e; k = 0; }
+            if (e >= bound) continue;
+            if (!dead6(e)) return e;
+        }
+    }
+
+    // find_match (csc_mf.cpp:243-495): candidate list in reference probe order.
+    CSC_HD u32 find_match(u32 x, u32 limit, const u32 *rp, Cand *out) {
+        const u8 *cur = S.lz + x;
+        const u32 pos = vld + x;
+        const u32 sb_end = x + limit;
+        u32 cnt = 0, minlen = 1, dist = 0;
+        // bound[] of csc_mf.cpp:245
+        // rep-distance probes (:266-299)
+        for (u32 i = 0; i < 4; i++) {
+            u32 rd = rp[i];
+            if (rd >= vld) continue;
+            if (minlen >= limit) continue;
+            const u8 *m = cur - rd;
+            if (m[minlen] != cur[minlen]) continue;
+            u32 ml = lcp_bytes(cur, m, limit);
+            if (ml && i == 0) { out[cnt].len = 1; out[cnt].dist = 1; cnt++; }
+            if (ml > minlen) {
+                minlen = ml;
+                out[cnt].len = ml; out[cnt].dist = 1 + i; cnt++;
+                if (ml >= good) { dist = 0xFFFFFFFFu; break; }
+            }
+        }
+        // 2-byte and 3-byte single-slot tables (:303-366)
+        u32 h2 = hash2_at(x, sb_end), h3 = hash3_at(x, sb_end);
+        u32 e2 = g_ld(&S.ht2[h2]), e3 = g_ld(&S.ht3[h3]);
+        if (pos - e2 > dist) {
+            dist = pos - e2;
+            // note `wpos > dist` (:306): a candidate at window offset 0 is dropped, dist stays poisoned
+            if (dist < vld && x > dist && minlen < limit) {
+                const u8 *m = cur - dist;
+                if (m[minlen] == cur[minlen]) {
+                    u32 ml = lcp_bytes(cur, m, limit);
+                    if (ml > minlen) {
+                        minlen = ml;
+                        if (!(ml <= 6 && dist >= mf_bound(ml))) {
+                            out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
+                            if (ml >= good) dist = 0xFFFFFFFFu;
+                        }
+                    }
+                }
+            }
+        }
+        if (pos - e3 > dist) {
+            dist = pos - e3;
+            if (dist < vld && x >= dist && minlen < limit) {
+                const u8 *m = cur - dist;
+                if (m[minlen] == cur[minlen]) {
+                    u32 ml = lcp_bytes(cur, m, limit);
+                    if (ml > minlen) {
+                        minlen = ml;
+                        if (!(ml <= 6 && dist >= mf_bound(ml))) {
+                            out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
+                            if (ml >= good) dist = 0xFFFFFFFFu;
+                        }
+                    }
+                }
+            }
+        }
+        S.ht2[h2] = pos;
+        S.ht3[h3] = pos;
+        // 6-byte table of width W (:453-485): first W live entries of the chain
+        if (W) {
+            u32 found = 0, src = x, k = 0;
+            while (found < W) {
+                size_t at = (size_t)src * K + k;
+                u32 e = S.P6[at];
+                if (e == kNone) break;
+                bool inrow = (src == x);
+                if (++k == K) { src = e; k = 0; }
+                if (dead6(e)) continue;
+                found++;
+                u32 d = x - e;
+                if (d <= dist) continue;
+                dist = d;
+                if (dist >= vld) continue;
+                if (minlen >= limit) continue;
+                u32 ml;
+                if (inrow) {
+                    ml = S.L6[at];
+                } else {
+                    const u8 *m = cur - dist;
+                    if (m[minlen] != cur[minlen]) continue;
+                    ml = lcp_bytes(cur, m, limit);
+                }
+                if (ml > minlen) {
+                    minlen = ml;
+                    if (ml <= 6 && dist >= mf_bound(ml)) continue;
+                    out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
+                    if (ml >= good) { dist = 0xFFFFFFFFu; break; }
+                }
+            }
+        }
+        // x itself is now the newest entry everywhere (alive by default)
+        return cnt;
+    }
+    CSC_HD static u32 mf_bound(u32 len) {   // bound[] csc_mf.cpp:245
+        return len < 2 ? 0u : len == 2 ? 64u : len == 3 ? 1024u : len == 4 ? 16u * 1024 : len == 5 ? 256u * 1024 : 4u * 1024 * 1024;
+    }
+
+    CSC_HD static bool second_better(Cand u1, Cand u2) {   // csc_mf.cpp:570-582 (== fold of :497-524)
+        if (u2.len <= 1) return false;
+        if (u2.len > u1.len + 3) return true;
+        if (u2.len > u1.len && u2.dist <= 4) return true;
+        if (u2.len + 2 > u1.len && u2.dist <= 4 && u1.dist > 4) return true;
+        if (u2.len >= u1.len && (u2.dist >> (4 * (u2.len - u1.len))) <= u1.dist) return true;
+        if (u2.len < u1.len && u2.len + 2 >= u1.len && u1.dist > 4 && (u1.dist >> (4 * (u1.len - u2.len))) > u2.dist) return true;
+        return false;
+    }
+    CSC_HD Cand find_best(u32 x, u32 limit) {   // FindMatch, csc_mf.cpp:497-524
+        Cand c[kMaxCand];
+        u32 n = find_match(x, limit, rep, c);
+        Cand best; best.len = 1; best.dist = 0;
+        for (u32 i = 0; i < n; i++) {
+            if (i == 0) { best = c[0]; continue; }
+            if (second_better(best, c[i])) best = c[i];
+        }
+        return best;
+    }
+
+    // SlidePos (csc_mf.cpp:134-206): positions s+1 .. s+len-1 are passed over by a match.
+    CSC_HD void slide(u32 s, u32 len, u32 sb_end) {
+        if (len <= 1) return;
+        u32 i0 = 1;
+        while (i0 + 128 < len) i0 += 4;
+        for (u32 i = 1 + 4 * CSC_LANE; i < i0; i += 4 * CSC_NLANES) {
+            u32 q = s + i;
+            g_max(&S.ht2[hash2_at(q, sb_end)], vld + q);
+            g_max(&S.ht3[hash3_at(q, sb_end)], vld + q);
+        }
+        for (u32 i = i0 + CSC_LANE; i < len; i += CSC_NLANES) {
+            u32 q = s + i;
+            g_max(&S.ht2[hash2_at(q, sb_end)], vld + q);
+            g_max(&S.ht3[hash3_at(q, sb_end)], vld + q);
+        }
+        w_sync();
+        if (W) {
+            bits_set_range(S.D6, s + 1, s + i0);          // never inserted (:145)
+            u32 first = s + i0;
+            if (i0 < len && bit_get_ro(S.Z6, first)) {    // h6 == lasth6 (== 0): slot 0 overwritten (:147-156)
+                u32 e = newest_alive6(first, first);
+                if (e != kNone) kill6(e);
+            }
+            for (u32 i = i0 + 1 + CSC_LANE; i < len; i += CSC_NLANES) {
+                u32 q = s + i;
+                if (S.P6[(size_t)q * K] == q - 1) kill6(q - 1);   // same hash as the previous slid position
+            }
+            w_sync();
+        }
+    }
+
+    // ------------------------------------------------------------- lazy parser
+    CSC_HD void encode_nonlit(Cand u) {   // csc_lz.cpp:127-154
+        if (u.dist <= 4) {
+            if (u.len == 1 && u.dist == 1) { encode_rep0len1(); return; }
+            encode_rep(u.dist - 1, u.len - 2);
+            u32 d = rep[u.dist - 1];
+            for (u32 j = u.dist - 1; j > 0; j--) rep[j] = rep[j - 1];
+            rep[0] = d;
+        } else {
+            encode_match(u.dist - 5, u.len - 2);
+            rep[3] = rep[2]; rep[2] = rep[1]; rep[1] = rep[0];
+            rep[0] = u.dist - 4;
+        }
+    }
+    CSC_HD void parse_lazy(u32 x0, u32 size) {   // compress_normal(size, true), csc_lz.cpp:156-199
+        const u32 end = x0 + size;
+        u32 x = x0;
+        Cand u1, u2;
+        u1.len = 1; u1.dist = 0;
+        bool got = false;
+        while (x < end) {
+            if (!got) u1 = find_best(x, end - x);
+            if (u1.len == 1 || u1.len >= good) {
+                if (u1.dist == 0) encode_literal(S.lz[x]);
+                else encode_nonlit(u1);
+                slide(x, u1.len, end);
+                x += u1.len;
+                if (u1.dist) ctx = S.lz[x - 1];
+                got = false;
+                continue;
+            }
+            u2 = find_best(x + 1, end - x - 1);
+            if (second_better(u1, u2)) {
+                encode_literal(S.lz[x]);
+                x++;
+                u1 = u2;
+                got = true;
+            } else {
+                encode_nonlit(u1);
+                slide(x + 1, u1.len - 1, end);
+                x += u1.len;
+                ctx = S.lz[x - 1];
+                got = false;
+            }
+        }
+    }
+
+    // ---------------------------------------------------------- optimal parser
+    // FindMatchWithPrice (csc_mf.cpp:584-625): t[0] longest candidate, t[1] rep0len1,
+    // t[2..] price per length.
+    CSC_HD void find_match_price(u32 x, u32 limit, u32 fstate, const u32 *rp, Cand *t) {
+        Cand c[kMaxCand];
+        u32 n = find_match(x, limit, rp, c);
+        if (n == 0) { t[0].len = 1; t[0].dist = 0; }
+        else t[0] = c[n - 1];
+        if (t[0].len >= good) return;
+        t[1].dist = 0;
+        u32 lpos = 1;
+        for (u32 i = 0; i < n; i++) {
+            u32 dprice, rdist;
+            if (c[i].len == 1 && c[i].dist == 1) {
+                t[1].len = rep0len1_price(fstate);
+                t[1].dist = 1;
+                continue;
+            } else if (c[i].dist <= 4) {
+                dprice = repdist_price(fstate, c[i].dist - 1);
+                rdist = 0;
+            } else {
+                dprice = matchdist_price(fstate, c[i].dist - 5);
+                rdist = c[i].dist - 4;
+            }
+            while (lpos < c[i].len) {
+                lpos++;
+                if (lpos <= 6 && rdist >= mf_bound(lpos)) { t[lpos].dist = 0; continue; }
+                t[lpos].dist = c[i].dist;
+                t[lpos].len = dprice + matchlen_price(lpos - 2);   // .len doubles as price (MFUnit union)
+            }
+        }
+    }
+
+    CSC_HD void ap_backward(u32 endi) {   // csc_lz.cpp:335-362
+        ApUnit *ap = S.ap;
+        for (u32 i = endi; i;) {
+            u32 b = ap[i].back_pos;
+            ap[b].next_pos = (u16)i;
+            i = b;
+        }
+        for (u32 i = 0; i != endi;) {
+            u32 nx = ap[i].next_pos;
+            u32 d = ap[nx].dist;
+            if (d == 0) {
+                encode_literal(ap[i].lit);
+            } else if (d <= 4) {
+                if (nx - i == 1 && d == 1) encode_rep0len1();
+                else encode_rep(d - 1, nx - i - 2);
+                ctx = ap[nx - 1].lit;
+            } else {
+                encode_match(d - 5, nx - i - 2);
+                ctx = ap[nx - 1].lit;
+            }
+            i = nx;
+        }
+        for (int j = 0; j < 4; j++) rep[j] = ap[endi].rep[j];
+    }
+
+    CSC_HD void parse_optimal(u32 x0, u32 size) {   // compress_advanced, csc_lz.cpp:207-333
+        const u32 end = x0 + size;
+        ApUnit *ap = S.ap;
+        Cand t[64];
+        u32 x = x0;          // wnd_curpos_
+        u32 i = 0;           // bytes of the sub-block already emitted
+        while (i < size) {
+            find_match_price(x, end - x, state, rep, t);
+            if (t[0].dist == 0) {
+                encode_literal(S.lz[x]);
+                i++; x++;
+                continue;
+            }
+            u32 apcur = 0, apend = 1;
+            ap[0].price = 0;
+            ap[0].back_pos = 0;
+            for (int j = 0; j < 4; j++) ap[0].rep[j] = rep[j];
+            ap[0].state = (u8)state;
+            const u32 aplimit = (size - i) < kApLimit ? (size - i) : kApLimit;
+            for (;;) {
+                ap[apcur].lit = S.lz[x];
+                if (apcur) {
+                    u32 l = ap[apcur].back_pos;
+                    u32 r0 = ap[l].rep[0], r1 = ap[l].rep[1], r2 = ap[l].rep[2], r3 = ap[l].rep[3];
+                    u32 ls = ap[l].state, d = ap[apcur].dist, ns;
+                    if (d == 0) {
+                        ns = (ls * 4) & 0x3F;
+                    } else if (d <= 4) {
+                        u32 len = apcur - l;
+                        if (len == 1 && d == 1) {
+                            ns = (ls * 4 + 2) & 0x3F;
+                        } else {
+                            ns = (ls * 4 + 3) & 0x3F;
+                            // note (csc_lz.cpp:246-256): case 2 also performs the
+                            // rep[0] assignment; idx 0 leaves the queue untouched
+                            u32 r[4] = {r0, r1, r2, r3};
+                            u32 tmp = r[d - 1];
+                            if (d == 4) { r[3] = r[2]; r[2] = r[1]; r[1] = r[0]; r[0] = tmp; }
+                            else if (d == 3) { r[2] = r[1]; r[1] = r[0]; r[0] = tmp; }
+                            else if (d == 2) { r[1] = r[0]; r[0] = tmp; }
+                            r0 = r[0]; r1 = r[1]; r2 = r[2]; r3 = r[3];
+                        }
+                    } else {
+                        ns = (ls * 4 + 1) & 0x3F;
+                        r3 = r2; r2 = r1; r1 = r0; r0 = d - 4;
+                    }
+                    ap[apcur].state = (u8)ns;
+                    ap[apcur].rep[0] = r0; ap[apcur].rep[1] = r1; ap[apcur].rep[2] = r2; ap[apcur].rep[3] = r3;
+                    if (apcur < aplimit) {
+                        u32 rr[4] = {r0, r1, r2, r3};
+                        find_match_price(x, end - x, ns, rr, t);
+                    }
+                }
+                if (apcur == aplimit) {
+                    ap_backward(apcur);
+                    i += apcur;
+                    break;
+                }
+                if (t[0].len == 1 && apcur + 1 == apend) {
+                    ap_backward(apcur);
+                    encode_literal(ap[apcur].lit);
+                    i += apcur;
+                    x++; i++;
+                    break;
+                }
+                if (apcur + 1 >= apend) ap[apend++].price = 0xFFFFFFFFu;
+                if (t[0].len >= good || (t[0].len > 1 && t[0].len + apcur >= aplimit)) {
+                    ap_backward(apcur);
+                    i += apcur;
+                    encode_nonlit(t[0]);
+                    slide(x, t[0].len, end);
+                    i += t[0].len;
+                    x += t[0].len;
+                    ctx = S.lz[x - 1];
+                    break;
+                }
+                u32 base = ap[apcur].price;
+                u32 lit_ctx = x ? S.lz[x - 1] : 0;
+                u32 cprice = literal_price(ap[apcur].state, lit_ctx, S.lz[x]);
+                if (cprice + base < ap[apcur + 1].price) {
+                    ap[apcur + 1].dist = 0;
+                    ap[apcur + 1].back_pos = (u16)apcur;
+                    ap[apcur + 1].price = cprice + base;
+                }
+                if (t[1].dist && t[1].len + base < ap[apcur + 1].price) {
+                    ap[apcur + 1].dist = 1;
+                    ap[apcur + 1].back_pos = (u16)apcur;
+                    ap[apcur + 1].price = t[1].len + base;
+                }
+                u32 len = t[0].len;
+                while (apcur + len >= apend) ap[apend++].price = 0xFFFFFFFFu;
+                while (len > 1) {
+                    if (t[len].dist && t[len].len + base < ap[apcur + len].price) {
+                        ap[apcur + len].dist = t[len].dist;
+                        ap[apcur + len].back_pos = (u16)apcur;
+                        ap[apcur + len].price = t[len].len + base;
+                    }
+                    len--;
+                }
+                apcur++;
+                x++;
+            }
+        }
+    }
+
+    // ------------------------------------------------------------ run encoders
+    CSC_HD void lz_run(u32 a, u32 size) {   // LZ::EncodeNormal mode 2/3, csc_lz.cpp:61-100
+        for (u32 off = 0; off < size;) {
+            u32 sb = size - off;
+            if (sb > kBlock) sb = kBlock;
+            if (S.cfg.lz_mode == 3) parse_optimal(a + off, sb);
+            else parse_lazy(a + off, sb);
+            off += sb;
+            if (err) return;
+        }
+        encode_match(64, 0);   // end marker (:95-98)
+    }
+    CSC_HD void skip_run(u32 a, u32 size) {   // mode 5: SlidePosFast (csc_mf.cpp:208-241)
+        if (W) bits_or_not_range(S.D6, S.Z2, a, a + size);
+    }
+    CSC_HD void bad_run(u32 a, u32 size) {   // CompressBad, csc_model.cpp:463-469
+        encode_int(size);
+        for (u32 i = 0; i < size; i++) direct16(S.lz[a + i], 8);
+    }
+    CSC_HD void entropy_run(u32 a, u32 size) {   // CompressLiterals, csc_model.cpp:448-461
+        encode_int(size);
+        for (u32 i = 0; i < size; i++) {
+            u32 c = S.lz[a + i];
+            u16 *row = S.p_lit + ctx * 256;
+            ctx = c;
+            lit_bits(row, c);
+        }
+    }
+    // byte k of Forward_Delta's output (csc_filters.cpp:132-164) without materialising it
+    CSC_HD u32 delta_byte(u32 a, u32 size, u32 chn, u32 k) const {
+        if (size < 512) return S.lz[a + k];
+        // channel c holds ceil((size - c)/chn) bytes
+        u32 base = size / chn, rem = size % chn;
+        u32 c, idx;
+        u32 big = (base + 1) * rem;           // bytes in the first `rem` channels
+        if (k < big) { c = k / (base + 1); idx = k % (base + 1); }
+        else { c = rem + (k - big) / base; idx = (k - big) % base; }
+        u32 j = c + idx * chn;
+        u32 prev;
+        if (idx) prev = S.lz[a + j - chn];
+        else if (c == 0) prev = 0;
+        else {   // last byte of channel c-1
+            u32 cnt = base + ((c - 1) < rem ? 1 : 0);
+            prev = S.lz[a + (c - 1) + (cnt - 1) * chn];
+        }
+        return (S.lz[a + j] - prev) & 0xFF;
+    }
+    CSC_HD void delta_run(u32 a, u32 size, u32 chn) {   // Forward_Delta + CompressRLE, csc_model.cpp:471-513
+        encode_int(size);
+        u32 sctx = 0;
+        u32 pm1 = 0;   // src[i-1]
+        for (u32 i = 0; i < size;) {
+            u32 c0 = delta_byte(a, size, chn, i);
+            if (i > 0 && size - i > 3 && pm1 == c0 && c0 == delta_byte(a, size, chn, i + 1) &&
+                c0 == delta_byte(a, size, chn, i + 2)) {
+                u32 j = i + 3, len = 3;
+                while (j < size && delta_byte(a, size, chn, j) == c0) { len++; j++; }
+                if (len > 10) {
+                    sctx = c0;
+                    enc_bit(M.p_rle_flag, 1);
+                    encode_matchlen_2(len - 11);
+                    i = j;
+                    pm1 = c0;
+                    continue;
+                }
+            }
+            enc_bit(M.p_rle_flag, 0);
+            lit_bits(S.p_delta + sctx * 256, c0);
+            sctx = c0;
+            pm1 = c0;
+            i++;
+        }
+    }
+
+    // IsDuplicateBlock / TestFind (csc_lz.cpp:102-112, csc_mf.cpp:526-568): window ends at run_start
+    CSC_HD bool dup_block(u32 b0, u32 bsize, u32 run_start) {
+        if (!W) return false;   // -m5 head table: handled by the bounded search path
+        bool hit = false;
+        for (u32 base = 0; base + 18 < bsize && !hit; base += CSC_NLANES) {
+            u32 off = base + CSC_LANE;
+            bool mine = false;
+            if (off + 18 < bsize) {
+                u32 p = b0 + off;
+                if (bit_get_ro(S.Z2, p)) {
+                    u32 e = newest_alive6(p, run_start);
+                    if (e != kNone && run_start - e < vld) {
+                        u32 limit = bsize - off, k = 0;
+                        const u8 *a = S.lz + p, *m = S.lz + e;
+                        u32 valid = run_start - e;   // bytes beyond are unwritten (zero) window
+                        while (k < limit) {
+                            u8 mv = k < valid ? m[k] : (u8)0;
+                            if (a[k] != mv) break;
+                            k++;
+                            if (k > 18) break;
+                        }
+                        mine = k > 18;
+                    }
+                }
+            }
+            hit = w_any(mine);
+        }
+        return hit;
+    }
+
+    CSC_HD void compress_run(u32 a, u32 size, u32 type, u32 first_blk) {   // compress_block, csc_encoder_main.cpp:35-83
+        if (!size) return;
+        if (type == DT_NORMAL || type == DT_FAST) {
+            encode_int(DT_NORMAL);
+            lz_run(a, size);
+        } else if (type == DT_EXE) {
+            encode_int(DT_EXE);
+            lz_run(a, size);
+        } else if (type == DT_ENGTXT) {
+            if (S.dict_ok[first_blk]) { encode_int(DT_ENGTXT); encode_int(size); }
+            else encode_int(DT_NORMAL);
+            lz_run(a, size);
+        } else if (type == DT_BAD) {
+            encode_int(DT_BAD);
+            skip_run(a, size);
+            bad_run(a, size);
+        } else if (type == DT_ENTROPY) {
+            encode_int(DT_ENTROPY);
+            skip_run(a, size);
+            entropy_run(a, size);
+        } else {
+            encode_int(type);
+            skip_run(a, size);
+            delta_run(a, size, dlt_channels(type - DT_DLT));
+        }
+    }
+
+    // one Compress() call (csc_encoder_main.cpp:85-146)
+    CSC_HD void compress_segment(u32 seg, u32 a, u32 size) {
+        const u32 rc0 = rc_n, bc0 = bc_n, ev0 = ev_n;
+        const bool use_filters = (S.cfg.flt_dlt + S.cfg.flt_txt + S.cfg.flt_exe) != 0;
+        u32 last_type = DT_NORMAL, last_begin = 0, last_size = 0;
+        u32 bpb = 0;
+        u32 blk = S.seg_blk0[seg];
+        u32 last_blk = blk;
+        for (u32 i = 0; i < size; blk++) {
+            u32 cur = size - i < kBlock ? size - i : kBlock;
+            u32 t = DT_NORMAL;
+            bool inherited = false;
+            if (use_filters) {
+                t = S.binfo[blk] & 0xFF;
+                if (t != DT_SKIP) bpb = S.bbpb[blk];
+            }
+            if (t == DT_SKIP) { t = last_type; inherited = true; }
+            if (t != DT_NORMAL) {
+                if (t == DT_EXE && !S.cfg.flt_exe) t = DT_NORMAL;
+                else if (t == DT_ENGTXT && !S.cfg.flt_txt) t = DT_NORMAL;
+                else if (t >= DT_DLT && !S.cfg.flt_dlt) t = DT_NORMAL;
+            }
+            if (t >= DT_DLT) {   // GetDltBpb(...) >= bpb * 0.95 (csc_encoder_main.cpp:118-121)
+                bool fail;
+                if (inherited) fail = (double)S.tail_dlt[seg * 5 + (t - DT_DLT)] >= (double)bpb * 0.95;
+                else fail = ((S.binfo[blk] >> 8) & 1) != 0;
+                if (fail) t = DT_NORMAL;
+            }
+            if (t >= DT_NO_LZ) {
+                if (dup_block(a + i, cur, a + last_begin)) t = DT_NORMAL;
+            }
+            if (last_type != t) {   // (size limit of :128 cannot trigger inside one Read())
+                if (last_size) {
+                    compress_run(a + last_begin, last_size, last_type, last_blk);
+                    encode_int(0);
+                }
+                last_begin = i;
+                last_size = 0;
+                last_blk = blk;
+            }
+            last_type = t;
+            last_size += cur;
+            i += cur;
+            if (err) return;
+        }
+        if (last_size) {
+            compress_run(a + last_begin, last_size, last_type, last_blk);
+            encode_int(1);
+            flush_segment(seg, rc0, bc0, ev0);
+        }
+    }
+
+    CSC_HD void run() {
+        vld = S.cfg.vld_rge; W = S.cfg.ht_width; K = S.K; good = S.cfg.good_len;
+        err = 0; tr_n = 0;
+        rc_n = bc_n = ev_n = 0;
+        coder_reset();
+        model_reset();
+        rep[0] = rep[1] = rep[2] = rep[3] = S.cfg.wnd_size;   // csc_lz.cpp:46-49
+        u32 a = 0;
+        for (u32 s = 0; s < S.nseg && !err; s++) {
+            compress_segment(s, a, S.seg_size[s]);
+            a += S.seg_size[s];
+        }
+        if (CSC_LANE == 0) {
+            *S.status = err;
+            if (S.trace_n) *S.trace_n = tr_n;
+        }
+    }
+};
+
+}  // namespace cscb

@@ -1,0 +1,99 @@
+// warp.h -- the few warp-level primitives the per-stream engines are written in.
+//
+// The serial part of libcsc (parser + adaptive coder) runs ONE
+// STREAM PER WARP.  The engine code is warp-uniform: all 32 lanes execute the
+// same scalar control flow on the same values (so no shuffles are needed to
+// broadcast state), and the lanes fan out only inside these primitives:
+// cooperative byte compares, lane-strided loops over bitmaps / positions, and
+// ballots.  For host-side simulation in tests (tests/hostsim) the same code is
+// compiled with a single lane.
+#pragma once
+#include "csc_defs.h"
+
+namespace cscb {
+
+#if defined(__CUDA_ARCH__)
+#define CSC_LANE (threadIdx.x & 31u)
+#define CSC_NLANES 32u
+CSC_HD void w_sync() { __syncwarp(); }
+CSC_HD bool w_any(bool p) { return __any_sync(0xFFFFFFFFu, p); }
+CSC_HD u32 w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+CSC_HD u32 w_min(u32 v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+CSC_HD u32 w_add(u32 v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
+CSC_HD void g_or(u32 *p, u32 m) { atomicOr(p, m); }
+CSC_HD void g_max(u32 *p, u32 v) { atomicMax(p, v); }
+CSC_HD u32 g_ld(const u32 *p) { return __ldcg(p); }   // L2-coherent read of lane-written data
+CSC_HD u32 ffs32(u32 m) { return (u32)__ffs((int)m); }
+#else
+#define CSC_LANE 0u
+#define CSC_NLANES 1u
+CSC_HD void w_sync() {}
+CSC_HD bool w_any(bool p) { return p; }
+CSC_HD u32 w_ballot(bool p) { return p ? 1u : 0u; }
+CSC_HD u32 w_min(u32 v) { return v; }
+CSC_HD u32 w_add(u32 v) { return v; }
+CSC_HD void g_or(u32 *p, u32 m) { *p |= m; }
+CSC_HD void g_max(u32 *p, u32 v) { if (v > *p) *p = v; }
+CSC_HD u32 g_ld(const u32 *p) { return *p; }
+CSC_HD u32 ffs32(u32 m) { return (u32)__builtin_ffs((int)m); }
+#endif
+
+// Longest common prefix of a[0..limit) and b[0..limit): the byte-compare loop of
+// every probe in find_match (csc_mf.cpp:279,317,348,470), done 32 bytes per
+// step by the warp.
+CSC_HD u32 lcp_bytes(const u8 *a, const u8 *b, u32 limit) {
+    for (u32 k = 0; k < limit; k += CSC_NLANES) {
+        u32 i = k + CSC_LANE;
+        bool mis = (i >= limit) || (a[i] != b[i]);
+        u32 m = w_ballot(mis);
+        if (m) return k + ffs32(m) - 1;
+    }
+    return limit;
+}
+
+// same, but bytes of b at or beyond b_valid read as zero (window area that has
+// not been written yet, csc_lz.cpp:50,67)
+CSC_HD u32 lcp_bytes_zpad(const u8 *a, const u8 *b, u32 limit, u32 b_valid) {
+    for (u32 k = 0; k < limit; k += CSC_NLANES) {
+        u32 i = k + CSC_LANE;
+        bool mis = true;
+        if (i < limit) {
+            u8 bv = (i < b_valid) ? b[i] : (u8)0;
+            mis = (a[i] != bv);
+        }
+        u32 m = w_ballot(mis);
+        if (m) return k + ffs32(m) - 1;
+    }
+    return limit;
+}
+
+CSC_HD bool bit_get(const u32 *map, u32 i) { return (g_ld(&map[i >> 5]) >> (i & 31)) & 1u; }
+CSC_HD bool bit_get_ro(const u32 *map, u32 i) { return (map[i >> 5] >> (i & 31)) & 1u; }
+
+// set bits [a, b) of a bitmap (lane-strided over words)
+CSC_HD void bits_set_range(u32 *map, u32 a, u32 b) {
+    if (a >= b) return;
+    u32 w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (u32 w = w0 + CSC_LANE; w <= w1; w += CSC_NLANES) {
+        u32 m = 0xFFFFFFFFu;
+        if (w == w0) m &= 0xFFFFFFFFu << (a & 31);
+        if (w == w1) m &= 0xFFFFFFFFu >> (31 - ((b - 1) & 31));
+        g_or(&map[w], m);
+    }
+    w_sync();
+}
+
+// dst[a,b) |= ~src[a,b)
+CSC_HD void bits_or_not_range(u32 *dst, const u32 *src, u32 a, u32 b) {
+    if (a >= b) return;
+    u32 w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (u32 w = w0 + CSC_LANE; w <= w1; w += CSC_NLANES) {
+        u32 m = 0xFFFFFFFFu;
+        if (w == w0) m &= 0xFFFFFFFFu << (a & 31);
+        if (w == w1) m &= 0xFFFFFFFFu >> (31 - ((b - 1) & 31));
+        g_or(&dst[w], m & ~src[w]);
+    }
+    w_sync();
+}
+
+}  // namespace cscb

@@ -1,0 +1,242 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the very same engine sources the CUDA kernels are built from
+// (csc_b200/csrc/enc_engine.cuh, dec_engine.cuh, blocks.cuh, plan.h) for the
+// host with a single-lane "warp", and feeds them match-finder arrays produced
+// by a brute-force CPU builder.  There is no GPU in the development container,
+// so this is how the serial logic is iterated against the oracle before a
+// gpurun call; the product library never links or calls any of this.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../csc_b200/csrc/host_common.h"
+#include "../../csc_b200/csrc/plan.h"
+#include "../../csc_b200/csrc/enc_engine.cuh"
+#include "../../csc_b200/csrc/dec_engine.cuh"
+
+using namespace cscb;
+
+namespace {
+
+struct Sink {
+    std::vector<u8> *v;
+    void operator()(const u8 *p, u32 n) { v->insert(v->end(), p, p + n); }
+};
+
+// Brute-force "last-K prior occurrences per position" (what mf_kernels.cu computes with a
+// sort + segmented scan) through an actual last-occurrence table.
+void build_mf_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, u32 bits, u32 K, std::vector<u32> &P6,
+                  std::vector<u16> &L6, std::vector<u32> &Z2, std::vector<u32> &Z6) {
+    u32 words = (n + 31) / 32 + 1;
+    Z2.assign(words, 0);
+    Z6.assign(words, 0);
+    P6.assign((size_t)n * (K ? K : 1), kNone);
+    L6.assign((size_t)n * (K ? K : 1), 0);
+    std::vector<u32> last;
+    if (K) last.assign((size_t)1 << bits, kNone);
+    u32 a = 0;
+    for (u32 s = 0; s < seg.size(); s++) {
+        for (u32 off = 0; off < seg[s]; off += kBlock) {
+            u32 sb = seg[s] - off < kBlock ? seg[s] - off : kBlock;
+            u32 sb_end = a + off + sb;
+            for (u32 x = a + off; x < sb_end; x++) {
+                u32 avail = sb_end - x;
+                if (hash2_padded(lz + x, avail) % 16 == 0) Z2[x >> 5] |= 1u << (x & 31);
+                if (!K) continue;
+                u32 h = hash6_padded(lz + x, avail, bits);
+                if (h == 0) Z6[x >> 5] |= 1u << (x & 31);
+                u32 prev = last[h];
+                last[h] = x;
+                u32 e = prev;
+                for (u32 k = 0; k < K && e != kNone; k++) {
+                    P6[(size_t)x * K + k] = e;
+                    u32 l = 0;
+                    while (l < avail && lz[x + l] == lz[e + l]) l++;
+                    L6[(size_t)x * K + k] = (u16)l;
+                    e = P6[(size_t)e * K];
+                }
+            }
+        }
+        a += seg[s];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Whole stream through the host-simulated product path. Same contract as oracle ref_encode.
+// trace: optional (kind,a,b) triples; returns 0 or negative.
+int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint32_t read_size, int flt_mask,
+              int with_props, uint8_t *out, size_t cap, size_t *out_n, uint32_t *trace, size_t trace_cap,
+              size_t *trace_n) {
+    u32 n = (u32)n_;
+    CSCProps p;
+    props_init(&p, dict_size, level);
+    p.DLTFilter = flt_mask & 1; p.TXTFilter = (flt_mask >> 1) & 1; p.EXEFilter = (flt_mask >> 2) & 1;
+    EncCfg cfg = cfg_from_props(&p);
+    if (n > cfg.wnd_size) return kErrUnsupported;
+    std::vector<u8> res;
+    Sink sink{&res};
+    if (with_props) { u8 hdr[10]; write_props(&p, hdr); sink(hdr, 10); }
+    Framer fr(p.csc_blocksize);
+    if (n) {
+        if (!read_size || read_size > p.raw_blocksize) read_size = p.raw_blocksize;
+        std::vector<u32> seg, seg_blk0;
+        u32 nblk = 0;
+        for (u32 a = 0; a < n; a += read_size) {
+            u32 s = n - a < read_size ? n - a : read_size;
+            seg.push_back(s);
+            seg_blk0.push_back(nblk);
+            nblk += (s + kBlock - 1) / kBlock;
+        }
+        std::vector<u8> lz(in, in + n);
+        lz.resize(n + 64, 0);
+        AnalyzerTables AT;
+        build_analyzer_tables(AT);
+        DictTables DT;
+        build_dict_tables(DT);
+        std::vector<u32> binfo(nblk), bbpb(nblk), tail_dlt(seg.size() * 5, 0);
+        std::vector<u8> dict_ok(nblk, 0);
+        u32 a = 0;
+        bool use_filters = (cfg.flt_dlt + cfg.flt_txt + cfg.flt_exe) != 0;
+        for (u32 s = 0; s < seg.size(); s++) {
+            u32 b = seg_blk0[s];
+            for (u32 off = 0; off < seg[s]; off += kBlock, b++) {
+                u32 sz = seg[s] - off < kBlock ? seg[s] - off : kBlock;
+                if (use_filters) analyze_block(lz.data() + a + off, sz, AT, &binfo[b], &bbpb[b], &tail_dlt[s * 5]);
+                else { binfo[b] = DT_NORMAL; bbpb[b] = 0; }
+            }
+            std::vector<FilterRun> runs((seg[s] + kBlock - 1) / kBlock + 1);
+            u32 nr = plan_segment(binfo.data(), seg_blk0[s], a, seg[s], cfg.flt_dlt, cfg.flt_txt, cfg.flt_exe, runs.data());
+            std::vector<u8> tmp;
+            for (u32 r = 0; r < nr; r++) {
+                if (runs[r].kind == DT_EXE) e8e9_run(lz.data() + runs[r].off, runs[r].size, false);
+                else {
+                    tmp.resize(runs[r].size);
+                    dict_ok[runs[r].first_blk] = (u8)dict_forward(lz.data() + runs[r].off, runs[r].size, tmp.data(), DT);
+                }
+            }
+            a += seg[s];
+        }
+        std::vector<u32> P6, Z2, Z6;
+        std::vector<u16> L6;
+        u32 K = cfg.ht_width;
+        build_mf_cpu(lz.data(), n, seg, cfg.ht_bits, K, P6, L6, Z2, Z6);
+        std::vector<u32> D6((n + 31) / 32 + 1, 0), ht2(16384, 0), ht3(65536, 0);
+        std::vector<u16> p_lit(65536, 2048), p_delta(65536, 2048);
+        std::vector<ApUnit> ap(kApLimit + 2);
+        u32 rc_cap = n * 2 + 65536 * 2, bc_cap = n * 2 + 65536 * 2;
+        std::vector<u8> rc(rc_cap), bc(bc_cap), ev(rc_cap / 32768 + bc_cap / 32768 + 64);
+        std::vector<SegOut> so(seg.size());
+        i32 status = 0;
+        u32 tn = 0;
+        EncStream S;
+        memset(&S, 0, sizeof(S));
+        S.cfg = cfg; S.lz = lz.data(); S.n = n; S.nseg = (u32)seg.size();
+        S.seg_size = seg.data(); S.seg_blk0 = seg_blk0.data(); S.binfo = binfo.data(); S.bbpb = bbpb.data();
+        S.tail_dlt = tail_dlt.data(); S.dict_ok = dict_ok.data();
+        S.P6 = P6.data(); S.L6 = L6.data(); S.K = K ? K : 1; S.Z2 = Z2.data(); S.Z6 = Z6.data(); S.D6 = D6.data();
+        S.ht2 = ht2.data(); S.ht3 = ht3.data(); S.p_lit = p_lit.data(); S.p_delta = p_delta.data(); S.ap = ap.data();
+        S.rc_out = rc.data(); S.rc_cap = rc_cap; S.bc_out = bc.data(); S.bc_cap = bc_cap;
+        S.events = ev.data(); S.ev_cap = (u32)ev.size(); S.segout = so.data(); S.status = &status;
+        S.trace = trace; S.trace_cap = (u32)trace_cap; S.trace_n = &tn;
+        ModelSmall *M = new ModelSmall;
+        build_p2bits(M->p2bits);
+        Encoder *E = new Encoder(S, *M);
+        E->run();
+        delete E;
+        delete M;
+        if (trace_n) *trace_n = tn;
+        if (status < 0) return status;
+        for (u32 s = 0; s < seg.size(); s++)
+            fr.segment(sink, rc.data() + so[s].rc_off, so[s].rc_len, bc.data() + so[s].bc_off, so[s].bc_len,
+                       ev.data() + so[s].ev_off, so[s].ev_len);
+    }
+    fr.eof(sink);
+    *out_n = res.size();
+    if (res.size() > cap) return kErrOverflow;
+    memcpy(out, res.data(), res.size());
+    return 0;
+}
+
+// Whole stream (with 10-byte props header) through the host-simulated decoder engine.
+int hs_decode(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_n) {
+    if (n < 10) return -1;
+    CSCProps p;
+    memset(&p, 0, sizeof(p));
+    read_props(&p, in);
+    DecInput di;
+    int r = deframe(in + 10, n - 10, p.csc_blocksize, di);
+    if (r < 0) return r;
+    std::vector<u8> wnd(cap + 64);
+    std::vector<u16> p_lit(65536, 2048), p_delta(65536, 2048);
+    std::vector<DecRun> runs(cap / 512 + 1024);
+    u32 n_runs = 0, out_len = 0;
+    i32 status = 0;
+    DecStream D;
+    memset(&D, 0, sizeof(D));
+    D.wnd_size = (u32)p.dict_size; D.raw_blocksize = p.raw_blocksize;
+    D.rc = di.rc.data(); D.rc_len = (u32)di.rc.size(); D.bc = di.bc.data(); D.bc_len = (u32)di.bc.size();
+    D.rc_blk_off = di.rc_off.data(); D.n_rc_blk = (u32)di.rc_off.size() - 1;
+    D.bc_blk_off = di.bc_off.data(); D.n_bc_blk = (u32)di.bc_off.size() - 1;
+    D.wnd = wnd.data(); D.out_cap = (u32)cap;
+    D.p_lit = p_lit.data(); D.p_delta = p_delta.data();
+    D.runs = runs.data(); D.runs_cap = (u32)runs.size(); D.n_runs = &n_runs; D.out_len = &out_len; D.status = &status;
+    ModelSmall *M = new ModelSmall;
+    Decoder *dec = new Decoder(D, *M);
+    dec->run();
+    delete dec;
+    delete M;
+    if (status < 0) return status;
+    DictTables DT;
+    build_dict_tables(DT);
+    // inverse filters per run (csc_dec.cpp:596-651)
+    for (u32 i = 0; i < n_runs; i++) {
+        const DecRun &rn = runs[i];
+        if (rn.type == DT_EXE) { memcpy(out + rn.off, wnd.data() + rn.off, rn.size); e8e9_run(out + rn.off, rn.size, true); }
+        else if (rn.type == DT_ENGTXT) dict_inverse(wnd.data() + rn.off, rn.size, out + rn.off, DT);
+        else memcpy(out + rn.off, wnd.data() + rn.off, rn.size);
+    }
+    *out_n = out_len;
+    return 0;
+}
+
+// class-level helpers (compared with the oracle in tests)
+void hs_analyze_blocks(const uint8_t *buf, size_t n, uint32_t *info, uint32_t *bpb) {
+    AnalyzerTables AT;
+    build_analyzer_tables(AT);
+    u32 b = 0;
+    u32 tail[5];
+    for (size_t off = 0; off < n; off += kBlock, b++) {
+        u32 sz = (u32)(n - off < kBlock ? n - off : kBlock);
+        analyze_block(buf + off, sz, AT, &info[b], &bpb[b], tail);
+    }
+}
+int hs_filter(int which, int inverse, uint8_t *buf, uint32_t n, uint32_t chn) {
+    std::vector<u8> tmp(n + 16);
+    int r = 1;
+    if (which == 0) e8e9_run(buf, n, inverse != 0);
+    else if (which == 1) {
+        DictTables DT;
+        build_dict_tables(DT);
+        if (inverse) { dict_inverse(buf, n, tmp.data(), DT); memcpy(buf, tmp.data(), n); }
+        else r = (int)dict_forward(buf, n, tmp.data(), DT);
+    } else {
+        if (inverse) delta_inverse(buf, n, chn, tmp.data()); else delta_forward(buf, n, chn, tmp.data());
+        memcpy(buf, tmp.data(), n);
+    }
+    return r;
+}
+void hs_props_init(uint32_t dict_size, int level, uint64_t *o) {
+    CSCProps p;
+    memset(&p, 0, sizeof(p));
+    props_init(&p, dict_size, level);
+    o[0] = p.dict_size; o[1] = p.csc_blocksize; o[2] = p.raw_blocksize; o[3] = p.hash_bits; o[4] = p.hash_width;
+    o[5] = p.bt_hash_bits; o[6] = p.bt_size; o[7] = p.bt_cyc; o[8] = p.good_len; o[9] = p.lz_mode;
+    o[10] = p.DLTFilter; o[11] = p.TXTFilter; o[12] = p.EXEFilter; o[13] = est_mem_usage(&p); o[14] = sizeof(CSCProps);
+}
+
+}  // extern "C"

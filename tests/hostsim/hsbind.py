@@ -1,0 +1,95 @@
+"""ctypes binding to tests/hostsim/_build/hostsim.so -- the engine sources compiled for the
+host (single-lane warp).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))
+_SO = os.path.join(_HERE, "_build", "hostsim.so")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, "hostsim.cpp")] + [
+        os.path.join(_ROOT, "csc_b200", "csrc", f) for f in os.listdir(os.path.join(_ROOT, "csc_b200", "csrc"))
+        if f.endswith((".h", ".cuh"))]
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
+        return
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    cmd = ["g++", "-O2", "-g", "-Wall", "-Wno-unused", "-Wno-unknown-pragmas", "-fPIC", "-shared",
+           "-I", os.path.join(_ROOT, "include"), "-o", _SO, os.path.join(_HERE, "hostsim.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError("hostsim build failed:\n" + r.stderr)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.hs_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t,
+                                   C.POINTER(C.c_size_t)]
+        _lib.hs_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        _lib.hs_analyze_blocks.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        _lib.hs_filter.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib.hs_props_init.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+    return _lib
+
+
+def _u8(a):
+    if isinstance(a, (bytes, bytearray)):
+        a = np.frombuffer(bytes(a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def encode(data, dict_size, level, read_size=0, flt_mask=7, with_props=True, trace=False):
+    a = _u8(data)
+    out = np.empty(a.size * 2 + (1 << 18), dtype=np.uint8)
+    n = C.c_size_t(0)
+    tn = C.c_size_t(0)
+    tr = np.zeros((a.size + 1024, 3), dtype=np.uint32) if trace else None
+    r = lib().hs_encode(a.ctypes.data, a.size, dict_size, level, read_size, flt_mask, int(with_props),
+                        out.ctypes.data, out.size, C.byref(n), tr.ctypes.data if trace else None,
+                        tr.shape[0] if trace else 0, C.byref(tn))
+    if r < 0:
+        raise RuntimeError(f"hs_encode failed: {r}")
+    res = out[: n.value].copy()
+    return (res, tr[: tn.value]) if trace else res
+
+
+def decode(stream, raw_size_hint):
+    a = _u8(stream)
+    out = np.empty(max(raw_size_hint, 16) + 64, dtype=np.uint8)
+    n = C.c_size_t(0)
+    r = lib().hs_decode(a.ctypes.data, a.size, out.ctypes.data, out.size - 64, C.byref(n))
+    if r < 0:
+        raise RuntimeError(f"hs_decode failed: {r}")
+    return out[: n.value].copy()
+
+
+def analyze_blocks(data):
+    a = _u8(data)
+    nb = (a.size + 8191) // 8192
+    t = np.zeros(nb, dtype=np.uint32)
+    b = np.zeros(nb, dtype=np.uint32)
+    lib().hs_analyze_blocks(a.ctypes.data, a.size, t.ctypes.data, b.ctypes.data)
+    return t, b
+
+
+def filt(which, inverse, data, chn=0):
+    a = _u8(data).copy()
+    r = lib().hs_filter(which, int(inverse), a.ctypes.data, a.size, chn)
+    return a, r
+
+
+def props(dict_size, level):
+    o = np.zeros(15, dtype=np.uint64)
+    lib().hs_props_init(dict_size, level, o.ctypes.data)
+    k = ["dict_size", "csc_blocksize", "raw_blocksize", "hash_bits", "hash_width", "bt_hash_bits", "bt_size",
+         "bt_cyc", "good_len", "lz_mode", "DLTFilter", "TXTFilter", "EXEFilter", "est_mem", "sizeof"]
+    return {kk: int(v) for kk, v in zip(k, o)}
