@@ -67,12 +67,10 @@ CSC_HD i32 channel_from_stats(const u32 *same, const u32 *succ, u32 size) {
 }
 
 // type decision from the histogram statistics (csc_analyzer.cpp:190-238); need_chn is set
-// when the channel statistics have to be consulted (returns DT_NONE in that case)
-CSC_HD u32 type_from_hist(const u32 *freq, u32 size, u32 entropy, const AnalyzerTables &T, bool *need_chn) {
-    u32 diff = 0, hi = 0, alpha = 0;
-    for (u32 i = 0; i < 256; i++) diff += (freq[i] > 0);
-    for (u32 i = 128; i < 256; i++) hi += freq[i];
-    for (u32 i = 'a'; i <= 'z'; i++) alpha += freq[i];
+// when the channel statistics have to be consulted (returns DT_NONE in that case).
+// diff = distinct bytes, hi = mass of bytes >= 0x80, alpha = mass of 'a'..'z'.
+CSC_HD u32 type_from_stats(const u32 *freq, u32 size, u32 entropy, u32 diff, u32 hi, u32 alpha,
+                           const AnalyzerTables &T, bool *need_chn) {
     u32 avg = size >> 8;
     *need_chn = false;
     if (hi < (size >> 3) && (freq[' '] + freq['\n'] + freq[':'] + freq['.'] + freq['/'] > (size >> 4)) &&
@@ -83,6 +81,13 @@ CSC_HD u32 type_from_hist(const u32 *freq, u32 size, u32 entropy, const Analyzer
     if (entropy < 400 * size && diff < 200) return DT_NORMAL;
     *need_chn = true;
     return DT_NONE;
+}
+CSC_HD u32 type_from_hist(const u32 *freq, u32 size, u32 entropy, const AnalyzerTables &T, bool *need_chn) {
+    u32 diff = 0, hi = 0, alpha = 0;
+    for (u32 i = 0; i < 256; i++) diff += (freq[i] > 0);
+    for (u32 i = 128; i < 256; i++) hi += freq[i];
+    for (u32 i = 'a'; i <= 'z'; i++) alpha += freq[i];
+    return type_from_stats(freq, size, entropy, diff, hi, alpha, T, need_chn);
 }
 CSC_HD u32 type_after_chn(i32 chn_idx, u32 entropy, u32 size) {
     if (chn_idx != -1) return DT_DLT + (u32)chn_idx;

@@ -16,10 +16,12 @@ typedef uint64_t u64;
 typedef int32_t i32;
 
 #if defined(__CUDACC__)
-#define CSC_HD __host__ __device__ __forceinline__
+#define CSC_HD __host__ __device__ inline
+#define CSC_HDF __host__ __device__ __forceinline__
 #define CSC_HDN __host__ __device__ __noinline__
 #else
 #define CSC_HD inline
+#define CSC_HDF inline
 #define CSC_HDN
 #endif
 

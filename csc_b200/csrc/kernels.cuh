@@ -1,0 +1,327 @@
+// kernels.cuh -- sm_100a kernels of the libcsc hot path.
+//
+//   k_analyze      one warp per 8 KiB block: histogram -> entropy, type heuristics, channel
+//                  statistics, delta-channel entropy          (csc_analyzer.cpp:122-239)
+//   k_plan         static EXE / ENGTXT run extraction          (csc_encoder_main.cpp:95-135)
+//   k_filter_runs  e8e9 / dictionary forward transforms per run (csc_filters.cpp:256-335,588)
+//   k_mf_hash      padded HASH6 keys + HASH2%16 / HASH6==0 bitmaps (csc_mf.cpp:23-42,215,136)
+//   k_mf_rows      sorted (stream,hash,pos) -> K nearest earlier same-hash positions per position
+//   k_mf_extend    forward match length of every (position, candidate) pair, capped at the
+//                  sub-block end                               (csc_mf.cpp:470, 8 B words)
+//   k_encode       one stream per warp: enc_engine.cuh
+//   k_decode       one stream per warp: dec_engine.cuh
+//   k_unfilter     inverse e8e9 / dictionary per decoded run   (csc_filters.cpp:337,600)
+//
+// Everything here is HBM/latency-bound integer and byte work: no tensor cores on purpose.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "csc_defs.h"
+#include "warp.h"
+#include "blocks.cuh"
+#include "plan.h"
+#include "enc_engine.cuh"
+#include "dec_engine.cuh"
+
+namespace cscb {
+
+struct BlockDesc {
+    u64 goff;      // byte offset of the block in the batch LZ buffer
+    u32 x;         // byte offset of the block in its stream
+    u32 size;      // <= 8192
+    u32 stream;
+    u32 seg;       // batch-global segment index
+    u32 cpos;      // compact position index of the block's first byte (sort arrays)
+    u32 pad;
+};
+struct SegDesc {
+    u64 goff;      // byte offset of the segment in the batch LZ buffer
+    u32 x;         // offset in stream
+    u32 size;
+    u32 stream;
+    u32 blk0;      // batch-global index of the segment's first block
+    u32 flt;       // bit0 DLT, bit1 TXT, bit2 EXE
+    u32 pad;
+};
+struct GRun { u64 goff; u32 size; u32 kind; u32 gblk; u32 pad; };
+
+// ------------------------------------------------------------------ analyzer
+static const int kAnWarps = 4;
+static const int kStageVec = (kBlock + 32) / 16 + 1;
+
+__device__ __forceinline__ void hist_clear(u32 *h, u32 lane) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[lane + 32 * i] = 0;
+    __syncwarp();
+}
+__device__ __forceinline__ u32 hist_entropy(const u32 *h, u32 size, const u32 *logtab, u32 lane) {
+    u32 part = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u32 f = h[lane + 32 * i]; part += f * logtab[f >> 4]; }
+    u32 tot = __reduce_add_sync(0xFFFFFFFFu, part);
+    return size * logtab[size >> 4] - tot;   // u32 wrap-around arithmetic, order independent
+}
+// histogram of the channel-delta residual (GetDltBpb): prev of the first byte of channel c is
+// the last byte of channel c-1
+__device__ __forceinline__ u32 dlt_bpb_warp(const u8 *sb, u32 size, u32 chn, u32 *h, const u32 *logtab, u32 lane) {
+    hist_clear(h, lane);
+    u32 base = size / chn, rem = size % chn;
+    for (u32 j = lane; j < size; j += 32) {
+        u32 prev;
+        if (j >= chn) prev = sb[j - chn];
+        else if (j == 0) prev = 0;
+        else { u32 c = j - 1; u32 cnt = base + (c < rem ? 1u : 0u); prev = cnt ? sb[c + (cnt - 1) * chn] : 0; }
+        atomicAdd(&h[(sb[j] - prev) & 0xFF], 1u);
+    }
+    __syncwarp();
+    return hist_entropy(h, size, logtab, lane) / size;
+}
+
+__global__ void __launch_bounds__(kAnWarps * 32)
+k_analyze(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, u32 nblk, const AnalyzerTables *__restrict__ Tg,
+          u32 *__restrict__ binfo, u32 *__restrict__ bbpb, u32 *__restrict__ tail_dlt) {
+    __shared__ uint4 s_data[kAnWarps][kStageVec];
+    __shared__ u32 s_hist[kAnWarps][256];
+    __shared__ AnalyzerTables T;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const u32 *src = reinterpret_cast<const u32 *>(Tg);
+        u32 *dst = reinterpret_cast<u32 *>(&T);
+        for (u32 i = threadIdx.x; i < sizeof(AnalyzerTables) / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const u32 b = blockIdx.x * kAnWarps + warp;
+    if (b >= nblk) return;
+    const BlockDesc bd = blk[b];
+    const u32 size = bd.size;
+    // stage the block with 16-byte loads from the enclosing aligned span
+    const u64 a0 = bd.goff & ~(u64)15;
+    const u32 shift = (u32)(bd.goff - a0);
+    const u32 nvec = (shift + size + 15) / 16;
+    const uint4 *g = reinterpret_cast<const uint4 *>(lz + a0);
+    for (u32 i = lane; i < nvec; i += 32) s_data[warp][i] = g[i];
+    __syncwarp();
+    const u8 *sb = reinterpret_cast<const u8 *>(s_data[warp]) + shift;
+    u32 *h = s_hist[warp];
+
+    if (size < 512) {   // DT_SKIP (csc_analyzer.cpp:193): the engine may need GetDltBpb of the inherited type
+        for (u32 k = 0; k < DLT_CHANNEL_MAX; k++) {
+            u32 v = size ? dlt_bpb_warp(sb, size, dlt_channels(k), h, T.logtab, lane) : 0;
+            if (lane == 0) tail_dlt[bd.seg * 5 + k] = v;
+        }
+        if (lane == 0) { binfo[b] = DT_SKIP; bbpb[b] = 0; }
+        return;
+    }
+    hist_clear(h, lane);
+    for (u32 i = lane; i < size; i += 32) atomicAdd(&h[sb[i]], 1u);
+    __syncwarp();
+    const u32 entropy = hist_entropy(h, size, T.logtab, lane);
+    u32 d = 0, hi = 0, al = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        u32 idx = lane + 32 * i, f = h[idx];
+        d += (f > 0);
+        if (idx >= 128) hi += f;
+        if (idx >= 'a' && idx <= 'z') al += f;
+    }
+    d = __reduce_add_sync(0xFFFFFFFFu, d);
+    hi = __reduce_add_sync(0xFFFFFFFFu, hi);
+    al = __reduce_add_sync(0xFFFFFFFFu, al);
+    bool need_chn;
+    u32 type = type_from_stats(h, size, entropy, d, hi, al, T, &need_chn);
+    if (need_chn) {   // get_channel_idx (csc_analyzer.cpp:122-164)
+        u32 same[DLT_CHANNEL_MAX] = {0, 0, 0, 0, 0}, succ[DLT_CHANNEL_MAX] = {0, 0, 0, 0, 0};
+        for (u32 i = lane; i + 16 < size; i += 32) {
+            u32 v = sb[i];
+#pragma unroll
+            for (u32 k = 0; k < DLT_CHANNEL_MAX; k++) {
+                u32 w = sb[i + dlt_channels(k)];
+                same[k] += (v == w);
+                succ[k] += absdiff(v, w);
+            }
+        }
+#pragma unroll
+        for (u32 k = 0; k < DLT_CHANNEL_MAX; k++) {
+            same[k] = __reduce_add_sync(0xFFFFFFFFu, same[k]);
+            succ[k] = __reduce_add_sync(0xFFFFFFFFu, succ[k]);
+        }
+        type = type_after_chn(channel_from_stats(same, succ, size), entropy, size);
+    }
+    const u32 bpb = entropy / size;
+    u32 fail = 0;
+    if (type >= DT_DLT) {
+        u32 dv = dlt_bpb_warp(sb, size, dlt_channels(type - DT_DLT), h, T.logtab, lane);
+        fail = ((double)dv >= (double)bpb * 0.95) ? 1u : 0u;
+    }
+    if (lane == 0) { binfo[b] = type | (fail << 8); bbpb[b] = bpb; }
+}
+
+// -------------------------------------------------------------- plan + filters
+__global__ void k_plan(const SegDesc *__restrict__ segs, u32 nseg, const u32 *__restrict__ binfo, FilterRun *scratch,
+                       GRun *runs, u32 *nruns) {
+    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const SegDesc sd = segs[s];
+    FilterRun *mine = scratch + sd.blk0;
+    u32 nr = plan_segment(binfo, sd.blk0, 0, sd.size, sd.flt & 1, (sd.flt >> 1) & 1, (sd.flt >> 2) & 1, mine);
+    if (!nr) return;
+    u32 at = atomicAdd(nruns, nr);
+    for (u32 i = 0; i < nr; i++) {
+        GRun r;
+        r.goff = sd.goff + mine[i].off; r.size = mine[i].size; r.kind = mine[i].kind; r.gblk = mine[i].first_blk; r.pad = 0;
+        runs[at + i] = r;
+    }
+}
+
+__global__ void k_filter_runs(u8 *lz, u8 *tmp, const GRun *__restrict__ runs, const u32 *__restrict__ nruns,
+                              const DictTables *__restrict__ D, u8 *dict_ok) {
+    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *nruns) return;
+    const GRun g = runs[r];
+    if (g.kind == DT_EXE) e8e9_run(lz + g.goff, g.size, false);
+    else dict_ok[g.gblk] = (u8)dict_forward(lz + g.goff, g.size, tmp + g.goff, *D);
+}
+
+// ------------------------------------------------------------------ match finder
+// One CTA per 8 KiB block (= sub-block of the reference window copy).  Keys are
+// (stream << key_shift) | HASH6 so that one batch-wide stable sort groups equal hashes of
+// one stream in position order.
+static const int kMfThreads = 256;
+__global__ void __launch_bounds__(kMfThreads)
+k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u32 *__restrict__ stream_bits,
+          const u64 *__restrict__ stream_goff, u32 key_shift, u64 *__restrict__ keys, u32 *__restrict__ vals,
+          u32 *Z2, u32 *Z6) {
+    __shared__ u8 s[kBlock + 16];
+    const BlockDesc bd = blk[blockIdx.x];
+    const u8 *src = lz + bd.goff;
+    for (u32 i = threadIdx.x; i < kBlock + 16; i += kMfThreads) s[i] = i < bd.size ? src[i] : (u8)0;   // zero padding (H2)
+    __syncthreads();
+    const u32 bits = stream_bits[bd.stream];
+    const u64 bitbase = (stream_goff[bd.stream]) + bd.x;   // bitmaps are indexed by batch byte offset
+    for (u32 i = threadIdx.x; i < bd.size; i += kMfThreads) {
+        const u8 *p = s + i;
+        u32 v = p[0] | (p[1] << 8) | (p[2] << 16) | ((u32)p[3] << 24);
+        u32 v2 = p[4] | (p[5] << 8);
+        u32 h6 = bits ? ((v ^ (v2 << 13)) * 2654435761u) >> (32 - bits) : 0;
+        u32 h2 = ((v & 0xFFFF) * 65521u) & 0x3FFF;
+        keys[bd.cpos + i] = ((u64)bd.stream << key_shift) | h6;
+        vals[bd.cpos + i] = bd.x + i;
+        u64 bit = bitbase + i;
+        if ((h2 & 15) == 0) atomicOr(&Z2[bit >> 5], 1u << (bit & 31));
+        if (bits && h6 == 0) atomicOr(&Z6[bit >> 5], 1u << (bit & 31));
+    }
+}
+
+__global__ void k_mf_rows(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u32 n, u32 key_shift,
+                          const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_K, u32 *__restrict__ P6) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 k = keys[i];
+    const u32 s = (u32)(k >> key_shift);
+    const u32 K = stream_K[s];
+    if (!K) return;
+    u32 *row = P6 + (stream_goff[s] + vals[i]) * K;
+    bool live = true;
+    for (u32 j = 0; j < K; j++) {
+        live = live && (i > j) && keys[i - 1 - j] == k;
+        row[j] = live ? vals[i - 1 - j] : kNone;
+    }
+}
+
+__device__ __forceinline__ u32 ld_u32_unaligned(const u8 *p) {
+    const u32 *a = reinterpret_cast<const u32 *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    u32 sh = (u32)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+    u32 lo = a[0];
+    if (!sh) return lo;
+    return __funnelshift_r(lo, a[1], sh);
+}
+
+// forward match lengths; one thread per (position, candidate) pair, 4 bytes per step
+__global__ void __launch_bounds__(kMfThreads)
+k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u64 *__restrict__ stream_goff,
+            const u32 *__restrict__ stream_K, const u32 *__restrict__ P6, u16 *__restrict__ L6) {
+    const BlockDesc bd = blk[blockIdx.x];
+    const u32 K = stream_K[bd.stream];
+    if (!K) return;
+    const u64 sg = stream_goff[bd.stream];
+    const u8 *base = lz + sg;
+    const u32 pairs = bd.size * K;
+    for (u32 t = threadIdx.x; t < pairs; t += kMfThreads) {
+        u32 i = t / K;
+        u32 x = bd.x + i;
+        u64 at = (sg + x) * K + (t - i * K);
+        u32 e = P6[at];
+        if (e == kNone) continue;
+        u32 limit = bd.size - i;
+        const u8 *a = base + x, *m = base + e;
+        u32 l = 0;
+        while (l + 4 <= limit) {
+            u32 d = ld_u32_unaligned(a + l) ^ ld_u32_unaligned(m + l);
+            if (d) { l += (__ffs((int)d) - 1) >> 3; goto done; }
+            l += 4;
+        }
+        while (l < limit && a[l] == m[l]) l++;
+    done:
+        L6[at] = (u16)l;
+    }
+}
+
+// ------------------------------------------------------------------ fill helper
+__global__ void k_fill_u16(u16 *p, u64 n, u16 v) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+// ------------------------------------------------------------------ serial engines
+static const int kEncWarps = 4;
+__global__ void __launch_bounds__(kEncWarps * 32)
+k_encode(const EncStream *__restrict__ streams, u32 ns, u32 *queue, const u32 *__restrict__ p2bits) {
+    __shared__ ModelSmall sm[kEncWarps];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 i = lane; i < 512; i += 32) sm[warp].p2bits[i] = p2bits[i];
+    __syncwarp();
+    for (;;) {
+        u32 s = 0;
+        if (lane == 0) s = atomicAdd(queue, 1u);
+        s = __shfl_sync(0xFFFFFFFFu, s, 0);
+        if (s >= ns) break;
+        EncStream S = streams[s];
+        Encoder E(S, sm[warp]);
+        E.run();
+        __syncwarp();
+    }
+}
+
+static const int kDecWarps = 4;
+__global__ void __launch_bounds__(kDecWarps * 32)
+k_decode(const DecStream *__restrict__ streams, u32 ns, u32 *queue) {
+    __shared__ ModelSmall sm[kDecWarps];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        u32 s = 0;
+        if (lane == 0) s = atomicAdd(queue, 1u);
+        s = __shfl_sync(0xFFFFFFFFu, s, 0);
+        if (s >= ns) break;
+        DecStream S = streams[s];
+        Decoder D(S, sm[warp]);
+        D.run();
+        __syncwarp();
+    }
+}
+
+// inverse filters: one thread per (stream, run); `out` already holds a copy of the window
+__global__ void k_unfilter(const DecStream *__restrict__ streams, u32 ns, u32 max_runs, u8 *const *__restrict__ outs,
+                           const DictTables *__restrict__ D) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 s = t / max_runs, r = t % max_runs;
+    if (s >= ns) return;
+    const DecStream &S = streams[s];
+    if (*S.status < 0 || r >= *S.n_runs) return;
+    const DecRun rn = S.runs[r];
+    u8 *out = outs[s];
+    if (rn.type == DT_EXE) e8e9_run(out + rn.off, rn.size, true);
+    else if (rn.type == DT_ENGTXT) dict_inverse(S.wnd + rn.off, rn.size, out + rn.off, *D);
+}
+
+}  // namespace cscb

@@ -1,0 +1,767 @@
+// pipeline.cu -- host side of the B200 libcsc hot path: batch layout in HBM, kernel
+// sequencing on one CUDA stream, result framing, and the C-ABI entry points
+// (include/csc_enc.h, include/csc_dec.h, include/csc_b200.h).
+//
+// There is NO CPU fallback: without a usable CUDA device every compute entry point fails.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <new>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/csc_enc.h"
+#include "../../include/csc_dec.h"
+#include "../../include/csc_b200.h"
+#include "host_common.h"
+#include "kernels.cuh"
+
+using namespace cscb;
+
+namespace {
+
+const int kErrCuda = -92;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            fprintf(stderr, "csc_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return kErrCuda;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) { fprintf(stderr, "csc_b200: cudaMalloc(%zu) failed: %s\n", bytes, cudaGetErrorString(e)); p = nullptr; return kErrCuda; }
+        cap = want;
+        return 0;
+    }
+    template <class T> T *as() const { return (T *)p; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; return kErrCuda; }
+        cap = want;
+        return 0;
+    }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct Timer {
+    cudaEvent_t ev[16];
+    int n = 0;
+    bool ok = false;
+    void init() { if (!ok) { for (auto &e : ev) cudaEventCreate(&e); ok = true; } }
+    void mark(cudaStream_t st) { if (n < 16) cudaEventRecord(ev[n++], st); }
+    float ms(int a, int b) { float t = 0; if (a < n && b < n) cudaEventElapsedTime(&t, ev[a], ev[b]); return t; }
+};
+
+struct Ctx {
+    bool init = false;
+    int dev = -1;
+    cudaStream_t st = nullptr;
+    AnalyzerTables *d_AT = nullptr;
+    DictTables *d_DT = nullptr;
+    u32 *d_p2bits = nullptr;
+    DevBuf lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
+        segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
+        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr;
+    PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta;
+    Timer tm;
+    CSCB200_Stats stats;
+};
+
+thread_local Ctx g_ctx;
+int g_device = -1;
+
+// debug: copy the intermediate arrays of a single-stream wave back to the host (tests only)
+struct DebugDump { u32 *binfo, *bbpb; u8 *lz; u32 *P6; u16 *L6; u32 *Z2, *Z6; u8 *dict_ok; u32 *tail_dlt; bool on; };
+thread_local DebugDump g_dump = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false};
+
+int ctx_init(Ctx &C) {
+    if (C.init) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "csc_b200: no CUDA device available (this library has no CPU fallback)\n");
+        return kErrCuda;
+    }
+    if (g_device >= 0) CK(cudaSetDevice(g_device));
+    CK(cudaGetDevice(&C.dev));
+    CK(cudaStreamCreateWithFlags(&C.st, cudaStreamNonBlocking));
+    AnalyzerTables AT;
+    build_analyzer_tables(AT);
+    DictTables *DT = new DictTables;
+    build_dict_tables(*DT);
+    u32 p2[512];
+    build_p2bits(p2);
+    CK(cudaMalloc(&C.d_AT, sizeof(AT)));
+    CK(cudaMalloc(&C.d_DT, sizeof(DictTables)));
+    CK(cudaMalloc(&C.d_p2bits, sizeof(p2)));
+    CK(cudaMemcpy(C.d_AT, &AT, sizeof(AT), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(C.d_DT, DT, sizeof(DictTables), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(C.d_p2bits, p2, sizeof(p2), cudaMemcpyHostToDevice));
+    delete DT;
+    C.tm.init();
+    C.init = true;
+    return 0;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// bounded memory sink for framed output
+struct MemSink {
+    u8 *p; size_t cap, off; bool overflow;
+    void operator()(const u8 *d, u32 n) {
+        if (off + n > cap) { overflow = true; off += n; return; }
+        memcpy(p + off, d, n);
+        off += n;
+    }
+};
+
+// one stream to encode
+struct EncJob {
+    const u8 *in; u32 n;
+    CSCProps props;
+    std::vector<u32> segs;     // Read() sizes
+    int status;
+    // results (host, pinned staging): filled by encode_wave
+    std::vector<SegOut> so;
+    const u8 *rc, *bc, *ev;
+};
+
+// ----------------------------------------------------------------------------- encode
+// Runs the whole device pipeline for a set of streams that fits in HBM at once and leaves,
+// per job, the RC/BC sub-streams + block events in pinned host memory.
+int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
+    const u32 ns = (u32)jobs.size();
+    if (!ns) return 0;
+    cudaStream_t st = C.st;
+    // ---- layout
+    std::vector<u64> goff(ns);
+    std::vector<u32> seg0(ns), sbits(ns), sK(ns), rcoff(ns), bcoff(ns), rccap(ns), evcap(ns), evoff(ns);
+    std::vector<BlockDesc> blks;
+    std::vector<SegDesc> segs;
+    std::vector<u32> segsize, segblk0;
+    u64 total = 0, rctot = 0, evtot = 0;
+    u32 cpos = 0, K = 0, key_shift = 0;
+    for (u32 s = 0; s < ns; s++) {
+        EncJob &J = *jobs[s];
+        EncCfg cfg = cfg_from_props(&J.props);
+        if (J.n > cfg.wnd_size || cfg.bt_bits || !cfg.ht_width) { J.status = kErrUnsupported; return kErrUnsupported; }
+        if (s == 0) K = cfg.ht_width;
+        if (cfg.ht_width != K) return kErrUnsupported;   // one level per wave
+        goff[s] = total;
+        seg0[s] = (u32)segs.size();
+        sbits[s] = cfg.ht_bits; sK[s] = cfg.ht_width;
+        key_shift = std::max(key_shift, cfg.ht_bits);
+        u32 x = 0;
+        u32 flt = (J.props.DLTFilter ? 1 : 0) | (J.props.TXTFilter ? 2 : 0) | (J.props.EXEFilter ? 4 : 0);
+        for (u32 sz : J.segs) {
+            SegDesc sd;
+            sd.goff = total + x; sd.x = x; sd.size = sz; sd.stream = s; sd.blk0 = (u32)blks.size(); sd.flt = flt; sd.pad = 0;
+            segsize.push_back(sz);
+            segblk0.push_back(sd.blk0);
+            for (u32 off = 0; off < sz; off += kBlock) {
+                BlockDesc bd;
+                bd.goff = total + x + off; bd.x = x + off; bd.size = std::min(kBlock, sz - off); bd.stream = s;
+                bd.seg = (u32)segs.size(); bd.cpos = cpos; bd.pad = 0;
+                cpos += bd.size;
+                blks.push_back(bd);
+            }
+            segs.push_back(sd);
+            x += sz;
+        }
+        total = align_up(total + J.n + 64, 256);
+        rccap[s] = (u32)align_up((size_t)J.n + J.n / 8 + 66000, 16);
+        rcoff[s] = (u32)rctot; bcoff[s] = (u32)rctot;
+        rctot += rccap[s];
+        evcap[s] = (2 * rccap[s]) / 65536 + 8;
+        evoff[s] = (u32)evtot;
+        evtot += evcap[s];
+        if (rctot >= 0xFFFF0000ull || total >= 0xFFFF0000ull) return kErrUnsupported;
+    }
+    const u32 nblk = (u32)blks.size(), nseg = (u32)segs.size(), npos = cpos;
+    total += 256;
+    C.stats.mf_positions += npos;
+    // ---- device memory
+    int r = 0;
+    r |= C.lz.ensure(total); r |= C.tmp.ensure(total);
+    r |= C.keys0.ensure((size_t)npos * 8 + 16); r |= C.keys1.ensure((size_t)npos * 8 + 16);
+    r |= C.vals0.ensure((size_t)npos * 4 + 16); r |= C.vals1.ensure((size_t)npos * 4 + 16);
+    r |= C.P6.ensure(total * K * 4); r |= C.L6.ensure(total * K * 2);
+    const size_t bmbytes = total / 8 + 64;
+    r |= C.Z2.ensure(bmbytes); r |= C.Z6.ensure(bmbytes); r |= C.D6.ensure(bmbytes);
+    r |= C.ht.ensure((size_t)ns * 81920 * 4);
+    r |= C.plit.ensure((size_t)ns * 131072 * 2);
+    r |= C.ap.ensure((size_t)ns * (kApLimit + 2) * sizeof(ApUnit));
+    r |= C.rc.ensure(rctot); r |= C.bc.ensure(rctot); r |= C.ev.ensure(evtot);
+    r |= C.segout.ensure((size_t)nseg * sizeof(SegOut)); r |= C.status.ensure((size_t)ns * 4);
+    r |= C.blkdesc.ensure((size_t)nblk * sizeof(BlockDesc)); r |= C.segdesc.ensure((size_t)nseg * sizeof(SegDesc));
+    r |= C.binfo.ensure((size_t)nblk * 4); r |= C.bbpb.ensure((size_t)nblk * 4);
+    r |= C.taildlt.ensure((size_t)nseg * 5 * 4); r |= C.dictok.ensure(nblk);
+    r |= C.planscratch.ensure((size_t)nblk * sizeof(FilterRun)); r |= C.runs.ensure((size_t)nblk * sizeof(GRun));
+    r |= C.counters.ensure(64); r |= C.streams.ensure((size_t)ns * sizeof(EncStream));
+    r |= C.segsize.ensure((size_t)nseg * 4); r |= C.segblk0.ensure((size_t)nseg * 4);
+    r |= C.sbits.ensure((size_t)ns * 4); r |= C.sgoff.ensure((size_t)ns * 8); r |= C.sK.ensure((size_t)ns * 4);
+    if (r) return kErrCuda;
+    u32 stream_bits = 1;
+    while ((1u << stream_bits) < ns) stream_bits++;
+    const int end_bit = (int)(key_shift + stream_bits);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, C.keys0.as<u64>(), C.keys1.as<u64>(), C.vals0.as<u32>(),
+                                    C.vals1.as<u32>(), (int)npos, 0, end_bit, st);
+    if (C.cubtmp.ensure(cub_bytes + 16)) return kErrCuda;
+
+    // ---- stream descriptors
+    std::vector<EncStream> es(ns);
+    for (u32 s = 0; s < ns; s++) {
+        EncJob &J = *jobs[s];
+        EncStream &S = es[s];
+        memset(&S, 0, sizeof(S));
+        S.cfg = cfg_from_props(&J.props);
+        S.lz = C.lz.as<u8>() + goff[s]; S.n = J.n; S.nseg = (u32)J.segs.size();
+        S.seg_size = C.segsize.as<u32>() + seg0[s]; S.seg_blk0 = C.segblk0.as<u32>() + seg0[s];
+        S.binfo = C.binfo.as<u32>(); S.bbpb = C.bbpb.as<u32>();
+        S.tail_dlt = C.taildlt.as<u32>() + (size_t)seg0[s] * 5; S.dict_ok = C.dictok.as<u8>();
+        S.P6 = C.P6.as<u32>() + goff[s] * K; S.L6 = C.L6.as<u16>() + goff[s] * K; S.K = K;
+        S.Z2 = C.Z2.as<u32>() + goff[s] / 32; S.Z6 = C.Z6.as<u32>() + goff[s] / 32; S.D6 = C.D6.as<u32>() + goff[s] / 32;
+        S.ht2 = C.ht.as<u32>() + (size_t)s * 81920; S.ht3 = S.ht2 + 16384;
+        S.p_lit = C.plit.as<u16>() + (size_t)s * 131072; S.p_delta = S.p_lit + 65536;
+        S.ap = C.ap.as<ApUnit>() + (size_t)s * (kApLimit + 2);
+        S.rc_out = C.rc.as<u8>() + rcoff[s]; S.rc_cap = rccap[s];
+        S.bc_out = C.bc.as<u8>() + bcoff[s]; S.bc_cap = rccap[s];
+        S.events = C.ev.as<u8>() + evoff[s]; S.ev_cap = evcap[s];
+        S.segout = C.segout.as<SegOut>() + seg0[s];
+        S.status = C.status.as<i32>() + s;
+    }
+    Timer &T = C.tm;
+    T.n = 0;
+    T.mark(st);                                                                   // 0
+    // ---- uploads
+    for (u32 s = 0; s < ns; s++)
+        if (jobs[s]->n) CK(cudaMemcpyAsync(C.lz.as<u8>() + goff[s], jobs[s]->in, jobs[s]->n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.blkdesc.p, blks.data(), (size_t)nblk * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.segdesc.p, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.segsize.p, segsize.data(), (size_t)nseg * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.segblk0.p, segblk0.data(), (size_t)nseg * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.sbits.p, sbits.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.sgoff.p, goff.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.sK.p, sK.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.streams.p, es.data(), (size_t)ns * sizeof(EncStream), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(C.Z2.p, 0, bmbytes, st));
+    CK(cudaMemsetAsync(C.Z6.p, 0, bmbytes, st));
+    CK(cudaMemsetAsync(C.D6.p, 0, bmbytes, st));
+    CK(cudaMemsetAsync(C.ht.p, 0, (size_t)ns * 81920 * 4, st));
+    CK(cudaMemsetAsync(C.status.p, 0, (size_t)ns * 4, st));
+    CK(cudaMemsetAsync(C.counters.p, 0, 64, st));
+    CK(cudaMemsetAsync(C.dictok.p, 0, nblk, st));
+    CK(cudaMemsetAsync(C.taildlt.p, 0, (size_t)nseg * 5 * 4, st));
+    CK(cudaMemsetAsync(C.segout.p, 0, (size_t)nseg * sizeof(SegOut), st));
+    k_fill_u16<<<592, 256, 0, st>>>(C.plit.as<u16>(), (u64)ns * 131072, 2048);
+    T.mark(st);                                                                   // 1
+    u32 launches = 1;
+    // ---- analyzer, static plan, filters
+    k_analyze<<<(nblk + kAnWarps - 1) / kAnWarps, kAnWarps * 32, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), nblk, C.d_AT,
+                                                                           C.binfo.as<u32>(), C.bbpb.as<u32>(), C.taildlt.as<u32>());
+    T.mark(st);                                                                   // 2
+    u32 *d_nruns = C.counters.as<u32>();
+    u32 *d_queue = C.counters.as<u32>() + 1;
+    k_plan<<<(nseg + 127) / 128, 128, 0, st>>>(C.segdesc.as<SegDesc>(), nseg, C.binfo.as<u32>(), C.planscratch.as<FilterRun>(),
+                                               C.runs.as<GRun>(), d_nruns);
+    k_filter_runs<<<(nblk + 63) / 64, 64, 0, st>>>(C.lz.as<u8>(), C.tmp.as<u8>(), C.runs.as<GRun>(), d_nruns, C.d_DT, C.dictok.as<u8>());
+    T.mark(st);                                                                   // 3
+    launches += 3;
+    // ---- match finder precomputation
+    k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), key_shift,
+                                           C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>());
+    T.mark(st);                                                                   // 4
+    cub::DeviceRadixSort::SortPairs(C.cubtmp.p, cub_bytes, C.keys0.as<u64>(), C.keys1.as<u64>(), C.vals0.as<u32>(), C.vals1.as<u32>(),
+                                    (int)npos, 0, end_bit, st);
+    T.mark(st);                                                                   // 5
+    k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(C.keys1.as<u64>(), C.vals1.as<u32>(), npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(),
+                                                  C.P6.as<u32>());
+    T.mark(st);                                                                   // 6
+    k_mf_extend<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
+                                             C.L6.as<u16>());
+    T.mark(st);                                                                   // 7
+    launches += 3 + (u32)((end_bit + 7) / 8) * 2 + 1;
+    if (g_dump.on && ns == 1) {
+        CK(cudaStreamSynchronize(st));
+        u32 n1 = jobs[0]->n;
+        CK(cudaMemcpy(g_dump.binfo, C.binfo.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_dump.bbpb, C.bbpb.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_dump.lz, C.lz.p, n1, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_dump.P6, C.P6.p, (size_t)n1 * K * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_dump.L6, C.L6.p, (size_t)n1 * K * 2, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_dump.Z2, C.Z2.p, (size_t)(n1 + 31) / 32 * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_dump.Z6, C.Z6.p, (size_t)(n1 + 31) / 32 * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_dump.dict_ok, C.dictok.p, nblk, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(g_dump.tail_dlt, C.taildlt.p, (size_t)nseg * 5 * 4, cudaMemcpyDeviceToHost));
+    }
+    // ---- serial engines, one stream per warp
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, C.dev);
+    u32 grid = std::min<u32>((ns + kEncWarps - 1) / kEncWarps, (u32)nsm * 8);
+    k_encode<<<grid, kEncWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns, d_queue, C.d_p2bits);
+    T.mark(st);                                                                   // 8
+    launches += 1;
+    CK(cudaGetLastError());
+    // ---- results
+    if (C.h_segout.ensure((size_t)nseg * sizeof(SegOut)) || C.h_status.ensure((size_t)ns * 4) || C.h_ev.ensure(evtot + 16)) return kErrCuda;
+    CK(cudaMemcpyAsync(C.h_segout.p, C.segout.p, (size_t)nseg * sizeof(SegOut), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(C.h_status.p, C.status.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(C.h_ev.p, C.ev.p, evtot, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const SegOut *hso = C.h_segout.as<SegOut>();
+    const i32 *hst = C.h_status.as<i32>();
+    std::vector<u32> rcn(ns, 0), bcn(ns, 0), hrcoff(ns), hbcoff(ns);
+    size_t hrc = 0, hbc = 0;
+    int ret = 0;
+    for (u32 s = 0; s < ns; s++) {
+        EncJob &J = *jobs[s];
+        J.status = hst[s];
+        if (J.status < 0) { ret = J.status; continue; }
+        u32 nsg = (u32)J.segs.size();
+        J.so.assign(hso + seg0[s], hso + seg0[s] + nsg);
+        if (nsg) {
+            rcn[s] = J.so[nsg - 1].rc_off + J.so[nsg - 1].rc_len;
+            bcn[s] = J.so[nsg - 1].bc_off + J.so[nsg - 1].bc_len;
+        }
+        hrcoff[s] = (u32)hrc; hbcoff[s] = (u32)hbc;
+        hrc += align_up(rcn[s], 16); hbc += align_up(bcn[s], 16);
+    }
+    if (C.h_rc.ensure(hrc + 16) || C.h_bc.ensure(hbc + 16)) return kErrCuda;
+    for (u32 s = 0; s < ns; s++) {
+        if (jobs[s]->status < 0) continue;
+        if (rcn[s]) CK(cudaMemcpyAsync(C.h_rc.as<u8>() + hrcoff[s], C.rc.as<u8>() + rcoff[s], rcn[s], cudaMemcpyDeviceToHost, st));
+        if (bcn[s]) CK(cudaMemcpyAsync(C.h_bc.as<u8>() + hbcoff[s], C.bc.as<u8>() + bcoff[s], bcn[s], cudaMemcpyDeviceToHost, st));
+        jobs[s]->rc = C.h_rc.as<u8>() + hrcoff[s];
+        jobs[s]->bc = C.h_bc.as<u8>() + hbcoff[s];
+        jobs[s]->ev = C.h_ev.as<u8>() + evoff[s];
+    }
+    T.mark(st);                                                                   // 9
+    CK(cudaStreamSynchronize(st));
+    CSCB200_Stats &S = C.stats;
+    S.ms_h2d += T.ms(0, 1); S.ms_analyze += T.ms(1, 2); S.ms_filters += T.ms(2, 3); S.ms_mf_hash += T.ms(3, 4);
+    S.ms_mf_sort += T.ms(4, 5); S.ms_mf_rows += T.ms(5, 6); S.ms_mf_extend += T.ms(6, 7); S.ms_encode += T.ms(7, 8);
+    S.ms_d2h += T.ms(8, 9); S.ms_total_gpu += T.ms(0, 9);
+    S.kernel_launches += launches; S.streams += ns; S.waves += 1;
+    return ret;
+}
+
+// frame one encoded job through `sink`
+template <class Sink> void frame_job(EncJob &J, Framer &fr, Sink &sink) {
+    for (size_t s = 0; s < J.so.size(); s++) {
+        const SegOut &o = J.so[s];
+        fr.segment(sink, const_cast<u8 *>(J.rc) + o.rc_off, o.rc_len, J.bc + o.bc_off, o.bc_len, J.ev + o.ev_off, o.ev_len);
+    }
+}
+
+size_t per_stream_bytes() { return 81920 * 4 + 131072 * 2 + (kApLimit + 2) * sizeof(ApUnit) + 140000 * 2 + 4096; }
+size_t per_pos_bytes(u32 K) { return 2 + 24 + 6 * (size_t)K + 1 + 3; }
+
+// ----------------------------------------------------------------------------- decode
+struct DecJob {
+    const u8 *in; size_t n;        // stream incl. 10-byte props
+    u8 *out; size_t out_cap;
+    size_t out_size;
+    int status;
+    CSCProps props;
+    DecInput di;
+    std::vector<DecRun> runs;      // filled when want_runs
+};
+
+int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
+    const u32 ns = (u32)jobs.size();
+    if (!ns) return 0;
+    cudaStream_t st = C.st;
+    std::vector<size_t> woff(ns), rcoff(ns), bcoff(ns), offoff(ns), runoff(ns);
+    std::vector<u32> runcap(ns);
+    size_t wtot = 0, rctot = 0, offtot = 0, runtot = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (u32 s = 0; s < ns; s++) {
+        DecJob &J = *jobs[s];
+        J.status = 0; J.out_size = 0;
+        if (J.n < CSC_PROP_SIZE) { J.status = -1; return -1; }
+        memset(&J.props, 0, sizeof(J.props));
+        read_props(&J.props, J.in);
+        if (J.props.dict_size > 1024u * 1048576u || J.props.dict_size < 32 * 1024 || !J.props.csc_blocksize) { J.status = -1; return -1; }
+        if (deframe(J.in + CSC_PROP_SIZE, J.n - CSC_PROP_SIZE, J.props.csc_blocksize, J.di) < 0) { J.status = -1; return -1; }
+        if (J.di.rc_off.size() < 2 || J.di.bc_off.size() < 2) { J.status = -1; return -1; }
+        woff[s] = wtot; wtot = align_up(wtot + J.out_cap + 64, 256);
+        rcoff[s] = rctot; rctot = align_up(rctot + J.di.rc.size(), 16);
+        bcoff[s] = rctot; rctot = align_up(rctot + J.di.bc.size(), 16);
+        offoff[s] = offtot; offtot += J.di.rc_off.size() + J.di.bc_off.size();
+        runcap[s] = (u32)(J.out_cap / 4096 + 64);
+        runoff[s] = runtot; runtot += runcap[s];
+    }
+    double ms_deframe = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    int r = 0;
+    r |= C.dwnd.ensure(wtot + 256); r |= C.dout.ensure(wtot + 256); r |= C.rc.ensure(rctot + 64);
+    r |= C.doffs.ensure(offtot * 4 + 16); r |= C.druns.ensure(runtot * sizeof(DecRun));
+    r |= C.plit.ensure((size_t)ns * 131072 * 2); r |= C.dmeta.ensure((size_t)ns * 16);
+    r |= C.streams.ensure((size_t)ns * sizeof(DecStream)); r |= C.counters.ensure(64); r |= C.doutptr.ensure((size_t)ns * 8);
+    if (r) return kErrCuda;
+    std::vector<DecStream> ds(ns);
+    std::vector<u8 *> outp(ns);
+    std::vector<u32> offs(offtot);
+    for (u32 s = 0; s < ns; s++) {
+        DecJob &J = *jobs[s];
+        DecStream &D = ds[s];
+        memset(&D, 0, sizeof(D));
+        D.wnd_size = (u32)J.props.dict_size; D.raw_blocksize = J.props.raw_blocksize;
+        D.rc = C.rc.as<u8>() + rcoff[s]; D.rc_len = (u32)J.di.rc.size() - 16;
+        D.bc = C.rc.as<u8>() + bcoff[s]; D.bc_len = (u32)J.di.bc.size() - 16;
+        memcpy(&offs[offoff[s]], J.di.rc_off.data(), J.di.rc_off.size() * 4);
+        memcpy(&offs[offoff[s] + J.di.rc_off.size()], J.di.bc_off.data(), J.di.bc_off.size() * 4);
+        D.rc_blk_off = C.doffs.as<u32>() + offoff[s]; D.n_rc_blk = (u32)J.di.rc_off.size() - 1;
+        D.bc_blk_off = D.rc_blk_off + J.di.rc_off.size(); D.n_bc_blk = (u32)J.di.bc_off.size() - 1;
+        D.wnd = C.dwnd.as<u8>() + woff[s]; D.out_cap = (u32)J.out_cap;
+        D.p_lit = C.plit.as<u16>() + (size_t)s * 131072; D.p_delta = D.p_lit + 65536;
+        D.runs = C.druns.as<DecRun>() + runoff[s]; D.runs_cap = runcap[s];
+        u32 *meta = C.dmeta.as<u32>() + (size_t)s * 4;
+        D.n_runs = meta; D.out_len = meta + 1; D.status = (i32 *)(meta + 2);
+        outp[s] = C.dout.as<u8>() + woff[s];
+    }
+    Timer &T = C.tm;
+    T.n = 0;
+    T.mark(st);                                                                   // 0
+    for (u32 s = 0; s < ns; s++) {
+        DecJob &J = *jobs[s];
+        CK(cudaMemcpyAsync(C.rc.as<u8>() + rcoff[s], J.di.rc.data(), J.di.rc.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(C.rc.as<u8>() + bcoff[s], J.di.bc.data(), J.di.bc.size(), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(C.doffs.p, offs.data(), offtot * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.streams.p, ds.data(), (size_t)ns * sizeof(DecStream), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.doutptr.p, outp.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(C.dmeta.p, 0, (size_t)ns * 16, st));
+    CK(cudaMemsetAsync(C.counters.p, 0, 64, st));
+    k_fill_u16<<<592, 256, 0, st>>>(C.plit.as<u16>(), (u64)ns * 131072, 2048);
+    T.mark(st);                                                                   // 1
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, C.dev);
+    u32 grid = std::min<u32>((ns + kDecWarps - 1) / kDecWarps, (u32)nsm * 8);
+    k_decode<<<grid, kDecWarps * 32, 0, st>>>(C.streams.as<DecStream>(), ns, C.counters.as<u32>() + 1);
+    T.mark(st);                                                                   // 2
+    CK(cudaMemcpyAsync(C.dout.p, C.dwnd.p, wtot, cudaMemcpyDeviceToDevice, st));
+    u32 max_runs = *std::max_element(runcap.begin(), runcap.end());
+    u64 nthreads = (u64)ns * max_runs;
+    k_unfilter<<<(u32)((nthreads + 127) / 128), 128, 0, st>>>(C.streams.as<DecStream>(), ns, max_runs, C.doutptr.as<u8 *>(), C.d_DT);
+    T.mark(st);                                                                   // 3
+    CK(cudaGetLastError());
+    if (C.h_meta.ensure((size_t)ns * 16)) return kErrCuda;
+    CK(cudaMemcpyAsync(C.h_meta.p, C.dmeta.p, (size_t)ns * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const u32 *hm = C.h_meta.as<u32>();
+    int ret = 0;
+    for (u32 s = 0; s < ns; s++) {
+        DecJob &J = *jobs[s];
+        J.status = (i32)hm[s * 4 + 2];
+        if (J.status < 0) { ret = J.status; continue; }
+        J.out_size = hm[s * 4 + 1];
+        if (J.out_size) CK(cudaMemcpyAsync(J.out, C.dout.as<u8>() + woff[s], J.out_size, cudaMemcpyDeviceToHost, st));
+        if (want_runs) {
+            J.runs.resize(hm[s * 4]);
+            if (!J.runs.empty())
+                CK(cudaMemcpyAsync(J.runs.data(), C.druns.as<DecRun>() + runoff[s], J.runs.size() * sizeof(DecRun), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    T.mark(st);                                                                   // 4
+    CK(cudaStreamSynchronize(st));
+    CSCB200_Stats &S = C.stats;
+    S.ms_h2d += T.ms(0, 1); S.ms_decode += T.ms(1, 2); S.ms_unfilter += T.ms(2, 3); S.ms_d2h += T.ms(3, 4);
+    S.ms_total_gpu += T.ms(0, 4); S.ms_frame += ms_deframe;
+    S.kernel_launches += 3; S.streams += ns; S.waves += 1;
+    return ret;
+}
+
+size_t mem_budget() {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)8 << 30;
+    return tot - tot / 8;   // buffers are cached in the context, so budget against the whole device
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+// tests only: capture the intermediate arrays of the next single-stream encode
+void CSCB200_DebugDump(uint32_t *binfo, uint32_t *bbpb, uint8_t *lz, uint32_t *P6, uint16_t *L6, uint32_t *Z2, uint32_t *Z6,
+                       uint8_t *dict_ok, uint32_t *tail_dlt) {
+    g_dump.binfo = binfo; g_dump.bbpb = bbpb; g_dump.lz = lz; g_dump.P6 = P6; g_dump.L6 = L6; g_dump.Z2 = Z2; g_dump.Z6 = Z6;
+    g_dump.dict_ok = dict_ok; g_dump.tail_dlt = tail_dlt; g_dump.on = binfo != nullptr;
+}
+
+int CSCB200_Available(void) {
+    int n = 0;
+    return (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
+}
+int CSCB200_SetDevice(int device) {
+    g_device = device;
+    if (g_ctx.init && g_ctx.dev != device) return kErrUnsupported;   // context already bound on this thread
+    return 0;
+}
+void CSCB200_GetStats(CSCB200_Stats *out) { *out = g_ctx.stats; }
+
+size_t CSCB200_EncodeBound(size_t n) { return n + n / 4 + (n / 65536 + 8) * 8 + 256; }
+
+int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
+                         int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size) {
+    Ctx &C = g_ctx;
+    if (ctx_init(C)) return kErrCuda;
+    memset(&C.stats, 0, sizeof(C.stats));
+    if (n <= 0) return 0;
+    std::vector<EncJob> jobs(n);
+    for (int i = 0; i < n; i++) {
+        EncJob &J = jobs[i];
+        if (in_size[i] >= 0xF0000000ull) return kErrUnsupported;
+        J.in = in[i]; J.n = (u32)in_size[i]; J.status = 0; J.rc = J.bc = J.ev = nullptr;
+        uint32_t d = (uint64_t)dict_size > in_size[i] ? (uint32_t)in_size[i] : dict_size;   // csa_worker.cpp:35
+        props_init(&J.props, d, level);
+        J.props.DLTFilter = flt_mask & 1; J.props.TXTFilter = (flt_mask >> 1) & 1; J.props.EXEFilter = (flt_mask >> 2) & 1;
+        for (u32 a = 0; a < J.n; a += J.props.raw_blocksize) J.segs.push_back(std::min<u32>(J.props.raw_blocksize, J.n - a));
+        C.stats.bytes_in += J.n;
+    }
+    // waves: as many streams as fit the memory budget (largest first inside a wave for balance)
+    const size_t budget = mem_budget();
+    const u32 K = jobs[0].props.hash_width;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    int ret = 0;
+    size_t at = 0;
+    while (at < order.size()) {
+        std::vector<EncJob *> wave;
+        size_t bytes = 0, pos = 0;
+        while (at < order.size()) {
+            EncJob &J = jobs[order[at]];
+            size_t need = per_stream_bytes() + (size_t)J.n * per_pos_bytes(K) + 4096;
+            if (!wave.empty() && (bytes + need > budget || pos + J.n > 0x70000000ull)) break;
+            bytes += need; pos += J.n;
+            if (J.n) wave.push_back(&J);
+            at++;
+        }
+        std::stable_sort(wave.begin(), wave.end(), [](const EncJob *a, const EncJob *b) { return a->n > b->n; });
+        int r = encode_wave(C, wave);
+        if (r < 0) { ret = r; break; }
+        auto t0 = std::chrono::steady_clock::now();
+        for (EncJob *J : wave) {
+            size_t i = J - jobs.data();
+            MemSink sink{out[i], out_cap[i], 0, false};
+            if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&J->props, hdr); sink(hdr, CSC_PROP_SIZE); }
+            Framer fr(J->props.csc_blocksize);
+            frame_job(*J, fr, sink);
+            fr.eof(sink);
+            out_size[i] = sink.off;
+            if (sink.overflow) ret = kErrOverflow;
+            C.stats.bytes_out += sink.off;
+        }
+        C.stats.ms_frame += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (ret < 0) return ret;
+    for (int i = 0; i < n; i++) {
+        if (jobs[i].n) continue;   // empty chunk: header + EOF segment only
+        MemSink sink{out[i], out_cap[i], 0, false};
+        if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&jobs[i].props, hdr); sink(hdr, CSC_PROP_SIZE); }
+        Framer fr(jobs[i].props.csc_blocksize);
+        fr.eof(sink);
+        out_size[i] = sink.off;
+        if (sink.overflow) ret = kErrOverflow;
+    }
+    return ret;
+}
+
+int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out, const size_t *out_cap,
+                         size_t *out_size) {
+    Ctx &C = g_ctx;
+    if (ctx_init(C)) return kErrCuda;
+    memset(&C.stats, 0, sizeof(C.stats));
+    if (n <= 0) return 0;
+    std::vector<DecJob> jobs(n);
+    for (int i = 0; i < n; i++) {
+        jobs[i].in = in[i]; jobs[i].n = in_size[i]; jobs[i].out = out[i]; jobs[i].out_cap = out_cap[i];
+        C.stats.bytes_in += in_size[i];
+    }
+    const size_t budget = mem_budget();
+    int ret = 0;
+    size_t at = 0;
+    while (at < jobs.size()) {
+        std::vector<DecJob *> wave;
+        size_t bytes = 0;
+        while (at < jobs.size()) {
+            size_t need = jobs[at].out_cap * 2 + jobs[at].n + 131072 * 2 + jobs[at].out_cap / 256 + 8192;
+            if (!wave.empty() && bytes + need > budget) break;
+            bytes += need;
+            wave.push_back(&jobs[at]);
+            at++;
+        }
+        int r = decode_wave(C, wave, false);
+        if (r < 0) { ret = r; break; }
+    }
+    for (int i = 0; i < n; i++) { out_size[i] = jobs[i].out_size; C.stats.bytes_out += jobs[i].out_size; }
+    return ret;
+}
+
+// ------------------------------------------------------------------- libcsc handle API
+struct EncHandle {
+    CSCProps props;
+    ISeqOutStream *os;
+    Framer *fr;
+    bool used;
+    uint64_t outsize;
+};
+
+void CSCEncProps_Init(CSCProps *p, uint32_t dict_size, int level) { props_init(p, dict_size, level); }
+void CSCEnc_WriteProperties(const CSCProps *props, uint8_t *s, int full) { (void)full; write_props(props, s); }
+uint64_t CSCEnc_EstMemUsage(const CSCProps *p) { return est_mem_usage(p); }
+
+CSCEncHandle CSCEnc_Create(const CSCProps *props, ISeqOutStream *outstream, ISzAlloc *alloc) {
+    (void)alloc;   // device memory is managed by the library; host scratch uses the C++ heap
+    if (ctx_init(g_ctx)) return NULL;
+    EncHandle *h = new (std::nothrow) EncHandle;
+    if (!h) return NULL;
+    h->props = *props; h->os = outstream; h->used = false; h->outsize = 0;
+    h->fr = new Framer(props->csc_blocksize);
+    return h;
+}
+void CSCEnc_Destroy(CSCEncHandle p) {
+    EncHandle *h = (EncHandle *)p;
+    if (!h) return;
+    delete h->fr;
+    delete h;
+}
+
+struct CbSink {
+    ISeqOutStream *os; bool fail; uint64_t payload;
+    void operator()(const u8 *d, u32 n) {
+        if (fail || !n) return;
+        if (os->Write(os, d, n) != n) fail = true;
+    }
+};
+
+int CSCEnc_Encode(CSCEncHandle p, ISeqInStream *is, ICompressProgress *progress) {
+    EncHandle *h = (EncHandle *)p;
+    Ctx &C = g_ctx;
+    if (ctx_init(C)) return kErrCuda;
+    // pull the whole input, one Read() of raw_blocksize per flush segment (csc_enc.cpp:169-176)
+    std::vector<u8> data;
+    EncJob J;
+    J.props = h->props; J.status = 0;
+    uint64_t insize = 0;
+    for (;;) {
+        size_t want = h->props.raw_blocksize;
+        size_t old = data.size();
+        data.resize(old + want);
+        size_t got = want;
+        int rr = is->Read(is, data.data() + old, &got);
+        if (rr < 0) return READ_ERROR;
+        data.resize(old + got);
+        if (!got) break;
+        J.segs.push_back((u32)got);
+        insize += got;
+        if (progress) progress->Progress(progress, insize, h->outsize);
+        if (data.size() >= 0xF0000000ull) return kErrUnsupported;
+    }
+    if (data.empty()) return 0;
+    if (h->used) return kErrUnsupported;   // one data-carrying Encode per handle in this version
+    h->used = true;
+    J.in = data.data(); J.n = (u32)data.size();
+    memset(&C.stats, 0, sizeof(C.stats));
+    std::vector<EncJob *> wave{&J};
+    int r = encode_wave(C, wave);
+    if (r < 0) return r;
+    CbSink sink{h->os, false, 0};
+    frame_job(J, *h->fr, sink);
+    for (const SegOut &o : J.so) h->outsize += o.rc_len + o.bc_len;
+    if (progress) progress->Progress(progress, insize, h->outsize);
+    return sink.fail ? WRITE_ERROR : 0;
+}
+
+int CSCEnc_Encode_Flush(CSCEncHandle p) {
+    EncHandle *h = (EncHandle *)p;
+    CbSink sink{h->os, false, 0};
+    h->fr->eof(sink);
+    return sink.fail ? WRITE_ERROR : 0;
+}
+
+struct DecHandle {
+    CSCProps props;
+    ISeqInStream *is;
+};
+
+void CSCDec_ReadProperties(CSCProps *props, uint8_t *s) { read_props(props, s); }
+
+CSCDecHandle CSCDec_Create(const CSCProps *props, ISeqInStream *instream, ISzAlloc *alloc) {
+    (void)alloc;
+    if (props->dict_size > 1024u * 1048576u || props->dict_size < 32 * 1024) return NULL;
+    if (ctx_init(g_ctx)) return NULL;
+    DecHandle *h = new (std::nothrow) DecHandle;
+    if (!h) return NULL;
+    h->props = *props; h->is = instream;
+    return h;
+}
+void CSCDec_Destroy(CSCDecHandle p) { delete (DecHandle *)p; }
+
+int CSCDec_Decode(CSCDecHandle p, ISeqOutStream *os, ICompressProgress *progress) {
+    DecHandle *h = (DecHandle *)p;
+    Ctx &C = g_ctx;
+    if (ctx_init(C)) return kErrCuda;
+    // the compressed stream is pulled to its end, then decoded on the device in one go
+    std::vector<u8> comp(CSC_PROP_SIZE);
+    write_props(&h->props, comp.data());
+    for (;;) {
+        size_t want = 1 << 20, old = comp.size();
+        comp.resize(old + want);
+        size_t got = want;
+        int rr = h->is->Read(h->is, comp.data() + old, &got);
+        comp.resize(old + (rr < 0 ? 0 : got));
+        if (rr < 0) return READ_ERROR;
+        if (!got) break;
+    }
+    memset(&C.stats, 0, sizeof(C.stats));
+    size_t cap = std::max<size_t>(comp.size() * 8, (size_t)16 << 20);
+    std::vector<u8> out;
+    DecJob J;
+    for (;;) {
+        out.resize(cap);
+        J = DecJob();
+        J.in = comp.data(); J.n = comp.size(); J.out = out.data(); J.out_cap = cap;
+        std::vector<DecJob *> wave{&J};
+        int r = decode_wave(C, wave, true);
+        if (r == kErrOverflow && cap < ((size_t)3 << 30)) { cap *= 4; continue; }   // raw size is not in the stream: grow and redo
+        if (r < 0) return r;
+        break;
+    }
+    uint64_t done = 0;
+    for (const DecRun &rn : J.runs) {   // one Write per decoded run, as CSCDec_Decode does (csc_dec.cpp:767)
+        if (!rn.size) continue;
+        done += rn.size;
+        if (progress) progress->Progress(progress, comp.size(), done);
+        size_t w = os->Write(os, out.data() + rn.off, rn.size);
+        if (w == CSC_WRITE_ABORT) break;
+        if (w < rn.size) return WRITE_ERROR;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+/* csc_b200.h -- additive batched entry points of the B200 libcsc library.
+ *
+ * One libcsc handle is one serially dependent stream, so a GPU
+ * is only used well when many independent streams are in flight: exactly the
+ * units csarc creates with its -p / -t task split (archiver/csarc.cpp:532-543,
+ * one CSCEnc/CSCDec handle per task in archiver/csa_worker.cpp:23-90).  These
+ * calls take many chunks at once and produce, per chunk, EXACTLY the bytes the
+ * per-handle API (csc_enc.h / csc_dec.h) produces -- they are additive, plain
+ * C-ABI (pointers and sizes, no CUDA or torch types), and never touch CSCProps'
+ * layout.  Host buffers may be pageable or pinned; device selection is by
+ * CSCB200_SetDevice (default: current CUDA device).
+ */
+#ifndef _CSC_B200_H_
+#define _CSC_B200_H_
+#include "csc_common.h"
+
+EXTERN_C_BEGIN
+
+/* Worst-case size of one encoded chunk (props header included). */
+size_t CSCB200_EncodeBound(size_t in_size);
+
+/* Encode n independent chunks.  Chunk i is coded exactly like
+ *   CSCEncProps_Init(&p, min(dict_size, in_size[i]), level);      (csa_worker.cpp:35)
+ *   [p.DLTFilter/TXTFilter/EXEFilter from flt_mask bits 0/1/2]
+ *   CSCEnc_WriteProperties (if with_props) ; CSCEnc_Encode with Read() == p.raw_blocksize ;
+ *   CSCEnc_Encode_Flush.
+ * out[i] receives out_size[i] <= out_cap[i] bytes.  Returns 0 or a negative code
+ * (READ_ERROR/WRITE_ERROR family, -90 output overflow, -91 unsupported, -92 CUDA failure). */
+int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level,
+                         int flt_mask, int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size);
+
+/* Decode n independent libcsc streams (each starting with its 10-byte props header), the
+ * counterpart of one CSCDec handle per task (csa_worker.cpp:59-90). */
+int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out,
+                         const size_t *out_cap, size_t *out_size);
+
+/* Device-resident variants used by the benchmark's kernel-only timing: same work, but the
+ * chunk payloads are already in HBM (d_in / d_out are device pointers). */
+int CSCB200_SetDevice(int device);
+
+/* Timing / launch statistics of the last Encode/Decode call on this thread's context. */
+typedef struct {
+    double ms_h2d, ms_analyze, ms_filters, ms_mf_hash, ms_mf_sort, ms_mf_rows, ms_mf_extend, ms_encode, ms_d2h,
+        ms_frame, ms_decode, ms_unfilter, ms_total_gpu;
+    uint64_t bytes_in, bytes_out, mf_positions;
+    uint32_t kernel_launches, streams, waves;
+} CSCB200_Stats;
+void CSCB200_GetStats(CSCB200_Stats *out);
+
+/* 1 if a CUDA device is usable, else 0 (the library has no CPU fallback). */
+int CSCB200_Available(void);
+
+EXTERN_C_END
+#endif

@@ -65,7 +65,17 @@ void build_mf_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, u32 bits, u3
 
 }  // namespace
 
+struct StageDump { u32 *binfo, *bbpb; u8 *lz; u32 *P6; u16 *L6; u32 *Z2, *Z6; u8 *dict_ok; u32 *tail_dlt; bool on; };
+static StageDump g_dump = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false};
+
 extern "C" {
+
+// capture the intermediate arrays of the next hs_encode (compared with the GPU's in tests)
+void hs_debug_dump(uint32_t *binfo, uint32_t *bbpb, uint8_t *lz, uint32_t *P6, uint16_t *L6, uint32_t *Z2, uint32_t *Z6,
+                   uint8_t *dict_ok, uint32_t *tail_dlt) {
+    g_dump.binfo = binfo; g_dump.bbpb = bbpb; g_dump.lz = lz; g_dump.P6 = P6; g_dump.L6 = L6; g_dump.Z2 = Z2; g_dump.Z6 = Z6;
+    g_dump.dict_ok = dict_ok; g_dump.tail_dlt = tail_dlt; g_dump.on = binfo != nullptr;
+}
 
 // Whole stream through the host-simulated product path. Same contract as oracle ref_encode.
 // trace: optional (kind,a,b) triples; returns 0 or negative.
@@ -125,6 +135,13 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         std::vector<u16> L6;
         u32 K = cfg.ht_width;
         build_mf_cpu(lz.data(), n, seg, cfg.ht_bits, K, P6, L6, Z2, Z6);
+        if (g_dump.on) {
+            memcpy(g_dump.binfo, binfo.data(), nblk * 4); memcpy(g_dump.bbpb, bbpb.data(), nblk * 4);
+            memcpy(g_dump.lz, lz.data(), n); memcpy(g_dump.P6, P6.data(), (size_t)n * K * 4);
+            memcpy(g_dump.L6, L6.data(), (size_t)n * K * 2); memcpy(g_dump.Z2, Z2.data(), (size_t)(n + 31) / 32 * 4);
+            memcpy(g_dump.Z6, Z6.data(), (size_t)(n + 31) / 32 * 4); memcpy(g_dump.dict_ok, dict_ok.data(), nblk);
+            memcpy(g_dump.tail_dlt, tail_dlt.data(), seg.size() * 5 * 4);
+        }
         std::vector<u32> D6((n + 31) / 32 + 1, 0), ht2(16384, 0), ht3(65536, 0);
         std::vector<u16> p_lit(65536, 2048), p_delta(65536, 2048);
         std::vector<ApUnit> ap(kApLimit + 2);

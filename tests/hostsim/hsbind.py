@@ -93,3 +93,33 @@ def props(dict_size, level):
     k = ["dict_size", "csc_blocksize", "raw_blocksize", "hash_bits", "hash_width", "bt_hash_bits", "bt_size",
          "bt_cyc", "good_len", "lz_mode", "DLTFilter", "TXTFilter", "EXEFilter", "est_mem", "sizeof"]
     return {kk: int(v) for kk, v in zip(k, o)}
+
+
+class Stages:
+    """Intermediate arrays of one single-stream encode (analyzer, filters, match-finder rows)."""
+
+    def __init__(self, n, K):
+        nblk = (n + 8191) // 8192 + 4
+        self.binfo = np.zeros(nblk, np.uint32); self.bbpb = np.zeros(nblk, np.uint32)
+        self.lz = np.zeros(n + 64, np.uint8); self.P6 = np.zeros(n * K + 8, np.uint32); self.L6 = np.zeros(n * K + 8, np.uint16)
+        self.Z2 = np.zeros((n + 31) // 32 + 2, np.uint32); self.Z6 = np.zeros((n + 31) // 32 + 2, np.uint32)
+        self.dict_ok = np.zeros(nblk, np.uint8); self.tail_dlt = np.zeros(64 * 5, np.uint32)
+
+    def ptrs(self):
+        return [a.ctypes.data for a in (self.binfo, self.bbpb, self.lz, self.P6, self.L6, self.Z2, self.Z6, self.dict_ok,
+                                        self.tail_dlt)]
+
+
+def encode_stages(data, dict_size, level):
+    """hostsim encode + its intermediate arrays."""
+    a = _u8(data)
+    K = props(dict_size, level)["hash_width"]
+    st = Stages(a.size, max(K, 1))
+    l = lib()
+    l.hs_debug_dump.argtypes = [C.c_void_p] * 9
+    l.hs_debug_dump(*st.ptrs())
+    try:
+        out = encode(a, dict_size, level)
+    finally:
+        l.hs_debug_dump(*([None] * 9))
+    return out, st
