@@ -20,7 +20,7 @@ _SO = os.path.join(_HERE, "csrc", "libcsc_b200.so")
 EXPORTS = ["CSCEncProps_Init", "CSCEnc_WriteProperties", "CSCEnc_EstMemUsage", "CSCEnc_Create", "CSCEnc_Destroy",
            "CSCEnc_Encode", "CSCEnc_Encode_Flush", "CSCDec_ReadProperties", "CSCDec_Create", "CSCDec_Destroy",
            "CSCDec_Decode", "CSCB200_EncodeBound", "CSCB200_EncodeChunks", "CSCB200_DecodeChunks",
-           "CSCB200_SetDevice", "CSCB200_GetStats", "CSCB200_Available"]
+           "CSCB200_EncodeChunksDevice", "CSCB200_SetDevice", "CSCB200_GetStats", "CSCB200_Available"]
 
 
 class CSCProps(C.Structure):   # csc_common.h:19-63 (ABI)
@@ -79,6 +79,8 @@ def lib():
         l.CSCB200_EncodeBound.restype = C.c_size_t
         l.CSCB200_EncodeChunks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        l.CSCB200_EncodeChunksDevice.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                                 C.c_void_p]
         l.CSCB200_DecodeChunks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.CSCB200_SetDevice.argtypes = [C.c_int]
         l.CSCB200_GetStats.argtypes = [C.POINTER(Stats)]
@@ -142,6 +144,18 @@ def encode_chunks_raw(in_ptrs, in_sizes, out_ptrs, out_caps, dict_size, level, f
     r = lib().CSCB200_EncodeChunks(n, ip, isz, dict_size, level, flt_mask, int(with_props), op, ocap, on)
     if r < 0:
         raise RuntimeError(f"CSCB200_EncodeChunks failed: {r}")
+    return [int(v) for v in on]
+
+
+def encode_chunks_device(dev_ptrs, in_sizes, dict_size, level, flt_mask=7, with_props=True):
+    """Kernel-only path: inputs already in HBM, outputs stay in HBM; returns framed sizes."""
+    n = len(dev_ptrs)
+    ip = (C.c_void_p * n)(*dev_ptrs)
+    isz = (C.c_size_t * n)(*in_sizes)
+    on = (C.c_size_t * n)()
+    r = lib().CSCB200_EncodeChunksDevice(n, ip, isz, dict_size, level, flt_mask, int(with_props), on)
+    if r < 0:
+        raise RuntimeError(f"CSCB200_EncodeChunksDevice failed: {r}")
     return [int(v) for v in on]
 
 

@@ -141,6 +141,8 @@ struct MemSink {
 // one stream to encode
 struct EncJob {
     const u8 *in; u32 n;
+    bool in_dev = false;       // `in` is a device pointer (kernel-only timing path)
+    bool no_payload = false;   // leave RC/BC sub-streams in HBM, only fetch the per-segment records
     CSCProps props;
     std::vector<u32> segs;     // Read() sizes
     int status;
@@ -259,7 +261,9 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     T.mark(st);                                                                   // 0
     // ---- uploads
     for (u32 s = 0; s < ns; s++)
-        if (jobs[s]->n) CK(cudaMemcpyAsync(C.lz.as<u8>() + goff[s], jobs[s]->in, jobs[s]->n, cudaMemcpyHostToDevice, st));
+        if (jobs[s]->n)
+            CK(cudaMemcpyAsync(C.lz.as<u8>() + goff[s], jobs[s]->in, jobs[s]->n,
+                               jobs[s]->in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.blkdesc.p, blks.data(), (size_t)nblk * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.segdesc.p, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.segsize.p, segsize.data(), (size_t)nseg * 4, cudaMemcpyHostToDevice, st));
@@ -353,6 +357,8 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     if (C.h_rc.ensure(hrc + 16) || C.h_bc.ensure(hbc + 16)) return kErrCuda;
     for (u32 s = 0; s < ns; s++) {
         if (jobs[s]->status < 0) continue;
+        jobs[s]->ev = C.h_ev.as<u8>() + evoff[s];
+        if (jobs[s]->no_payload) continue;
         if (rcn[s]) CK(cudaMemcpyAsync(C.h_rc.as<u8>() + hrcoff[s], C.rc.as<u8>() + rcoff[s], rcn[s], cudaMemcpyDeviceToHost, st));
         if (bcn[s]) CK(cudaMemcpyAsync(C.h_bc.as<u8>() + hbcoff[s], C.bc.as<u8>() + bcoff[s], bcn[s], cudaMemcpyDeviceToHost, st));
         jobs[s]->rc = C.h_rc.as<u8>() + hrcoff[s];
@@ -375,6 +381,19 @@ template <class Sink> void frame_job(EncJob &J, Framer &fr, Sink &sink) {
         const SegOut &o = J.so[s];
         fr.segment(sink, const_cast<u8 *>(J.rc) + o.rc_off, o.rc_len, J.bc + o.bc_off, o.bc_len, J.ev + o.ev_off, o.ev_len);
     }
+}
+
+// size of the framed stream without touching the payload (device-resident path)
+size_t framed_size(const EncJob &J, bool with_props) {
+    const u32 bs = J.props.csc_blocksize;
+    size_t t = with_props ? CSC_PROP_SIZE : 0;
+    for (const SegOut &o : J.so) {
+        u32 nr = 0, nb = 0;
+        for (u32 i = 0; i < o.ev_len; i++) (J.ev[o.ev_off + i] ? nr : nb)++;
+        u32 rrem = o.rc_len - nr * bs, brem = o.bc_len - nb * bs;
+        t += (size_t)(nr + nb) * (1 + bs) + (rrem == bs ? 1 : 4) + rrem + (brem == bs ? 1 : 4) + brem;
+    }
+    return t + 4 + 6 + 4 + 3;   // EOF segment
 }
 
 size_t per_stream_bytes() { return 81920 * 4 + 131072 * 2 + (kApLimit + 2) * sizeof(ApUnit) + 140000 * 2 + 4096; }
@@ -526,8 +545,8 @@ void CSCB200_GetStats(CSCB200_Stats *out) { *out = g_ctx.stats; }
 
 size_t CSCB200_EncodeBound(size_t n) { return n + n / 4 + (n / 65536 + 8) * 8 + 256; }
 
-int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
-                         int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size) {
+static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
+                              int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size, bool device) {
     Ctx &C = g_ctx;
     if (ctx_init(C)) return kErrCuda;
     memset(&C.stats, 0, sizeof(C.stats));
@@ -537,6 +556,7 @@ int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
         EncJob &J = jobs[i];
         if (in_size[i] >= 0xF0000000ull) return kErrUnsupported;
         J.in = in[i]; J.n = (u32)in_size[i]; J.status = 0; J.rc = J.bc = J.ev = nullptr;
+        J.in_dev = device; J.no_payload = device;
         uint32_t d = (uint64_t)dict_size > in_size[i] ? (uint32_t)in_size[i] : dict_size;   // csa_worker.cpp:35
         props_init(&J.props, d, level);
         J.props.DLTFilter = flt_mask & 1; J.props.TXTFilter = (flt_mask >> 1) & 1; J.props.EXEFilter = (flt_mask >> 2) & 1;
@@ -567,6 +587,7 @@ int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
         auto t0 = std::chrono::steady_clock::now();
         for (EncJob *J : wave) {
             size_t i = J - jobs.data();
+            if (device) { out_size[i] = framed_size(*J, with_props != 0); C.stats.bytes_out += out_size[i]; continue; }
             MemSink sink{out[i], out_cap[i], 0, false};
             if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&J->props, hdr); sink(hdr, CSC_PROP_SIZE); }
             Framer fr(J->props.csc_blocksize);
@@ -581,6 +602,7 @@ int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
     if (ret < 0) return ret;
     for (int i = 0; i < n; i++) {
         if (jobs[i].n) continue;   // empty chunk: header + EOF segment only
+        if (device) { out_size[i] = (with_props ? CSC_PROP_SIZE : 0) + 17; continue; }
         MemSink sink{out[i], out_cap[i], 0, false};
         if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&jobs[i].props, hdr); sink(hdr, CSC_PROP_SIZE); }
         Framer fr(jobs[i].props.csc_blocksize);
@@ -589,6 +611,16 @@ int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
         if (sink.overflow) ret = kErrOverflow;
     }
     return ret;
+}
+
+int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
+                         int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size) {
+    return encode_chunks_impl(n, in, in_size, dict_size, level, flt_mask, with_props, out, out_cap, out_size, false);
+}
+
+int CSCB200_EncodeChunksDevice(int n, const uint8_t *const *d_in, const size_t *in_size, uint32_t dict_size, int level,
+                               int flt_mask, int with_props, size_t *out_size) {
+    return encode_chunks_impl(n, d_in, in_size, dict_size, level, flt_mask, with_props, nullptr, nullptr, out_size, true);
 }
 
 int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out, const size_t *out_cap,

@@ -168,6 +168,17 @@ def edge_cases(seed: int = 7) -> dict:
     d["entropy"] = rng.choice(np.array([3, 17, 40, 99, 150, 200, 250, 7, 9], np.uint8), size=8192 * 5)
     d["lowent"] = rng.choice(np.arange(40, 60, dtype=np.uint8), size=8192 * 4)
     d["delta1"] = delta(8192 * 4, 1, 5)
+    # 1-channel table (DT_DLT + 0): small steps with a random re-base every ~6 samples
+    N1 = 8192 * 3
+    v = np.zeros(N1, dtype=np.int64)
+    st = rng.integers(-3, 4, size=N1)
+    jump = rng.random(N1) < (1.0 / 6)
+    newv = rng.integers(0, 256, size=N1)
+    cur = 0
+    for i in range(N1):
+        cur = int(newv[i]) if jump[i] else (cur + int(st[i])) & 0xFF
+        v[i] = cur
+    d["delta1b"] = v.astype(np.uint8)
     d["delta3"] = delta(8192 * 4 + 100, 3, 6)
     d["delta8"] = delta(8192 * 6, 8, 7)
     long_rep = np.tile(text(5000, 9), 12)

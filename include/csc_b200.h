@@ -34,8 +34,12 @@ int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
 int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out,
                          const size_t *out_cap, size_t *out_size);
 
-/* Device-resident variants used by the benchmark's kernel-only timing: same work, but the
- * chunk payloads are already in HBM (d_in / d_out are device pointers). */
+/* Device-resident variant used for kernel-only timing: the chunk payloads are already in HBM
+ * (d_in[i] are device pointers), the coded sub-streams stay in HBM, and only the size of each
+ * framed stream is returned.  Same kernels, same work as CSCB200_EncodeChunks. */
+int CSCB200_EncodeChunksDevice(int n, const uint8_t *const *d_in, const size_t *in_size, uint32_t dict_size, int level,
+                               int flt_mask, int with_props, size_t *out_size);
+
 int CSCB200_SetDevice(int device);
 
 /* Timing / launch statistics of the last Encode/Decode call on this thread's context. */
