@@ -83,6 +83,8 @@ struct ModelSmall {
     u16 p_rle_flag;
     u32 len_price[32];
     u32 p2bits[512];      // p_2_bits_ (csc_model.cpp:68-70), host-libm derived
+    u32 row_e[8];         // scratch: candidate row of the current position (lane-gathered)
+    u32 row_l[8];
 };
 
 // per-segment output record written by the encoder engine, read by host framing

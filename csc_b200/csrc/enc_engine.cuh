@@ -322,20 +322,73 @@ struct Encoder {
         }
     }
 
+    // Lane-parallel fetch of the candidate row of x: entry k, its precomputed length and its
+    // liveness bit are read by lane k (one memory round trip for the whole bucket instead of
+    // W dependent ones) and parked in the warp's scratch.  Returns (valid | dead << 8) masks.
+    CSC_HD u32 gather_row(u32 x) {
+        u32 e = kNone, l = 0;
+        bool dead = false;
+        const size_t at = (size_t)x * K;
+#if defined(__CUDA_ARCH__)
+        if (CSC_LANE < K) {
+            e = S.P6[at + CSC_LANE];
+            l = S.L6[at + CSC_LANE];
+            if (e != kNone) dead = dead6(e);
+            M.row_e[CSC_LANE] = e;
+            M.row_l[CSC_LANE] = l;
+        }
+        u32 valid = w_ballot(e != kNone), deadm = w_ballot(dead);
+        w_sync();
+        return valid | (deadm << 8);
+#else
+        u32 valid = 0, deadm = 0;
+        for (u32 k = 0; k < K; k++) {
+            e = S.P6[at + k]; l = S.L6[at + k];
+            dead = (e != kNone) && dead6(e);
+            M.row_e[k] = e; M.row_l[k] = l;
+            if (e != kNone) valid |= 1u << k;
+            if (dead) deadm |= 1u << k;
+        }
+        return valid | (deadm << 8);
+#endif
+    }
+
+    // warm the lines the next find_match(y) will need while the coder is busy with a packet
+    CSC_HD void prefetch_fm(u32 y, u32 sb_end) {
+        if (y >= sb_end) return;
+        if (W) { pf_l2(S.P6 + (size_t)y * K); pf_l2(S.L6 + (size_t)y * K); }
+        pf_l2(S.ht2 + hash2_at(y, sb_end));
+        pf_l2(S.ht3 + hash3_at(y, sb_end));
+        for (int i = 0; i < 4; i++) if (rep[i] < vld && rep[i] <= y) pf_l2(S.lz + y - rep[i]);
+        const u16 *row = S.p_lit + (u32)S.lz[y - (y ? 1 : 0)] * 256;
+        pf_l2(row); pf_l2(row + 64); pf_l2(row + 128); pf_l2(row + 192);
+    }
+
     // find_match (csc_mf.cpp:243-495): candidate list in reference probe order.
     CSC_HD u32 find_match(u32 x, u32 limit, const u32 *rp, Cand *out) {
         const u8 *cur = S.lz + x;
         const u32 pos = vld + x;
         const u32 sb_end = x + limit;
         u32 cnt = 0, minlen = 1, dist = 0;
-        // bound[] of csc_mf.cpp:245
+        // ---- issue every independent load first: tables, candidate row, first probe bytes
+        const u32 h2 = hash2_at(x, sb_end), h3 = hash3_at(x, sb_end);
+        const u32 e2 = g_ld(&S.ht2[h2]), e3 = g_ld(&S.ht3[h3]);
+        const u32 rowm = W ? gather_row(x) : 0;
+        const bool deep = limit > 1;
+        const u32 c1 = deep ? cur[1] : 0;
+        u32 rb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) rb[i] = (deep && rp[i] < vld) ? (cur - rp[i])[1] : 0x100;
+        const u32 d2 = pos - e2, d3 = pos - e3;
+        const u32 t2 = (deep && d2 < vld && x > d2) ? (cur - d2)[1] : 0x100;
+        const u32 t3 = (deep && d3 < vld && x >= d3) ? (cur - d3)[1] : 0x100;
         // rep-distance probes (:266-299)
         for (u32 i = 0; i < 4; i++) {
             u32 rd = rp[i];
             if (rd >= vld) continue;
             if (minlen >= limit) continue;
             const u8 *m = cur - rd;
-            if (m[minlen] != cur[minlen]) continue;
+            if (minlen == 1 ? (rb[i] != c1) : (m[minlen] != cur[minlen])) continue;
             u32 ml = lcp_bytes(cur, m, limit);
             if (ml && i == 0) { out[cnt].len = 1; out[cnt].dist = 1; cnt++; }
             if (ml > minlen) {
@@ -345,14 +398,12 @@ struct Encoder {
             }
         }
         // 2-byte and 3-byte single-slot tables (:303-366)
-        u32 h2 = hash2_at(x, sb_end), h3 = hash3_at(x, sb_end);
-        u32 e2 = g_ld(&S.ht2[h2]), e3 = g_ld(&S.ht3[h3]);
-        if (pos - e2 > dist) {
-            dist = pos - e2;
+        if (d2 > dist) {
+            dist = d2;
             // note `wpos > dist` (:306): a candidate at window offset 0 is dropped, dist stays poisoned
             if (dist < vld && x > dist && minlen < limit) {
                 const u8 *m = cur - dist;
-                if (m[minlen] == cur[minlen]) {
+                if (minlen == 1 ? (t2 == c1) : (m[minlen] == cur[minlen])) {
                     u32 ml = lcp_bytes(cur, m, limit);
                     if (ml > minlen) {
                         minlen = ml;
@@ -364,11 +415,11 @@ struct Encoder {
                 }
             }
         }
-        if (pos - e3 > dist) {
-            dist = pos - e3;
+        if (d3 > dist) {
+            dist = d3;
             if (dist < vld && x >= dist && minlen < limit) {
                 const u8 *m = cur - dist;
-                if (m[minlen] == cur[minlen]) {
+                if (minlen == 1 ? (t3 == c1) : (m[minlen] == cur[minlen])) {
                     u32 ml = lcp_bytes(cur, m, limit);
                     if (ml > minlen) {
                         minlen = ml;
@@ -383,34 +434,51 @@ struct Encoder {
         S.ht2[h2] = pos;
         S.ht3[h3] = pos;
         // 6-byte table of width W (:453-485): first W live entries of the chain
-        if (W) {
-            u32 found = 0, src = x, k = 0;
-            while (found < W) {
-                size_t at = (size_t)src * K + k;
-                u32 e = S.P6[at];
-                if (e == kNone) break;
-                bool inrow = (src == x);
-                if (++k == K) { src = e; k = 0; }
-                if (dead6(e)) continue;
+        if (W && dist != 0xFFFFFFFFu) {
+            const u32 valid = rowm & 0xFF, deadm = rowm >> 8;
+            u32 found = 0, k = 0;
+            bool chain_open = true;
+            for (; k < K && found < W; k++) {
+                if (!((valid >> k) & 1)) { chain_open = false; break; }
+                if ((deadm >> k) & 1) continue;
                 found++;
+                u32 e = M.row_e[k];
                 u32 d = x - e;
                 if (d <= dist) continue;
                 dist = d;
                 if (dist >= vld) continue;
                 if (minlen >= limit) continue;
-                u32 ml;
-                if (inrow) {
-                    ml = S.L6[at];
-                } else {
-                    const u8 *m = cur - dist;
-                    if (m[minlen] != cur[minlen]) continue;
-                    ml = lcp_bytes(cur, m, limit);
-                }
+                u32 ml = M.row_l[k];
                 if (ml > minlen) {
                     minlen = ml;
                     if (ml <= 6 && dist >= mf_bound(ml)) continue;
                     out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
                     if (ml >= good) { dist = 0xFFFFFFFFu; break; }
+                }
+            }
+            // dead entries inside the row: keep walking the chain behind the row (rare)
+            if (chain_open && found < W && dist != 0xFFFFFFFFu && k == K) {
+                u32 src = M.row_e[K - 1], kk = 0;
+                while (found < W) {
+                    u32 e = S.P6[(size_t)src * K + kk];
+                    if (e == kNone) break;
+                    if (++kk == K) { src = e; kk = 0; }
+                    if (dead6(e)) continue;
+                    found++;
+                    u32 d = x - e;
+                    if (d <= dist) continue;
+                    dist = d;
+                    if (dist >= vld) continue;
+                    if (minlen >= limit) continue;
+                    const u8 *m = cur - dist;
+                    if (m[minlen] != cur[minlen]) continue;
+                    u32 ml = lcp_bytes(cur, m, limit);
+                    if (ml > minlen) {
+                        minlen = ml;
+                        if (ml <= 6 && dist >= mf_bound(ml)) continue;
+                        out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
+                        if (ml >= good) { dist = 0xFFFFFFFFu; break; }
+                    }
                 }
             }
         }
@@ -493,16 +561,17 @@ struct Encoder {
         u1.len = 1; u1.dist = 0;
         bool got = false;
         while (x < end) {
-            if (!got) u1 = find_best(x, end - x);
+            if (!got) { prefetch_fm(x + 1, end); u1 = find_best(x, end - x); }
             if (u1.len == 1 || u1.len >= good) {
                 if (u1.dist == 0) encode_literal(S.lz[x]);
-                else encode_nonlit(u1);
+                else { prefetch_fm(x + u1.len, end); encode_nonlit(u1); }
                 slide(x, u1.len, end);
                 x += u1.len;
                 if (u1.dist) ctx = S.lz[x - 1];
                 got = false;
                 continue;
             }
+            prefetch_fm(x + 2, end);
             u2 = find_best(x + 1, end - x - 1);
             if (second_better(u1, u2)) {
                 encode_literal(S.lz[x]);
@@ -510,6 +579,7 @@ struct Encoder {
                 u1 = u2;
                 got = true;
             } else {
+                prefetch_fm(x + u1.len, end);
                 encode_nonlit(u1);
                 slide(x + 1, u1.len - 1, end);
                 x += u1.len;
@@ -584,6 +654,7 @@ struct Encoder {
         u32 x = x0;          // wnd_curpos_
         u32 i = 0;           // bytes of the sub-block already emitted
         while (i < size) {
+            prefetch_fm(x + 1, end);
             find_match_price(x, end - x, state, rep, t);
             if (t[0].dist == 0) {
                 encode_literal(S.lz[x]);
@@ -627,6 +698,7 @@ struct Encoder {
                     ap[apcur].rep[0] = r0; ap[apcur].rep[1] = r1; ap[apcur].rep[2] = r2; ap[apcur].rep[3] = r3;
                     if (apcur < aplimit) {
                         u32 rr[4] = {r0, r1, r2, r3};
+                        prefetch_fm(x + 1, end);
                         find_match_price(x, end - x, ns, rr, t);
                     }
                 }

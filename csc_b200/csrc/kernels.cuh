@@ -173,13 +173,192 @@ __global__ void k_plan(const SegDesc *__restrict__ segs, u32 nseg, const u32 *__
     }
 }
 
-__global__ void k_filter_runs(u8 *lz, u8 *tmp, const GRun *__restrict__ runs, const u32 *__restrict__ nruns,
-                              const DictTables *__restrict__ D, u8 *dict_ok) {
-    u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= *nruns) return;
-    const GRun g = runs[r];
-    if (g.kind == DT_EXE) e8e9_run(lz + g.goff, g.size, false);
-    else dict_ok[g.gblk] = (u8)dict_forward(lz + g.goff, g.size, tmp + g.goff, *D);
+// ---- parallel filters: one CTA per run, 8 KiB tiles, 32 bytes per thread ---------------
+static const int kFltThreads = 256;
+static const int kFltSpan = 32;
+static const int kFltTile = kFltThreads * kFltSpan;
+static const int kFltLook = 64;   // look-back for re-synchronising the greedy tokenisation
+
+__device__ __forceinline__ u32 block_exscan(u32 v, u32 *s_warp, u32 *total) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (u32)d) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    u32 wbase = 0, tot = 0;
+    for (u32 w = 0; w < kFltThreads / 32; w++) { u32 x = s_warp[w]; if (w < warp) wbase += x; tot += x; }
+    __syncthreads();
+    *total = tot;
+    return wbase + inc - v;
+}
+
+// e8e9 (csc_filters.cpp:508-609).  The greedy opcode selection is a 4-state machine
+// (state = masked positions left after an E8/E9 hit); each thread composes the transition
+// function of its 32 bytes, a block-wide scan of function compositions gives every thread
+// its true entry state, and the operand rewrites are independent of each other.
+__device__ __forceinline__ u32 e89_step(u32 st, u32 byte, bool eligible) {
+    if (st) return st - 1;
+    return (eligible && (byte & 0xFE) == 0xE8) ? 3u : 0u;
+}
+__device__ void e8e9_run_cta(u8 *run, u32 size, bool inverse, u8 *s, u32 *s_warp) {
+    __shared__ u32 s_state;
+    if (threadIdx.x == 0) s_state = 0;
+    __syncthreads();
+    if (size < 6) return;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 t0 = 0; t0 < size; t0 += kFltTile) {
+        const u32 tn = min((u32)kFltTile, size - t0);
+        for (u32 i = threadIdx.x; i < tn + 8; i += kFltThreads) s[i] = (t0 + i < size) ? run[t0 + i] : (u8)0;
+        __syncthreads();
+        const u32 a = threadIdx.x * kFltSpan, b = min(a + kFltSpan, tn);
+        // transition function of this span: 2 bits per entry state
+        u32 f = 0;
+        for (u32 st0 = 0; st0 < 4; st0++) {
+            u32 st = st0;
+            for (u32 i = a; i < b; i++) st = e89_step(st, s[i], t0 + i + 5 < size);
+            f |= st << (2 * st0);
+        }
+        if (a >= tn) f = 0xE4;   // identity
+        // inclusive scan of compositions (apply earlier function first)
+        u32 inc = f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (u32)d) {
+                u32 c = 0;
+                for (u32 k = 0; k < 4; k++) { u32 mid = (o >> (2 * k)) & 3; c |= ((inc >> (2 * mid)) & 3) << (2 * k); }
+                inc = c;
+            }
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        u32 st = s_state;
+        for (u32 w = 0; w < warp; w++) st = (s_warp[w] >> (2 * st)) & 3;
+        u32 prevf = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+        if (lane) st = (prevf >> (2 * st)) & 3;
+        // st = entry state of this thread; walk the span and rewrite operands
+        for (u32 i = a; i < b; i++) {
+            u32 ns = e89_step(st, s[i], t0 + i + 5 < size);
+            if (!st && ns == 3) e89_apply(run, t0 + i, inverse);
+            st = ns;
+        }
+        __syncthreads();
+        if (threadIdx.x == kFltThreads - 1) s_state = st;   // spans past the tile end are identity
+        __syncthreads();
+    }
+}
+
+// dictionary forward (csc_filters.cpp:256-335).  Tokens never cross from a non-letter into a
+// letter run, so every thread re-synchronises by walking back to the start of the letter run
+// that covers its span start (bounded; pathological runs fall back to the scalar statement).
+struct DictSmem { u16 next[300][26]; u8 symbol[300]; };
+__device__ __forceinline__ bool is_lower(u32 c) { return c >= 'a' && c <= 'z'; }
+__device__ __forceinline__ u32 dict_tok(const u8 *p, const DictSmem &D, u32 *sym) {   // p[0] is a letter
+    u32 node = 0, best = 0, bs = 0;
+    for (u32 j = 0; j < 8;) {
+        u32 idx = (u32)p[j] - 'a';
+        if (idx > 25) break;
+        u32 nx = D.next[node][idx];
+        if (!nx) break;
+        node = nx; j++;
+        if (D.symbol[node]) { bs = D.symbol[node]; best = j; }
+    }
+    *sym = bs;
+    return bs ? best : 1;
+}
+__device__ void dict_forward_cta(u8 *run, u32 size, u8 *tmp, const DictTables *Dg, u8 *ok_out, DictSmem &D, u8 *s, u32 *s_warp) {
+    __shared__ u32 s_base, s_fallback;
+    if (size < 16384) { if (threadIdx.x == 0) *ok_out = 0; return; }
+    const u32 main_end = size - 5;   // tokens start below this; the tail is copied byte-wise
+    u32 total = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (threadIdx.x == 0) { s_base = 0; s_fallback = 0; }
+        __syncthreads();
+        for (u32 t0 = 0; t0 < size; t0 += kFltTile) {
+            const u32 tn = min((u32)kFltTile, size - t0);
+            // s[kFltLook + i] = run[t0 + i]
+            for (u32 i = threadIdx.x; i < kFltLook + tn + 8; i += kFltThreads) {
+                long long g = (long long)t0 + i - kFltLook;
+                s[i] = (g >= 0 && g < (long long)size) ? run[g] : (u8)0;
+            }
+            __syncthreads();
+            const u8 *w = s + kFltLook;   // w[i] = run[t0 + i]
+            const u32 a = threadIdx.x * kFltSpan, b = min(a + kFltSpan, tn);
+            u32 pos = a, cnt = 0;
+            if (a < tn) {
+                // first token start >= a
+                if (t0 + a > 0 && is_lower(w[(int)a - 1]) && is_lower(w[a])) {
+                    int back = (int)a - 1;
+                    while (back > -(int)kFltLook && (long long)t0 + back > 0 && is_lower(w[back - 1])) back--;
+                    // the letter run may start before the look-back window: give up on the parallel form
+                    if (back == -(int)kFltLook && (long long)t0 + back > 0) s_fallback = 1;
+                    u32 p = (u32)(back + (int)kFltLook);   // index into s
+                    const u32 target = a + kFltLook;
+                    while (p < target) {
+                        u32 gp = t0 + p - kFltLook;
+                        u32 sym, l = (gp < main_end && is_lower(s[p])) ? dict_tok(s + p, D, &sym) : 1;
+                        p += l;
+                    }
+                    pos = p - kFltLook;
+                }
+                // count / emit the tokens that start in [pos, b)
+                for (u32 i = pos; i < b;) {
+                    u32 gp = t0 + i, c = w[i];
+                    if (gp < main_end && is_lower(c)) { u32 sym; i += dict_tok(w + i, D, &sym); cnt += 1; }
+                    else { cnt += (c >= 0x82) ? 2 : 1; i++; }
+                }
+            }
+            u32 tile_total;
+            u32 off = block_exscan(cnt, s_warp, &tile_total);
+            if (pass == 1 && a < tn) {
+                u8 *o = tmp + s_base + off;
+                for (u32 i = pos; i < b;) {
+                    u32 gp = t0 + i, c = w[i];
+                    if (gp < main_end && is_lower(c)) {
+                        u32 sym, l = dict_tok(w + i, D, &sym);
+                        *o++ = sym ? (u8)sym : (u8)c;
+                        i += l;
+                    } else {
+                        if (c >= 0x82) *o++ = 254;
+                        *o++ = (u8)c;
+                        i++;
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_base += tile_total;
+            __syncthreads();
+        }
+        total = s_base;
+        if (s_fallback) {   // pathological letter run: scalar statement (exactness first)
+            if (threadIdx.x == 0) *ok_out = (u8)dict_forward(run, size, tmp, *Dg);
+            __syncthreads();
+            return;
+        }
+        if (pass == 0 && (double)total > (double)size * 0.82) { if (threadIdx.x == 0) *ok_out = 0; return; }
+        __syncthreads();
+    }
+    for (u32 i = threadIdx.x; i < size; i += kFltThreads) run[i] = i < total ? tmp[i] : (u8)0x20;
+    if (threadIdx.x == 0) *ok_out = 1;
+}
+
+__global__ void __launch_bounds__(kFltThreads)
+k_filter_runs(u8 *lz, u8 *tmp, const GRun *__restrict__ runs, const u32 *__restrict__ nruns, const DictTables *__restrict__ Dg,
+              u8 *dict_ok) {
+    __shared__ DictSmem D;
+    __shared__ u8 s[kFltLook + kFltTile + 16];
+    __shared__ u32 s_warp[kFltThreads / 32];
+    for (u32 i = threadIdx.x; i < 300 * 26; i += kFltThreads) D.next[i / 26][i % 26] = Dg->next[i / 26][i % 26];
+    for (u32 i = threadIdx.x; i < 300; i += kFltThreads) D.symbol[i] = Dg->symbol[i];
+    __syncthreads();
+    const u32 n = *nruns;
+    for (u32 r = blockIdx.x; r < n; r += gridDim.x) {
+        const GRun g = runs[r];
+        if (g.kind == DT_EXE) e8e9_run_cta(lz + g.goff, g.size, false, s, s_warp);
+        else dict_forward_cta(lz + g.goff, g.size, tmp + g.goff, Dg, dict_ok + g.gblk, D, s, s_warp);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------ match finder
@@ -236,33 +415,57 @@ __device__ __forceinline__ u32 ld_u32_unaligned(const u8 *p) {
     return __funnelshift_r(lo, a[1], sh);
 }
 
-// forward match lengths; one thread per (position, candidate) pair, 4 bytes per step
+// Forward match lengths L6[p][k] = LCP(p, P6[p][k]) capped at the sub-block end.
+// One CTA per 8 KiB block, each thread walks a strip of 32 consecutive positions.  Inside a
+// strip most compares disappear: if (p-1, e-1) was a pair of the previous position with length
+// L >= 1 then LCP(p, e) = L - 1 exactly (same cap), which is the common case in repetitive
+// data where whole phrases repeat.  Only strip heads and fresh chain entries touch the window,
+// 4 bytes per step through aligned loads + funnel shift.
+__device__ __forceinline__ u32 lcp_words(const u8 *a, const u8 *m, u32 limit) {
+    u32 l = 0;
+    while (l + 4 <= limit) {
+        u32 d = ld_u32_unaligned(a + l) ^ ld_u32_unaligned(m + l);
+        if (d) return l + ((__ffs((int)d) - 1) >> 3);
+        l += 4;
+    }
+    while (l < limit && a[l] == m[l]) l++;
+    return l;
+}
+
+template <int K>
 __global__ void __launch_bounds__(kMfThreads)
 k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u64 *__restrict__ stream_goff,
-            const u32 *__restrict__ stream_K, const u32 *__restrict__ P6, u16 *__restrict__ L6) {
+            const u32 *__restrict__ P6, u16 *__restrict__ L6) {
     const BlockDesc bd = blk[blockIdx.x];
-    const u32 K = stream_K[bd.stream];
-    if (!K) return;
     const u64 sg = stream_goff[bd.stream];
     const u8 *base = lz + sg;
-    const u32 pairs = bd.size * K;
-    for (u32 t = threadIdx.x; t < pairs; t += kMfThreads) {
-        u32 i = t / K;
-        u32 x = bd.x + i;
-        u64 at = (sg + x) * K + (t - i * K);
-        u32 e = P6[at];
-        if (e == kNone) continue;
-        u32 limit = bd.size - i;
-        const u8 *a = base + x, *m = base + e;
-        u32 l = 0;
-        while (l + 4 <= limit) {
-            u32 d = ld_u32_unaligned(a + l) ^ ld_u32_unaligned(m + l);
-            if (d) { l += (__ffs((int)d) - 1) >> 3; goto done; }
-            l += 4;
+    const u32 i0 = threadIdx.x * 32;
+    if (i0 >= bd.size) return;
+    const u32 i1 = min(i0 + 32, bd.size);
+    u32 pe[K], pl[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { pe[k] = kNone; pl[k] = 0; }
+    for (u32 i = i0; i < i1; i++) {
+        const u32 x = bd.x + i;
+        const u32 limit = bd.size - i;
+        const u64 at = (sg + x) * K;
+        u32 e[K], l[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) e[k] = P6[at + k];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            l[k] = 0;
+            if (e[k] == kNone) continue;
+            bool got = false;
+            if (e[k] > 0) {
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    if (!got && pe[j] == e[k] - 1 && pl[j] >= 1) { l[k] = pl[j] - 1; got = true; }
+            }
+            if (!got) l[k] = lcp_words(base + x, base + e[k], limit);
         }
-        while (l < limit && a[l] == m[l]) l++;
-    done:
-        L6[at] = (u16)l;
+#pragma unroll
+        for (int k = 0; k < K; k++) { if (e[k] != kNone) L6[at + k] = (u16)l[k]; pe[k] = e[k]; pl[k] = l[k]; }
     }
 }
 

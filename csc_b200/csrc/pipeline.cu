@@ -292,7 +292,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     u32 *d_queue = C.counters.as<u32>() + 1;
     k_plan<<<(nseg + 127) / 128, 128, 0, st>>>(C.segdesc.as<SegDesc>(), nseg, C.binfo.as<u32>(), C.planscratch.as<FilterRun>(),
                                                C.runs.as<GRun>(), d_nruns);
-    k_filter_runs<<<(nblk + 63) / 64, 64, 0, st>>>(C.lz.as<u8>(), C.tmp.as<u8>(), C.runs.as<GRun>(), d_nruns, C.d_DT, C.dictok.as<u8>());
+    k_filter_runs<<<std::min<u32>(nblk, 148 * 8), kFltThreads, 0, st>>>(C.lz.as<u8>(), C.tmp.as<u8>(), C.runs.as<GRun>(), d_nruns, C.d_DT, C.dictok.as<u8>());
     T.mark(st);                                                                   // 3
     launches += 3;
     // ---- match finder precomputation
@@ -305,8 +305,10 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(C.keys1.as<u64>(), C.vals1.as<u32>(), npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(),
                                                   C.P6.as<u32>());
     T.mark(st);                                                                   // 6
-    k_mf_extend<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
-                                             C.L6.as<u16>());
+    if (K == 1) k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
+    else if (K == 2) k_mf_extend<2><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
+    else if (K == 8) k_mf_extend<8><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
+    else return kErrUnsupported;
     T.mark(st);                                                                   // 7
     launches += 3 + (u32)((end_bit + 7) / 8) * 2 + 1;
     if (g_dump.on && ns == 1) {

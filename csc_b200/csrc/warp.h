@@ -24,6 +24,7 @@ CSC_HD void g_or(u32 *p, u32 m) { atomicOr(p, m); }
 CSC_HD void g_max(u32 *p, u32 v) { atomicMax(p, v); }
 CSC_HD u32 g_ld(const u32 *p) { return __ldcg(p); }   // L2-coherent read of lane-written data
 CSC_HD u32 ffs32(u32 m) { return (u32)__ffs((int)m); }
+CSC_HD void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
 #define CSC_LANE 0u
 #define CSC_NLANES 1u
@@ -36,6 +37,7 @@ CSC_HD void g_or(u32 *p, u32 m) { *p |= m; }
 CSC_HD void g_max(u32 *p, u32 v) { if (v > *p) *p = v; }
 CSC_HD u32 g_ld(const u32 *p) { return *p; }
 CSC_HD u32 ffs32(u32 m) { return (u32)__builtin_ffs((int)m); }
+CSC_HD void pf_l2(const void *) {}
 #endif
 
 // Longest common prefix of a[0..limit) and b[0..limit): the byte-compare loop of
