@@ -145,7 +145,13 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--total", type=int, default=TOTAL, help="bytes per GPU (default 1 GiB)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--chunk", type=int, default=CHUNK, help="independent chunk size (part of the parity key)")
+    ap.add_argument("--level", type=int, default=LEVEL)
     args = ap.parse_args()
+    global CHUNK, LEVEL, WORKLOAD
+    if args.chunk != CHUNK or args.level != LEVEL:
+        CHUNK, LEVEL = args.chunk, args.level
+        WORKLOAD = f"libcsc -m{LEVEL} -d64m, synthetic English-like text, independent {CHUNK >> 10} KiB chunks"
     if args.impl == "reference":
         return run_reference_arm(args)
 

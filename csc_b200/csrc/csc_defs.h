@@ -85,6 +85,8 @@ struct ModelSmall {
     u32 p2bits[512];      // p_2_bits_ (csc_model.cpp:68-70), host-libm derived
     u32 row_e[8];         // scratch: candidate row of the current position (lane-gathered)
     u32 row_l[8];
+    u32 cl[kMaxCand];     // scratch: candidate list of the current find_match (len, dist code)
+    u32 cd[kMaxCand];
 };
 
 // per-segment output record written by the encoder engine, read by host framing

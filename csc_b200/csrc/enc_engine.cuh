@@ -298,16 +298,20 @@ struct Encoder {
     }
 
     // ----------------------------------------------------- match finder (state)
-    CSC_HD u32 hash2_at(u32 x, u32 sb_end) const {   // HASH2, csc_mf.cpp:23-28; unwritten window bytes are 0
-        u32 b0 = S.lz[x], b1 = (x + 1 < sb_end) ? S.lz[x + 1] : 0;
-        return ((b0 | (b1 << 8)) * 65521u) & 0x3FFF;
+    // HASH2 / HASH3 (csc_mf.cpp:23-33) of position x from one unaligned word; window bytes at or
+    // beyond the sub-block end have not been written yet and read as 0
+    CSC_HDF u32 word_at(u32 x, u32 sb_end) const {
+        u32 w = ld32u(S.lz + x);
+        u32 avail = sb_end - x;
+        if (avail < 4) w &= 0xFFFFFFFFu >> ((4 - avail) * 8);
+        return w;
     }
-    CSC_HD u32 hash3_at(u32 x, u32 sb_end) const {   // HASH3, csc_mf.cpp:30-33
-        u32 b0 = S.lz[x], b1 = (x + 1 < sb_end) ? S.lz[x + 1] : 0, b2 = (x + 2 < sb_end) ? S.lz[x + 2] : 0;
-        return (b0 << 8) ^ (b1 << 5) ^ b2;
-    }
-    CSC_HD bool dead6(u32 e) const { return bit_get(S.D6, e); }
-    CSC_HD void kill6(u32 e) { g_or(&S.D6[e >> 5], 1u << (e & 31)); }
+    CSC_HDF static u32 h2_of(u32 w) { return ((w & 0xFFFF) * 65521u) & 0x3FFF; }
+    CSC_HDF static u32 h3_of(u32 w) { return ((w & 0xFF) << 8) ^ (((w >> 8) & 0xFF) << 5) ^ ((w >> 16) & 0xFF); }
+    CSC_HD u32 hash2_at(u32 x, u32 sb_end) const { return h2_of(word_at(x, sb_end)); }
+    CSC_HD u32 hash3_at(u32 x, u32 sb_end) const { return h3_of(word_at(x, sb_end)); }
+    CSC_HDF bool dead6(u32 e) const { return bit_get(S.D6, e); }
+    CSC_HDF void kill6(u32 e) { g_or(&S.D6[e >> 5], 1u << (e & 31)); }
 
     // newest position < bound on the 6-byte chain of x that is still in the table
     // (= slot 0 of the reference bucket at the time the window ended at `bound`)
@@ -322,174 +326,175 @@ struct Encoder {
         }
     }
 
-    // Lane-parallel fetch of the candidate row of x: entry k, its precomputed length and its
-    // liveness bit are read by lane k (one memory round trip for the whole bucket instead of
-    // W dependent ones) and parked in the warp's scratch.  Returns (valid | dead << 8) masks.
-    CSC_HD u32 gather_row(u32 x) {
-        u32 e = kNone, l = 0;
-        bool dead = false;
-        const size_t at = (size_t)x * K;
-#if defined(__CUDA_ARCH__)
-        if (CSC_LANE < K) {
-            e = S.P6[at + CSC_LANE];
-            l = S.L6[at + CSC_LANE];
-            if (e != kNone) dead = dead6(e);
-            M.row_e[CSC_LANE] = e;
-            M.row_l[CSC_LANE] = l;
-        }
-        u32 valid = w_ballot(e != kNone), deadm = w_ballot(dead);
-        w_sync();
-        return valid | (deadm << 8);
-#else
-        u32 valid = 0, deadm = 0;
-        for (u32 k = 0; k < K; k++) {
-            e = S.P6[at + k]; l = S.L6[at + k];
-            dead = (e != kNone) && dead6(e);
-            M.row_e[k] = e; M.row_l[k] = l;
-            if (e != kNone) valid |= 1u << k;
-            if (dead) deadm |= 1u << k;
-        }
-        return valid | (deadm << 8);
-#endif
-    }
-
     // warm the lines the next find_match(y) will need while the coder is busy with a packet
     CSC_HD void prefetch_fm(u32 y, u32 sb_end) {
         if (y >= sb_end) return;
         if (W) { pf_l2(S.P6 + (size_t)y * K); pf_l2(S.L6 + (size_t)y * K); }
-        pf_l2(S.ht2 + hash2_at(y, sb_end));
-        pf_l2(S.ht3 + hash3_at(y, sb_end));
-        for (int i = 0; i < 4; i++) if (rep[i] < vld && rep[i] <= y) pf_l2(S.lz + y - rep[i]);
-        const u16 *row = S.p_lit + (u32)S.lz[y - (y ? 1 : 0)] * 256;
-        pf_l2(row); pf_l2(row + 64); pf_l2(row + 128); pf_l2(row + 192);
+        u32 w = word_at(y, sb_end);
+        pf_l2(S.ht2 + h2_of(w));
+        pf_l2(S.ht3 + h3_of(w));
     }
 
-    // find_match (csc_mf.cpp:243-495): candidate list in reference probe order.
-    CSC_HD u32 find_match(u32 x, u32 limit, const u32 *rp, Cand *out) {
+    CSC_HDF static u32 mf_bound(u32 len) { return len < 2 ? 0u : 1u << (4 * len - 2); }   // bound[] csc_mf.cpp:245
+
+    CSC_HDF void push_cand(u32 &cnt, u32 len, u32 dist) { M.cl[cnt] = len; M.cd[cnt] = dist; cnt++; }
+
+    // one table / rep probe once the candidate is known to be in range: reference semantics of
+    // "pre-check byte at minlen, full compare, update minlen, bound filter, record, good_len stop"
+    // returns true when every further probe is disabled (dist poisoned)
+    CSC_HDF bool probe(const u8 *cur, u32 d, u32 limit, u32 pre, u32 c1, u32 code, bool bounded, u32 &minlen, u32 &cnt) {
+        const u8 *m = cur - d;
+        if (minlen == 1 ? (pre != c1) : (m[minlen] != cur[minlen])) return false;
+        u32 ml = lcp_bytes(cur, m, limit);
+        if (ml <= minlen) return false;
+        minlen = ml;
+        if (bounded && ml <= 6 && d >= mf_bound(ml)) return false;
+        push_cand(cnt, ml, code);
+        return ml >= good;
+    }
+
+    // find_match (csc_mf.cpp:243-495): candidate list (M.cl / M.cd) in reference probe order.
+    CSC_HD u32 find_match(u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
         const u8 *cur = S.lz + x;
         const u32 pos = vld + x;
         const u32 sb_end = x + limit;
         u32 cnt = 0, minlen = 1, dist = 0;
         // ---- issue every independent load first: tables, candidate row, first probe bytes
-        const u32 h2 = hash2_at(x, sb_end), h3 = hash3_at(x, sb_end);
+        const u32 w0 = word_at(x, sb_end);
+        const u32 h2 = h2_of(w0), h3 = h3_of(w0);
         const u32 e2 = g_ld(&S.ht2[h2]), e3 = g_ld(&S.ht3[h3]);
-        const u32 rowm = W ? gather_row(x) : 0;
-        const bool deep = limit > 1;
-        const u32 c1 = deep ? cur[1] : 0;
-        u32 rb[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) rb[i] = (deep && rp[i] < vld) ? (cur - rp[i])[1] : 0x100;
-        const u32 d2 = pos - e2, d3 = pos - e3;
-        const u32 t2 = (deep && d2 < vld && x > d2) ? (cur - d2)[1] : 0x100;
-        const u32 t3 = (deep && d3 < vld && x >= d3) ? (cur - d3)[1] : 0x100;
-        // rep-distance probes (:266-299)
-        for (u32 i = 0; i < 4; i++) {
-            u32 rd = rp[i];
-            if (rd >= vld) continue;
-            if (minlen >= limit) continue;
-            const u8 *m = cur - rd;
-            if (minlen == 1 ? (rb[i] != c1) : (m[minlen] != cur[minlen])) continue;
-            u32 ml = lcp_bytes(cur, m, limit);
-            if (ml && i == 0) { out[cnt].len = 1; out[cnt].dist = 1; cnt++; }
-            if (ml > minlen) {
-                minlen = ml;
-                out[cnt].len = ml; out[cnt].dist = 1 + i; cnt++;
-                if (ml >= good) { dist = 0xFFFFFFFFu; break; }
-            }
+        // candidate row: entry k, its length and its liveness bit are fetched by lane k
+        u32 re = kNone, rl = 0;
+        bool rdead = false;
+#if defined(__CUDA_ARCH__)
+        if (CSC_LANE < K) {
+            const size_t at = (size_t)x * K + CSC_LANE;
+            re = S.P6[at];
+            rl = S.L6[at];
+            if (re != kNone) rdead = dead6(re);
         }
-        // 2-byte and 3-byte single-slot tables (:303-366)
+#endif
+        const bool deep = limit > 1;
+        const u32 c1 = (w0 >> 8) & 0xFF;
+        const bool v0 = deep && r0 < vld, v1 = deep && r1 < vld, v2 = deep && r2 < vld, v3 = deep && r3 < vld;
+        const u32 b0 = v0 ? (cur - r0)[1] : 0x100, b1 = v1 ? (cur - r1)[1] : 0x100;
+        const u32 b2 = v2 ? (cur - r2)[1] : 0x100, b3 = v3 ? (cur - r3)[1] : 0x100;
+        const u32 d2 = pos - e2, d3 = pos - e3;
+        const bool q2 = deep && d2 < vld && x > d2, q3 = deep && d3 < vld && x >= d3;
+        const u32 t2 = q2 ? (cur - d2)[1] : 0x100, t3 = q3 ? (cur - d3)[1] : 0x100;
+        S.ht2[h2] = pos;
+        S.ht3[h3] = pos;
+        bool stop = false;
+        // rep-distance probes (:266-299); rep0 also yields the 1-byte match when it matches >= 2
+        if (v0 && b0 == c1) {
+            u32 ml = lcp_bytes(cur, cur - r0, limit);
+            if (ml) push_cand(cnt, 1, 1);
+            if (ml > minlen) { minlen = ml; push_cand(cnt, ml, 1); stop = ml >= good; }
+        }
+        if (!stop && v1 && minlen < limit) stop = probe(cur, r1, limit, b1, c1, 2, false, minlen, cnt);
+        if (!stop && v2 && minlen < limit) stop = probe(cur, r2, limit, b2, c1, 3, false, minlen, cnt);
+        if (!stop && v3 && minlen < limit) stop = probe(cur, r3, limit, b3, c1, 4, false, minlen, cnt);
+        if (stop) dist = 0xFFFFFFFFu;
+        // 2-byte and 3-byte single-slot tables (:303-366).  `wpos > dist` (:306): a 2-byte candidate
+        // at window offset 0 is dropped but still poisons dist.
         if (d2 > dist) {
             dist = d2;
-            // note `wpos > dist` (:306): a candidate at window offset 0 is dropped, dist stays poisoned
-            if (dist < vld && x > dist && minlen < limit) {
-                const u8 *m = cur - dist;
-                if (minlen == 1 ? (t2 == c1) : (m[minlen] == cur[minlen])) {
-                    u32 ml = lcp_bytes(cur, m, limit);
-                    if (ml > minlen) {
-                        minlen = ml;
-                        if (!(ml <= 6 && dist >= mf_bound(ml))) {
-                            out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
-                            if (ml >= good) dist = 0xFFFFFFFFu;
-                        }
-                    }
-                }
-            }
+            if (q2 && minlen < limit && probe(cur, d2, limit, t2, c1, 4 + d2, true, minlen, cnt)) dist = 0xFFFFFFFFu;
         }
         if (d3 > dist) {
             dist = d3;
-            if (dist < vld && x >= dist && minlen < limit) {
-                const u8 *m = cur - dist;
-                if (minlen == 1 ? (t3 == c1) : (m[minlen] == cur[minlen])) {
-                    u32 ml = lcp_bytes(cur, m, limit);
-                    if (ml > minlen) {
-                        minlen = ml;
-                        if (!(ml <= 6 && dist >= mf_bound(ml))) {
-                            out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
-                            if (ml >= good) dist = 0xFFFFFFFFu;
-                        }
-                    }
-                }
-            }
+            if (q3 && minlen < limit && probe(cur, d3, limit, t3, c1, 4 + d3, true, minlen, cnt)) dist = 0xFFFFFFFFu;
         }
-        S.ht2[h2] = pos;
-        S.ht3[h3] = pos;
-        // 6-byte table of width W (:453-485): first W live entries of the chain
+        // 6-byte table of width W (:453-485): the first W live entries of the chain
         if (W && dist != 0xFFFFFFFFu) {
-            const u32 valid = rowm & 0xFF, deadm = rowm >> 8;
-            u32 found = 0, k = 0;
-            bool chain_open = true;
-            for (; k < K && found < W; k++) {
-                if (!((valid >> k) & 1)) { chain_open = false; break; }
-                if ((deadm >> k) & 1) continue;
-                found++;
-                u32 e = M.row_e[k];
-                u32 d = x - e;
-                if (d <= dist) continue;
-                dist = d;
-                if (dist >= vld) continue;
-                if (minlen >= limit) continue;
-                u32 ml = M.row_l[k];
-                if (ml > minlen) {
-                    minlen = ml;
-                    if (ml <= 6 && dist >= mf_bound(ml)) continue;
-                    out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
-                    if (ml >= good) { dist = 0xFFFFFFFFu; break; }
+#if defined(__CUDA_ARCH__)
+            // lanes 0..K-1 evaluate their entry; the running minlen is a prefix maximum and the
+            // strictly increasing distances make the `<= dist` filter a compare with the entry value
+            const u32 validm = __ballot_sync(0xFFFFFFFFu, re != kNone);
+            const u32 alivem = __ballot_sync(0xFFFFFFFFu, re != kNone && !rdead);
+            const u32 lt = (1u << CSC_LANE) - 1;
+            const u32 d = x - re;
+            const bool cons = ((alivem >> CSC_LANE) & 1) && (u32)__popc(alivem & lt) < W;
+            const bool passd = cons && d > dist && d < vld && minlen < limit;
+            u32 pm = passd ? rl : 0;
+#pragma unroll
+            for (int sft = 1; sft < 8; sft <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, pm, sft); if (CSC_LANE >= (u32)sft) pm = max(pm, t); }
+            u32 excl = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
+            if (CSC_LANE == 0) excl = 0;
+            const u32 run = max(minlen, excl);
+            bool acc = passd && rl > run && !(rl <= 6 && d >= mf_bound(rl));
+            const u32 stopm = __ballot_sync(0xFFFFFFFFu, acc && rl >= good);
+            if (stopm && CSC_LANE > (u32)__ffs((int)stopm) - 1) acc = false;
+            const u32 accm = __ballot_sync(0xFFFFFFFFu, acc);
+            if (acc) { u32 idx = cnt + (u32)__popc(accm & lt); M.cl[idx] = rl; M.cd[idx] = 4 + d; }
+            cnt += (u32)__popc(accm);
+            __syncwarp();
+            // a dead entry inside a full row leaves the bucket short: keep walking behind the row (rare)
+            const u32 full = (K >= 32) ? 0xFFFFFFFFu : ((1u << K) - 1);
+            if (!stopm && validm == full && (u32)__popc(alivem) < W) {
+                u32 found = (u32)__popc(alivem);
+                u32 last_d = 0, last_l = 0;   // state after the row: dist / minlen
+                {
+                    const u32 pdm = __ballot_sync(0xFFFFFFFFu, cons);
+                    u32 md = cons ? d : 0;
+                    u32 ml2 = (passd && rl > run) ? rl : 0;
+#pragma unroll
+                    for (int sft = 16; sft; sft >>= 1) { md = max(md, __shfl_xor_sync(0xFFFFFFFFu, md, sft)); ml2 = max(ml2, __shfl_xor_sync(0xFFFFFFFFu, ml2, sft)); }
+                    last_d = pdm ? md : 0; last_l = ml2;
                 }
-            }
-            // dead entries inside the row: keep walking the chain behind the row (rare)
-            if (chain_open && found < W && dist != 0xFFFFFFFFu && k == K) {
-                u32 src = M.row_e[K - 1], kk = 0;
+                if (last_d > dist) dist = last_d;
+                if (last_l > minlen) minlen = last_l;
+                u32 src = __shfl_sync(0xFFFFFFFFu, re, K - 1), kk = 0;
                 while (found < W) {
                     u32 e = S.P6[(size_t)src * K + kk];
                     if (e == kNone) break;
                     if (++kk == K) { src = e; kk = 0; }
                     if (dead6(e)) continue;
                     found++;
-                    u32 d = x - e;
-                    if (d <= dist) continue;
-                    dist = d;
-                    if (dist >= vld) continue;
-                    if (minlen >= limit) continue;
-                    const u8 *m = cur - dist;
-                    if (m[minlen] != cur[minlen]) continue;
-                    u32 ml = lcp_bytes(cur, m, limit);
-                    if (ml > minlen) {
-                        minlen = ml;
-                        if (ml <= 6 && dist >= mf_bound(ml)) continue;
-                        out[cnt].len = ml; out[cnt].dist = 4 + dist; cnt++;
-                        if (ml >= good) { dist = 0xFFFFFFFFu; break; }
-                    }
+                    u32 dd = x - e;
+                    if (dd <= dist) continue;
+                    dist = dd;
+                    if (dist >= vld || minlen >= limit) continue;
+                    if (probe(cur, dd, limit, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
                 }
             }
+#else
+            u32 found = 0, src = x, k = 0;
+            while (found < W) {
+                size_t at = (size_t)src * K + k;
+                u32 e = S.P6[at];
+                if (e == kNone) break;
+                bool inrow = (src == x);
+                if (++k == K) { src = e; k = 0; }
+                if (dead6(e)) continue;
+                found++;
+                u32 d = x - e;
+                if (d <= dist) continue;
+                dist = d;
+                if (dist >= vld) continue;
+                if (minlen >= limit) continue;
+                u32 ml;
+                if (inrow) {
+                    ml = S.L6[at];
+                } else {
+                    const u8 *m = cur - dist;
+                    if (m[minlen] != cur[minlen]) continue;
+                    ml = lcp_bytes(cur, m, limit);
+                }
+                if (ml > minlen) {
+                    minlen = ml;
+                    if (ml <= 6 && dist >= mf_bound(ml)) continue;
+                    push_cand(cnt, ml, 4 + dist);
+                    if (ml >= good) break;
+                }
+            }
+#endif
         }
         // x itself is now the newest entry everywhere (alive by default)
         return cnt;
     }
-    CSC_HD static u32 mf_bound(u32 len) {   // bound[] csc_mf.cpp:245
-        return len < 2 ? 0u : len == 2 ? 64u : len == 3 ? 1024u : len == 4 ? 16u * 1024 : len == 5 ? 256u * 1024 : 4u * 1024 * 1024;
-    }
 
-    CSC_HD static bool second_better(Cand u1, Cand u2) {   // csc_mf.cpp:570-582 (== fold of :497-524)
+    CSC_HDF static bool second_better(Cand u1, Cand u2) {   // csc_mf.cpp:570-582 (== fold of :497-524)
         if (u2.len <= 1) return false;
         if (u2.len > u1.len + 3) return true;
         if (u2.len > u1.len && u2.dist <= 4) return true;
@@ -499,12 +504,11 @@ struct Encoder {
         return false;
     }
     CSC_HD Cand find_best(u32 x, u32 limit) {   // FindMatch, csc_mf.cpp:497-524
-        Cand c[kMaxCand];
-        u32 n = find_match(x, limit, rep, c);
+        u32 n = find_match(x, limit, rep[0], rep[1], rep[2], rep[3]);
         Cand best; best.len = 1; best.dist = 0;
         for (u32 i = 0; i < n; i++) {
-            if (i == 0) { best = c[0]; continue; }
-            if (second_better(best, c[i])) best = c[i];
+            Cand c; c.len = M.cl[i]; c.dist = M.cd[i];
+            if (i == 0 || second_better(best, c)) best = c;
         }
         return best;
     }
@@ -593,30 +597,30 @@ struct Encoder {
     // FindMatchWithPrice (csc_mf.cpp:584-625): t[0] longest candidate, t[1] rep0len1,
     // t[2..] price per length.
     CSC_HD void find_match_price(u32 x, u32 limit, u32 fstate, const u32 *rp, Cand *t) {
-        Cand c[kMaxCand];
-        u32 n = find_match(x, limit, rp, c);
+        u32 n = find_match(x, limit, rp[0], rp[1], rp[2], rp[3]);
         if (n == 0) { t[0].len = 1; t[0].dist = 0; }
-        else t[0] = c[n - 1];
+        else { t[0].len = M.cl[n - 1]; t[0].dist = M.cd[n - 1]; }
         if (t[0].len >= good) return;
         t[1].dist = 0;
         u32 lpos = 1;
         for (u32 i = 0; i < n; i++) {
+            const u32 clen = M.cl[i], cdist = M.cd[i];
             u32 dprice, rdist;
-            if (c[i].len == 1 && c[i].dist == 1) {
+            if (clen == 1 && cdist == 1) {
                 t[1].len = rep0len1_price(fstate);
                 t[1].dist = 1;
                 continue;
-            } else if (c[i].dist <= 4) {
-                dprice = repdist_price(fstate, c[i].dist - 1);
+            } else if (cdist <= 4) {
+                dprice = repdist_price(fstate, cdist - 1);
                 rdist = 0;
             } else {
-                dprice = matchdist_price(fstate, c[i].dist - 5);
-                rdist = c[i].dist - 4;
+                dprice = matchdist_price(fstate, cdist - 5);
+                rdist = cdist - 4;
             }
-            while (lpos < c[i].len) {
+            while (lpos < clen) {
                 lpos++;
                 if (lpos <= 6 && rdist >= mf_bound(lpos)) { t[lpos].dist = 0; continue; }
-                t[lpos].dist = c[i].dist;
+                t[lpos].dist = cdist;
                 t[lpos].len = dprice + matchlen_price(lpos - 2);   // .len doubles as price (MFUnit union)
             }
         }

@@ -40,17 +40,42 @@ CSC_HD u32 ffs32(u32 m) { return (u32)__builtin_ffs((int)m); }
 CSC_HD void pf_l2(const void *) {}
 #endif
 
+#if defined(__CUDA_ARCH__)
+CSC_HDF u32 ld32u(const u8 *p) {   // unaligned little-endian u32 through two aligned loads (buffers are padded)
+    const u32 *a = reinterpret_cast<const u32 *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    u32 sh = (u32)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+    return __funnelshift_r(a[0], a[1], sh);
+}
+#else
+CSC_HDF u32 ld32u(const u8 *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+#endif
+
 // Longest common prefix of a[0..limit) and b[0..limit): the byte-compare loop of
-// every probe in find_match (csc_mf.cpp:279,317,348,470), done 32 bytes per
-// step by the warp.
+// every probe in find_match (csc_mf.cpp:279,317,348,470), done 128 bytes per
+// step by the warp (4 bytes per lane).
 CSC_HD u32 lcp_bytes(const u8 *a, const u8 *b, u32 limit) {
-    for (u32 k = 0; k < limit; k += CSC_NLANES) {
-        u32 i = k + CSC_LANE;
-        bool mis = (i >= limit) || (a[i] != b[i]);
-        u32 m = w_ballot(mis);
-        if (m) return k + ffs32(m) - 1;
+#if defined(__CUDA_ARCH__)
+    for (u32 k = 0; k < limit; k += 128) {
+        u32 i = k + CSC_LANE * 4;
+        u32 d = 0xFFFFFFFFu;
+        if (i < limit) {
+            d = ld32u(a + i) ^ ld32u(b + i);
+            u32 rem = limit - i;   // bytes of this word that count
+            if (rem < 4) d |= 0xFFFFFFFFu << (rem * 8);
+        }
+        u32 m = __ballot_sync(0xFFFFFFFFu, d != 0);
+        if (m) {
+            u32 l = (u32)__ffs((int)m) - 1;
+            u32 dd = __shfl_sync(0xFFFFFFFFu, d, l);
+            return k + l * 4 + (((u32)__ffs((int)dd) - 1) >> 3);
+        }
     }
     return limit;
+#else
+    u32 l = 0;
+    while (l < limit && a[l] == b[l]) l++;
+    return l;
+#endif
 }
 
 // same, but bytes of b at or beyond b_valid read as zero (window area that has
