@@ -138,6 +138,7 @@ def run_reference_arm(args):
 
 
 def main():
+    global CHUNK, LEVEL, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -148,7 +149,6 @@ def main():
     ap.add_argument("--chunk", type=int, default=CHUNK, help="independent chunk size (part of the parity key)")
     ap.add_argument("--level", type=int, default=LEVEL)
     args = ap.parse_args()
-    global CHUNK, LEVEL, WORKLOAD
     if args.chunk != CHUNK or args.level != LEVEL:
         CHUNK, LEVEL = args.chunk, args.level
         WORKLOAD = f"libcsc -m{LEVEL} -d64m, synthetic English-like text, independent {CHUNK >> 10} KiB chunks"
