@@ -16,7 +16,7 @@ typedef uint64_t u64;
 typedef int32_t i32;
 
 #if defined(__CUDACC__)
-#define CSC_HD __host__ __device__ inline
+#define CSC_HD __host__ __device__ __noinline__
 #define CSC_HDF __host__ __device__ __forceinline__
 #define CSC_HDN __host__ __device__ __noinline__
 #else
@@ -87,7 +87,10 @@ struct ModelSmall {
     u32 row_l[8];
     u32 cl[kMaxCand];     // scratch: candidate list of the current find_match (len, dist code)
     u32 cd[kMaxCand];
+    u32 bq[32];           // pending range-coder decisions of the current packet: probability slot ids
+    u16 bq_p[32];         //   ... and the probabilities fetched for them (lane-parallel)
 };
+static const u32 kSlotGlobal = 0x80000000u;   // slot id flag: index into p_lit/p_delta (global), else u16 index into ModelSmall
 
 // per-segment output record written by the encoder engine, read by host framing
 struct SegOut {

@@ -46,6 +46,7 @@ struct Encoder {
     u32 range, cachesize, cache;
     u32 bc_bits, bc_val;
     u32 rc_n, rc_blk, bc_n, bc_blk, ev_n;
+    u32 bq_n, bq_bits;
     // model (csc_model.h)
     u32 state, ctx, lp_rebuild;
     // LZ (csc_lz.h:22)
@@ -82,6 +83,7 @@ struct Encoder {
     CSC_HD void coder_reset() {
         low = 0; range = 0xFFFFFFFFu; cachesize = 1; cache = 0;
         bc_bits = 0; bc_val = 0; rc_blk = 0; bc_blk = 0;
+        bq_n = 0; bq_bits = 0;
     }
     CSC_HD void shift_low() {   // csc_coder.cpp:89-112
         if ((u32)low < 0xFF000000u || (u32)(low >> 32) != 0) {
@@ -96,15 +98,54 @@ struct Encoder {
         cachesize++;
         low = (u64)((u32)low << 8);
     }
-    CSC_HD void enc_bit(u16 &pr, u32 bit) {   // csc_coder.h:67-81
-        u32 p = pr;
-        u32 bound = (range >> 12) * p;
-        if (bit) { range = bound; p += (0xFFFu - p) >> 5; }
-        else { low += bound; range -= bound; p -= p >> 5; }
-        pr = (u16)p;
-        if (range < (1u << 24)) { range <<= 8; shift_low(); }
+    // EncodeBit (csc_coder.h:67-81) is split in two.  The adaptive-probability half of a decision
+    // (load p, adapt, store) does not depend on the coder registers, so a packet first QUEUES its
+    // decisions (slot id + bit); flush_bits() then lets lane k fetch/adapt/store probability k (one
+    // memory round trip for the whole packet) and runs only the range/low recurrence serially.
+    // A queue never holds the same slot twice (callers flush in between), and it is flushed before
+    // any raw-bit write so that RC/BC block events keep their temporal order (H4).
+    CSC_HDF void q_push(u32 slot, u32 bit) {
+        M.bq[bq_n] = slot;
+        bq_bits |= bit << bq_n;
+        bq_n++;
+    }
+    CSC_HDF void enc_bit(u16 &pr, u32 bit) {   // small-model probability (lives in ModelSmall)
+        q_push((u32)(&pr - reinterpret_cast<u16 *>(&M)), bit);
+    }
+    CSC_HDF void enc_bit_g(u32 gidx, u32 bit) { q_push(kSlotGlobal | gidx, bit); }   // p_lit / p_delta entry
+    CSC_HD void flush_bits() {
+        const u32 n = bq_n;
+        if (!n) return;
+        const u32 bits = bq_bits;
+#if defined(__CUDA_ARCH__)
+        if (CSC_LANE < n) {
+            u32 slot = M.bq[CSC_LANE];
+            u16 *pp = (slot & kSlotGlobal) ? S.p_lit + (slot & ~kSlotGlobal) : reinterpret_cast<u16 *>(&M) + slot;
+            u32 v = *pp;
+            *pp = (u16)(((bits >> CSC_LANE) & 1) ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
+            M.bq_p[CSC_LANE] = (u16)v;
+        }
+        __syncwarp();
+#else
+        for (u32 k = 0; k < n; k++) {
+            u32 slot = M.bq[k];
+            u16 *pp = (slot & kSlotGlobal) ? S.p_lit + (slot & ~kSlotGlobal) : reinterpret_cast<u16 *>(&M) + slot;
+            u32 v = *pp;
+            *pp = (u16)(((bits >> k) & 1) ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
+            M.bq_p[k] = (u16)v;
+        }
+#endif
+        for (u32 k = 0; k < n; k++) {
+            u32 bound = (range >> 12) * M.bq_p[k];
+            if ((bits >> k) & 1) range = bound;
+            else { low += bound; range -= bound; }
+            if (range < (1u << 24)) { range <<= 8; shift_low(); }
+        }
+        w_sync();
+        bq_n = 0; bq_bits = 0;
     }
     CSC_HD void direct16(u32 val, u32 len) {   // csc_coder.cpp:76-87
+        flush_bits();   // keep RC decisions ahead of later raw bits (block-event order)
         bc_val = (bc_val << len) | val;
         bc_bits += len;
         while (bc_bits >= 8) {
@@ -117,6 +158,7 @@ struct Encoder {
         else { direct16(val >> 16, len - 16); direct16(val & 0xFFFF, 16); }
     }
     CSC_HD void flush_segment(u32 seg, u32 rc0, u32 bc0, u32 ev0) {   // csc_coder.cpp:40-74
+        flush_bits();
         for (int i = 0; i < 5; i++) shift_low();
         // one byte is skipped, not stored (H3): the host substitutes the stale ring byte
         if (rc_n < S.rc_cap) S.rc_out[rc_n] = 0; else err = kErrOverflow;
@@ -147,24 +189,20 @@ struct Encoder {
         state = 0; ctx = 0; lp_rebuild = 0;
     }
 
-    CSC_HD void lit_bits(u16 *row, u32 c) {
-        // the 8 tree nodes are known up front: load, code, store (csc_model.cpp:176-182)
+    // 8 literal bits under the order-1 row `row` (index of the row start in p_lit/p_delta, csc_model.cpp:176-182)
+    CSC_HD void lit_bits(u32 row, u32 c) {
         u32 cc = c | 0x100;
-        u16 pv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) pv[k] = row[cc >> (8 - k)];
-#pragma unroll
-        for (int k = 0; k < 8; k++) enc_bit(pv[k], (cc >> (7 - k)) & 1);
-#pragma unroll
-        for (int k = 0; k < 8; k++) row[cc >> (8 - k)] = pv[k];
+        for (int k = 0; k < 8; k++) enc_bit_g(row + (cc >> (8 - k)), (cc >> (7 - k)) & 1);
     }
     CSC_HD void encode_literal(u32 c) {   // csc_model.cpp:169-183
         trace(0, c, 0);
         enc_bit(M.p_state[state * 3 + 0], 0);
         state = (state * 4) & 0x3F;
-        u16 *row = S.p_lit + ctx * 256;
+        u32 row = ctx * 256;
         ctx = c;
         lit_bits(row, c);
+        flush_bits();
     }
     CSC_HD void encode_matchlen_1(u32 len) {   // csc_model.cpp:113-145
         if (len < 16) {
@@ -190,9 +228,11 @@ struct Encoder {
     CSC_HD void encode_matchlen_2(u32 len) {   // csc_model.cpp:147-159
         if (len >= 143) {
             encode_matchlen_1(143);
+            flush_bits();
             len -= 143;
-            while (len >= 143) { len -= 143; enc_bit(M.p_longlen, 0); }
+            while (len >= 143) { len -= 143; enc_bit(M.p_longlen, 0); flush_bits(); }
             enc_bit(M.p_longlen, 1);
+            flush_bits();
         }
         encode_matchlen_1(len);
     }
@@ -203,6 +243,7 @@ struct Encoder {
         enc_bit(M.p_state[state * 3 + 2], 0);
         ctx = 0;
         state = (state * 4 + 2) & 0x3F;
+        flush_bits();
     }
     CSC_HD void encode_rep(u32 idx, u32 lencode) {   // csc_model.cpp:218-232
         trace(3, lencode, idx);
@@ -214,6 +255,7 @@ struct Encoder {
         enc_bit(M.p_repdist[state * 3 + 1 + b1], b0);
         encode_matchlen_2(lencode);
         state = (state * 4 + 3) & 0x3F;
+        flush_bits();
     }
     CSC_HD void encode_match(u32 dist, u32 lencode) {   // csc_model.cpp:301-366
         trace(1, lencode, dist);
@@ -238,6 +280,7 @@ struct Encoder {
             do { enc_bit(p[c >> 4], (c >> 3) & 1); c <<= 1; } while (c < 0x100);
         }
         state = (state * 4 + 1) & 0x3F;
+        flush_bits();
     }
     CSC_HD void encode_int(u32 num) {   // csc_model.cpp:389-414
         u32 slot = num ? ilog2(num) : 0;
@@ -561,35 +604,36 @@ struct Encoder {
     CSC_HD void parse_lazy(u32 x0, u32 size) {   // compress_normal(size, true), csc_lz.cpp:156-199
         const u32 end = x0 + size;
         u32 x = x0;
-        Cand u1, u2;
+        Cand u1;
         u1.len = 1; u1.dist = 0;
-        bool got = false;
+        bool have = false;
         while (x < end) {
-            if (!got) { prefetch_fm(x + 1, end); u1 = find_best(x, end - x); }
-            if (u1.len == 1 || u1.len >= good) {
-                if (u1.dist == 0) encode_literal(S.lz[x]);
-                else { prefetch_fm(x + u1.len, end); encode_nonlit(u1); }
-                slide(x, u1.len, end);
-                x += u1.len;
-                if (u1.dist) ctx = S.lz[x - 1];
-                got = false;
+            if (!have || !(u1.len == 1 || u1.len >= good)) {
+                // the one probe site: u1 at x, or the lazy look-ahead u2 at x + 1
+                const u32 px = have ? x + 1 : x;
+                prefetch_fm(px + 1, end);
+                Cand c = find_best(px, end - px);
+                if (!have) { u1 = c; have = true; continue; }
+                if (second_better(u1, c)) {
+                    encode_literal(S.lz[x]);
+                    x++;
+                    u1 = c;
+                } else {
+                    prefetch_fm(x + u1.len, end);
+                    encode_nonlit(u1);
+                    slide(x + 1, u1.len - 1, end);
+                    x += u1.len;
+                    ctx = S.lz[x - 1];
+                    have = false;
+                }
                 continue;
             }
-            prefetch_fm(x + 2, end);
-            u2 = find_best(x + 1, end - x - 1);
-            if (second_better(u1, u2)) {
-                encode_literal(S.lz[x]);
-                x++;
-                u1 = u2;
-                got = true;
-            } else {
-                prefetch_fm(x + u1.len, end);
-                encode_nonlit(u1);
-                slide(x + 1, u1.len - 1, end);
-                x += u1.len;
-                ctx = S.lz[x - 1];
-                got = false;
-            }
+            if (u1.dist == 0) encode_literal(S.lz[x]);
+            else { prefetch_fm(x + u1.len, end); encode_nonlit(u1); }
+            slide(x, u1.len, end);
+            x += u1.len;
+            if (u1.dist) ctx = S.lz[x - 1];
+            have = false;
         }
     }
 
@@ -781,9 +825,10 @@ struct Encoder {
         encode_int(size);
         for (u32 i = 0; i < size; i++) {
             u32 c = S.lz[a + i];
-            u16 *row = S.p_lit + ctx * 256;
+            u32 row = ctx * 256;
             ctx = c;
             lit_bits(row, c);
+            flush_bits();
         }
     }
     // byte k of Forward_Delta's output (csc_filters.cpp:132-164) without materialising it
@@ -819,13 +864,15 @@ struct Encoder {
                     sctx = c0;
                     enc_bit(M.p_rle_flag, 1);
                     encode_matchlen_2(len - 11);
+                    flush_bits();
                     i = j;
                     pm1 = c0;
                     continue;
                 }
             }
             enc_bit(M.p_rle_flag, 0);
-            lit_bits(S.p_delta + sctx * 256, c0);
+            lit_bits(65536 + sctx * 256, c0);   // p_delta follows p_lit
+            flush_bits();
             sctx = c0;
             pm1 = c0;
             i++;

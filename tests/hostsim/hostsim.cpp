@@ -143,7 +143,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
             memcpy(g_dump.tail_dlt, tail_dlt.data(), seg.size() * 5 * 4);
         }
         std::vector<u32> D6((n + 31) / 32 + 1, 0), ht2(16384, 0), ht3(65536, 0);
-        std::vector<u16> p_lit(65536, 2048), p_delta(65536, 2048);
+        std::vector<u16> p_lit(131072, 2048);
         std::vector<ApUnit> ap(kApLimit + 2);
         u32 rc_cap = n * 2 + 65536 * 2, bc_cap = n * 2 + 65536 * 2;
         std::vector<u8> rc(rc_cap), bc(bc_cap), ev(rc_cap / 32768 + bc_cap / 32768 + 64);
@@ -156,7 +156,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         S.seg_size = seg.data(); S.seg_blk0 = seg_blk0.data(); S.binfo = binfo.data(); S.bbpb = bbpb.data();
         S.tail_dlt = tail_dlt.data(); S.dict_ok = dict_ok.data();
         S.P6 = P6.data(); S.L6 = L6.data(); S.K = K ? K : 1; S.Z2 = Z2.data(); S.Z6 = Z6.data(); S.D6 = D6.data();
-        S.ht2 = ht2.data(); S.ht3 = ht3.data(); S.p_lit = p_lit.data(); S.p_delta = p_delta.data(); S.ap = ap.data();
+        S.ht2 = ht2.data(); S.ht3 = ht3.data(); S.p_lit = p_lit.data(); S.p_delta = p_lit.data() + 65536; S.ap = ap.data();
         S.rc_out = rc.data(); S.rc_cap = rc_cap; S.bc_out = bc.data(); S.bc_cap = bc_cap;
         S.events = ev.data(); S.ev_cap = (u32)ev.size(); S.segout = so.data(); S.status = &status;
         S.trace = trace; S.trace_cap = (u32)trace_cap; S.trace_n = &tn;
