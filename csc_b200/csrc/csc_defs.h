@@ -16,7 +16,14 @@ typedef uint64_t u64;
 typedef int32_t i32;
 
 #if defined(__CUDACC__)
+// CSC_HD: ordinary function (inlined into its caller unless CSC_OUTLINE_ALL), CSC_HDF: always inline,
+// CSC_HDN: always out of line.  The serial engines are large; CSC_HDN marks the boundaries where
+// inlining would duplicate the hot loops (code size costs instruction-cache misses).
+#ifdef CSC_OUTLINE_ALL
 #define CSC_HD __host__ __device__ __noinline__
+#else
+#define CSC_HD __host__ __device__ inline
+#endif
 #define CSC_HDF __host__ __device__ __forceinline__
 #define CSC_HDN __host__ __device__ __noinline__
 #else

@@ -157,7 +157,7 @@ struct Encoder {
         if (len <= 16) direct16(val, len);
         else { direct16(val >> 16, len - 16); direct16(val & 0xFFFF, 16); }
     }
-    CSC_HD void flush_segment(u32 seg, u32 rc0, u32 bc0, u32 ev0) {   // csc_coder.cpp:40-74
+    CSC_HDN void flush_segment(u32 seg, u32 rc0, u32 bc0, u32 ev0) {   // csc_coder.cpp:40-74
         flush_bits();
         for (int i = 0; i < 5; i++) shift_low();
         // one byte is skipped, not stored (H3): the host substitutes the stale ring byte
@@ -174,7 +174,7 @@ struct Encoder {
     }
 
     // ------------------------------------------------------------------- model
-    CSC_HD void model_reset() {   // csc_model.cpp:88-111
+    CSC_HDN void model_reset() {   // csc_model.cpp:88-111
         for (u32 i = CSC_LANE; i < 64 * 3; i += CSC_NLANES) { M.p_state[i] = 2048; M.p_repdist[i] = 2048; }
         for (u32 i = CSC_LANE; i < 8 + 16 * 2 + 32 * 4; i += CSC_NLANES) M.p_dist[i] = 2048;
         for (u32 i = CSC_LANE; i < 128; i += CSC_NLANES) M.p_matchlen_extra3[i] = 2048;
@@ -397,7 +397,7 @@ struct Encoder {
     }
 
     // find_match (csc_mf.cpp:243-495): candidate list (M.cl / M.cd) in reference probe order.
-    CSC_HD u32 find_match(u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
+    CSC_HDN u32 find_match(u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
         const u8 *cur = S.lz + x;
         const u32 pos = vld + x;
         const u32 sb_end = x + limit;
@@ -557,7 +557,7 @@ struct Encoder {
     }
 
     // SlidePos (csc_mf.cpp:134-206): positions s+1 .. s+len-1 are passed over by a match.
-    CSC_HD void slide(u32 s, u32 len, u32 sb_end) {
+    CSC_HDN void slide(u32 s, u32 len, u32 sb_end) {
         if (len <= 1) return;
         u32 i0 = 1;
         while (i0 + 128 < len) i0 += 4;
@@ -601,7 +601,7 @@ struct Encoder {
             rep[0] = u.dist - 4;
         }
     }
-    CSC_HD void parse_lazy(u32 x0, u32 size) {   // compress_normal(size, true), csc_lz.cpp:156-199
+    CSC_HDN void parse_lazy(u32 x0, u32 size) {   // compress_normal(size, true), csc_lz.cpp:156-199
         const u32 end = x0 + size;
         u32 x = x0;
         Cand u1;
@@ -695,7 +695,7 @@ struct Encoder {
         for (int j = 0; j < 4; j++) rep[j] = ap[endi].rep[j];
     }
 
-    CSC_HD void parse_optimal(u32 x0, u32 size) {   // compress_advanced, csc_lz.cpp:207-333
+    CSC_HDN void parse_optimal(u32 x0, u32 size) {   // compress_advanced, csc_lz.cpp:207-333
         const u32 end = x0 + size;
         ApUnit *ap = S.ap;
         Cand t[64];
@@ -803,7 +803,7 @@ struct Encoder {
     }
 
     // ------------------------------------------------------------ run encoders
-    CSC_HD void lz_run(u32 a, u32 size) {   // LZ::EncodeNormal mode 2/3, csc_lz.cpp:61-100
+    CSC_HDN void lz_run(u32 a, u32 size) {   // LZ::EncodeNormal mode 2/3, csc_lz.cpp:61-100
         for (u32 off = 0; off < size;) {
             u32 sb = size - off;
             if (sb > kBlock) sb = kBlock;
@@ -814,14 +814,14 @@ struct Encoder {
         }
         encode_match(64, 0);   // end marker (:95-98)
     }
-    CSC_HD void skip_run(u32 a, u32 size) {   // mode 5: SlidePosFast (csc_mf.cpp:208-241)
+    CSC_HDN void skip_run(u32 a, u32 size) {   // mode 5: SlidePosFast (csc_mf.cpp:208-241)
         if (W) bits_or_not_range(S.D6, S.Z2, a, a + size);
     }
-    CSC_HD void bad_run(u32 a, u32 size) {   // CompressBad, csc_model.cpp:463-469
+    CSC_HDN void bad_run(u32 a, u32 size) {   // CompressBad, csc_model.cpp:463-469
         encode_int(size);
         for (u32 i = 0; i < size; i++) direct16(S.lz[a + i], 8);
     }
-    CSC_HD void entropy_run(u32 a, u32 size) {   // CompressLiterals, csc_model.cpp:448-461
+    CSC_HDN void entropy_run(u32 a, u32 size) {   // CompressLiterals, csc_model.cpp:448-461
         encode_int(size);
         for (u32 i = 0; i < size; i++) {
             u32 c = S.lz[a + i];
@@ -850,7 +850,7 @@ struct Encoder {
         }
         return (S.lz[a + j] - prev) & 0xFF;
     }
-    CSC_HD void delta_run(u32 a, u32 size, u32 chn) {   // Forward_Delta + CompressRLE, csc_model.cpp:471-513
+    CSC_HDN void delta_run(u32 a, u32 size, u32 chn) {   // Forward_Delta + CompressRLE, csc_model.cpp:471-513
         encode_int(size);
         u32 sctx = 0;
         u32 pm1 = 0;   // src[i-1]
@@ -880,7 +880,7 @@ struct Encoder {
     }
 
     // IsDuplicateBlock / TestFind (csc_lz.cpp:102-112, csc_mf.cpp:526-568): window ends at run_start
-    CSC_HD bool dup_block(u32 b0, u32 bsize, u32 run_start) {
+    CSC_HDN bool dup_block(u32 b0, u32 bsize, u32 run_start) {
         if (!W) return false;   // -m5 head table: handled by the bounded search path
         bool hit = false;
         for (u32 base = 0; base + 18 < bsize && !hit; base += CSC_NLANES) {
@@ -937,7 +937,7 @@ struct Encoder {
     }
 
     // one Compress() call (csc_encoder_main.cpp:85-146)
-    CSC_HD void compress_segment(u32 seg, u32 a, u32 size) {
+    CSC_HDN void compress_segment(u32 seg, u32 a, u32 size) {
         const u32 rc0 = rc_n, bc0 = bc_n, ev0 = ev_n;
         const bool use_filters = (S.cfg.flt_dlt + S.cfg.flt_txt + S.cfg.flt_exe) != 0;
         u32 last_type = DT_NORMAL, last_begin = 0, last_size = 0;

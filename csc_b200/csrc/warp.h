@@ -15,29 +15,29 @@ namespace cscb {
 #if defined(__CUDA_ARCH__)
 #define CSC_LANE (threadIdx.x & 31u)
 #define CSC_NLANES 32u
-CSC_HD void w_sync() { __syncwarp(); }
-CSC_HD bool w_any(bool p) { return __any_sync(0xFFFFFFFFu, p); }
-CSC_HD u32 w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
-CSC_HD u32 w_min(u32 v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
-CSC_HD u32 w_add(u32 v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
-CSC_HD void g_or(u32 *p, u32 m) { atomicOr(p, m); }
-CSC_HD void g_max(u32 *p, u32 v) { atomicMax(p, v); }
-CSC_HD u32 g_ld(const u32 *p) { return __ldcg(p); }   // L2-coherent read of lane-written data
-CSC_HD u32 ffs32(u32 m) { return (u32)__ffs((int)m); }
-CSC_HD void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+CSC_HDF void w_sync() { __syncwarp(); }
+CSC_HDF bool w_any(bool p) { return __any_sync(0xFFFFFFFFu, p); }
+CSC_HDF u32 w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+CSC_HDF u32 w_min(u32 v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+CSC_HDF u32 w_add(u32 v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
+CSC_HDF void g_or(u32 *p, u32 m) { atomicOr(p, m); }
+CSC_HDF void g_max(u32 *p, u32 v) { atomicMax(p, v); }
+CSC_HDF u32 g_ld(const u32 *p) { return __ldcg(p); }   // L2-coherent read of lane-written data
+CSC_HDF u32 ffs32(u32 m) { return (u32)__ffs((int)m); }
+CSC_HDF void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
 #define CSC_LANE 0u
 #define CSC_NLANES 1u
-CSC_HD void w_sync() {}
-CSC_HD bool w_any(bool p) { return p; }
-CSC_HD u32 w_ballot(bool p) { return p ? 1u : 0u; }
-CSC_HD u32 w_min(u32 v) { return v; }
-CSC_HD u32 w_add(u32 v) { return v; }
-CSC_HD void g_or(u32 *p, u32 m) { *p |= m; }
-CSC_HD void g_max(u32 *p, u32 v) { if (v > *p) *p = v; }
-CSC_HD u32 g_ld(const u32 *p) { return *p; }
-CSC_HD u32 ffs32(u32 m) { return (u32)__builtin_ffs((int)m); }
-CSC_HD void pf_l2(const void *) {}
+CSC_HDF void w_sync() {}
+CSC_HDF bool w_any(bool p) { return p; }
+CSC_HDF u32 w_ballot(bool p) { return p ? 1u : 0u; }
+CSC_HDF u32 w_min(u32 v) { return v; }
+CSC_HDF u32 w_add(u32 v) { return v; }
+CSC_HDF void g_or(u32 *p, u32 m) { *p |= m; }
+CSC_HDF void g_max(u32 *p, u32 v) { if (v > *p) *p = v; }
+CSC_HDF u32 g_ld(const u32 *p) { return *p; }
+CSC_HDF u32 ffs32(u32 m) { return (u32)__builtin_ffs((int)m); }
+CSC_HDF void pf_l2(const void *) {}
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -53,7 +53,7 @@ CSC_HDF u32 ld32u(const u8 *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2
 // Longest common prefix of a[0..limit) and b[0..limit): the byte-compare loop of
 // every probe in find_match (csc_mf.cpp:279,317,348,470), done 128 bytes per
 // step by the warp (4 bytes per lane).
-CSC_HD u32 lcp_bytes(const u8 *a, const u8 *b, u32 limit) {
+CSC_HDN u32 lcp_bytes(const u8 *a, const u8 *b, u32 limit) {
 #if defined(__CUDA_ARCH__)
     for (u32 k = 0; k < limit; k += 128) {
         u32 i = k + CSC_LANE * 4;
@@ -94,8 +94,8 @@ CSC_HD u32 lcp_bytes_zpad(const u8 *a, const u8 *b, u32 limit, u32 b_valid) {
     return limit;
 }
 
-CSC_HD bool bit_get(const u32 *map, u32 i) { return (g_ld(&map[i >> 5]) >> (i & 31)) & 1u; }
-CSC_HD bool bit_get_ro(const u32 *map, u32 i) { return (map[i >> 5] >> (i & 31)) & 1u; }
+CSC_HDF bool bit_get(const u32 *map, u32 i) { return (g_ld(&map[i >> 5]) >> (i & 31)) & 1u; }
+CSC_HDF bool bit_get_ro(const u32 *map, u32 i) { return (map[i >> 5] >> (i & 31)) & 1u; }
 
 // set bits [a, b) of a bitmap (lane-strided over words)
 CSC_HD void bits_set_range(u32 *map, u32 a, u32 b) {
