@@ -183,3 +183,37 @@ def test_golden_fixtures(hs):
         exp = np.frombuffer(bytes.fromhex(rec["stream_hex"]), np.uint8)
         assert same(hs.encode(d, 32768, rec["level"]), exp)
         assert same(hs.decode(exp, d.size), d)
+
+
+# ---------------------------------------------------------------- the CPU restatement (oracle/restate)
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+def test_restatement_pinned_to_reference(ref, level):
+    from oracle import restate
+    for name, d in EC.items():
+        dict_size = max(d.size, 32768)
+        exp = ref.encode(d, dict_size, level)
+        assert same(restate.encode(d, dict_size, level), exp), name
+        assert same(restate.decode(exp, d.size), d), name
+
+
+def test_restatement_window_wrap_and_segments(ref):
+    from oracle import restate
+    d = synth.mixed(700000, 8)
+    for level in (1, 3):
+        for dict_size in (40000, 200000):
+            for rs in (0, 100000):
+                exp = ref.encode(d, dict_size, level, rs)
+                assert same(restate.encode(d, dict_size, level, rs), exp)
+                assert same(restate.decode(exp, d.size), d)
+
+
+def test_restatement_matches_golden():
+    """pins the restatement without the reference (the GPU box has no /root/reference)"""
+    import hashlib
+    import json
+    from oracle import restate
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+    for rec in [r for r in g["streams"] if r["level"] <= 4]:
+        d = EC[rec["name"]]
+        out = restate.encode(d, max(d.size, 32768), rec["level"])
+        assert out.size == rec["size"] and hashlib.sha256(out.tobytes()).hexdigest() == rec["sha256"], rec
