@@ -32,6 +32,10 @@ typedef int32_t i32;
 #define CSC_HDN
 #endif
 
+#if !defined(__CUDACC__)
+struct uint4 { unsigned int x, y, z, w; };   // host simulation only
+#endif
+
 namespace cscb {
 
 // ---- block types (csc_typedef.h:20-41) -------------------------------------

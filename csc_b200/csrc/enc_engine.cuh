@@ -54,6 +54,11 @@ struct Encoder {
     i32 err;
     u32 tr_n;
     u32 vld, W, K, good;
+    // parser -> coder command ring (two-warp pipeline of the lazy modes); null = execute in place
+    uint4 *ring;
+    volatile u32 *vhead, *vtail;
+    u32 ring_cap, head, tail;
+    u32 seg_rc0, seg_bc0, seg_ev0;
 
     CSC_HD Encoder(const EncStream &s, ModelSmall &m) : S(s), M(m) {}
 
@@ -587,16 +592,86 @@ struct Encoder {
         }
     }
 
+    // ---------------------------------------------------- parser -> coder commands
+    // The lazy parser never reads model or coder state, so for -m1/-m2 the stream is cut in two:
+    // one warp parses and emits packet commands, a second warp of the same CTA runs the adaptive
+    // coder on them (k_encode, pair mode).  With ring == nullptr (optimal parser, host simulation)
+    // a command is executed on the spot.
+    enum : u32 { OP_LIT = 1, OP_MATCH, OP_REP, OP_REP01, OP_INT, OP_BAD, OP_ENTROPY, OP_DELTA, OP_FLUSH, OP_END };
+    CSC_HDN void exec(u32 op, u32 a, u32 b, u32 c) {
+        if (err) return;
+        switch (op) {
+            case OP_LIT: encode_literal(a); break;
+            case OP_MATCH: encode_match(a, b); if (c < 0x100) ctx = c; break;
+            case OP_REP: encode_rep(a, b); ctx = c; break;
+            case OP_REP01: encode_rep0len1(); ctx = c; break;
+            case OP_INT: encode_int(a); break;
+            case OP_BAD: bad_run(a, b); break;
+            case OP_ENTROPY: entropy_run(a, b); break;
+            case OP_DELTA: delta_run(a, b, c); break;
+            case OP_FLUSH:
+                flush_segment(a, seg_rc0, seg_bc0, seg_ev0);
+                seg_rc0 = rc_n; seg_bc0 = bc_n; seg_ev0 = ev_n;
+                break;
+            default: break;
+        }
+    }
+#if defined(__CUDACC__)
+    __device__ __forceinline__ bool spin(volatile u32 *flag, u32 mine, bool want_equal) {   // false on watchdog expiry
+        long long t0 = clock64();
+        while ((*flag == mine) == want_equal) {
+            __nanosleep(40);
+            if (clock64() - t0 > 8000000000ll) return false;   // ~4 s: never hang the GPU
+        }
+        return true;
+    }
+    __device__ __noinline__ void ring_push(u32 op, u32 a, u32 b, u32 c) {
+        if (head - tail >= ring_cap) {   // refresh our view of the consumer, wait while full
+            tail = *vtail;
+            if (head - tail >= ring_cap) {
+                if (!spin(vtail, tail, true)) { err = kErrUnsupported; return; }
+                tail = *vtail;
+            }
+        }
+        ring[head % ring_cap] = make_uint4(op, a, b, c);
+        __threadfence();
+        head++;
+        __syncwarp();
+        if (CSC_LANE == 0) *vhead = head;
+    }
+    __device__ __noinline__ uint4 ring_pop() {
+        if (tail == head) {
+            head = *vhead;
+            if (tail == head) {
+                if (!spin(vhead, tail, true)) { err = kErrUnsupported; return make_uint4(OP_END, (u32)kErrUnsupported, 0, 0); }
+                head = *vhead;
+            }
+        }
+        __threadfence();
+        uint4 v = __ldcg(&ring[tail % ring_cap]);
+        tail++;
+        __syncwarp();
+        if (CSC_LANE == 0) *vtail = tail;
+        return v;
+    }
+#endif
+    CSC_HDF void emit(u32 op, u32 a, u32 b, u32 c) {
+#if defined(__CUDA_ARCH__)
+        if (ring) { ring_push(op, a, b, c); return; }
+#endif
+        exec(op, a, b, c);
+    }
+
     // ------------------------------------------------------------- lazy parser
-    CSC_HD void encode_nonlit(Cand u) {   // csc_lz.cpp:127-154
+    CSC_HD void encode_nonlit(Cand u, u32 newctx) {   // csc_lz.cpp:127-154 (+ SetLiteralCtx of the caller)
         if (u.dist <= 4) {
-            if (u.len == 1 && u.dist == 1) { encode_rep0len1(); return; }
-            encode_rep(u.dist - 1, u.len - 2);
+            if (u.len == 1 && u.dist == 1) { emit(OP_REP01, 0, 0, newctx); return; }
+            emit(OP_REP, u.dist - 1, u.len - 2, newctx);
             u32 d = rep[u.dist - 1];
             for (u32 j = u.dist - 1; j > 0; j--) rep[j] = rep[j - 1];
             rep[0] = d;
         } else {
-            encode_match(u.dist - 5, u.len - 2);
+            emit(OP_MATCH, u.dist - 5, u.len - 2, newctx);
             rep[3] = rep[2]; rep[2] = rep[1]; rep[1] = rep[0];
             rep[0] = u.dist - 4;
         }
@@ -615,24 +690,22 @@ struct Encoder {
                 Cand c = find_best(px, end - px);
                 if (!have) { u1 = c; have = true; continue; }
                 if (second_better(u1, c)) {
-                    encode_literal(S.lz[x]);
+                    emit(OP_LIT, S.lz[x], 0, 0);
                     x++;
                     u1 = c;
                 } else {
                     prefetch_fm(x + u1.len, end);
-                    encode_nonlit(u1);
+                    encode_nonlit(u1, S.lz[x + u1.len - 1]);
                     slide(x + 1, u1.len - 1, end);
                     x += u1.len;
-                    ctx = S.lz[x - 1];
                     have = false;
                 }
                 continue;
             }
-            if (u1.dist == 0) encode_literal(S.lz[x]);
-            else { prefetch_fm(x + u1.len, end); encode_nonlit(u1); }
+            if (u1.dist == 0) emit(OP_LIT, S.lz[x], 0, 0);
+            else { prefetch_fm(x + u1.len, end); encode_nonlit(u1, S.lz[x + u1.len - 1]); }
             slide(x, u1.len, end);
             x += u1.len;
-            if (u1.dist) ctx = S.lz[x - 1];
             have = false;
         }
     }
@@ -681,14 +754,12 @@ struct Encoder {
             u32 nx = ap[i].next_pos;
             u32 d = ap[nx].dist;
             if (d == 0) {
-                encode_literal(ap[i].lit);
+                emit(OP_LIT, ap[i].lit, 0, 0);
             } else if (d <= 4) {
-                if (nx - i == 1 && d == 1) encode_rep0len1();
-                else encode_rep(d - 1, nx - i - 2);
-                ctx = ap[nx - 1].lit;
+                if (nx - i == 1 && d == 1) emit(OP_REP01, 0, 0, ap[nx - 1].lit);
+                else emit(OP_REP, d - 1, nx - i - 2, ap[nx - 1].lit);
             } else {
-                encode_match(d - 5, nx - i - 2);
-                ctx = ap[nx - 1].lit;
+                emit(OP_MATCH, d - 5, nx - i - 2, ap[nx - 1].lit);
             }
             i = nx;
         }
@@ -705,7 +776,7 @@ struct Encoder {
             prefetch_fm(x + 1, end);
             find_match_price(x, end - x, state, rep, t);
             if (t[0].dist == 0) {
-                encode_literal(S.lz[x]);
+                emit(OP_LIT, S.lz[x], 0, 0);
                 i++; x++;
                 continue;
             }
@@ -757,7 +828,7 @@ struct Encoder {
                 }
                 if (t[0].len == 1 && apcur + 1 == apend) {
                     ap_backward(apcur);
-                    encode_literal(ap[apcur].lit);
+                    emit(OP_LIT, ap[apcur].lit, 0, 0);
                     i += apcur;
                     x++; i++;
                     break;
@@ -766,11 +837,10 @@ struct Encoder {
                 if (t[0].len >= good || (t[0].len > 1 && t[0].len + apcur >= aplimit)) {
                     ap_backward(apcur);
                     i += apcur;
-                    encode_nonlit(t[0]);
+                    encode_nonlit(t[0], S.lz[x + t[0].len - 1]);
                     slide(x, t[0].len, end);
                     i += t[0].len;
                     x += t[0].len;
-                    ctx = S.lz[x - 1];
                     break;
                 }
                 u32 base = ap[apcur].price;
@@ -812,7 +882,7 @@ struct Encoder {
             off += sb;
             if (err) return;
         }
-        encode_match(64, 0);   // end marker (:95-98)
+        emit(OP_MATCH, 64, 0, 0x100);   // end marker (:95-98), literal context untouched
     }
     CSC_HDN void skip_run(u32 a, u32 size) {   // mode 5: SlidePosFast (csc_mf.cpp:208-241)
         if (W) bits_or_not_range(S.D6, S.Z2, a, a + size);
@@ -912,33 +982,32 @@ struct Encoder {
     CSC_HD void compress_run(u32 a, u32 size, u32 type, u32 first_blk) {   // compress_block, csc_encoder_main.cpp:35-83
         if (!size) return;
         if (type == DT_NORMAL || type == DT_FAST) {
-            encode_int(DT_NORMAL);
+            emit(OP_INT, DT_NORMAL, 0, 0);
             lz_run(a, size);
         } else if (type == DT_EXE) {
-            encode_int(DT_EXE);
+            emit(OP_INT, DT_EXE, 0, 0);
             lz_run(a, size);
         } else if (type == DT_ENGTXT) {
-            if (S.dict_ok[first_blk]) { encode_int(DT_ENGTXT); encode_int(size); }
-            else encode_int(DT_NORMAL);
+            if (S.dict_ok[first_blk]) { emit(OP_INT, DT_ENGTXT, 0, 0); emit(OP_INT, size, 0, 0); }
+            else emit(OP_INT, DT_NORMAL, 0, 0);
             lz_run(a, size);
         } else if (type == DT_BAD) {
-            encode_int(DT_BAD);
+            emit(OP_INT, DT_BAD, 0, 0);
             skip_run(a, size);
-            bad_run(a, size);
+            emit(OP_BAD, a, size, 0);
         } else if (type == DT_ENTROPY) {
-            encode_int(DT_ENTROPY);
+            emit(OP_INT, DT_ENTROPY, 0, 0);
             skip_run(a, size);
-            entropy_run(a, size);
+            emit(OP_ENTROPY, a, size, 0);
         } else {
-            encode_int(type);
+            emit(OP_INT, type, 0, 0);
             skip_run(a, size);
-            delta_run(a, size, dlt_channels(type - DT_DLT));
+            emit(OP_DELTA, a, size, dlt_channels(type - DT_DLT));
         }
     }
 
     // one Compress() call (csc_encoder_main.cpp:85-146)
     CSC_HDN void compress_segment(u32 seg, u32 a, u32 size) {
-        const u32 rc0 = rc_n, bc0 = bc_n, ev0 = ev_n;
         const bool use_filters = (S.cfg.flt_dlt + S.cfg.flt_txt + S.cfg.flt_exe) != 0;
         u32 last_type = DT_NORMAL, last_begin = 0, last_size = 0;
         u32 bpb = 0;
@@ -970,7 +1039,7 @@ struct Encoder {
             if (last_type != t) {   // (size limit of :128 cannot trigger inside one Read())
                 if (last_size) {
                     compress_run(a + last_begin, last_size, last_type, last_blk);
-                    encode_int(0);
+                    emit(OP_INT, 0, 0, 0);
                 }
                 last_begin = i;
                 last_size = 0;
@@ -983,28 +1052,58 @@ struct Encoder {
         }
         if (last_size) {
             compress_run(a + last_begin, last_size, last_type, last_blk);
-            encode_int(1);
-            flush_segment(seg, rc0, bc0, ev0);
+            emit(OP_INT, 1, 0, 0);
+            emit(OP_FLUSH, seg, 0, 0);
         }
     }
 
-    CSC_HD void run() {
+    CSC_HD void init_common() {
         vld = S.cfg.vld_rge; W = S.cfg.ht_width; K = S.K; good = S.cfg.good_len;
         err = 0; tr_n = 0;
         rc_n = bc_n = ev_n = 0;
+        seg_rc0 = seg_bc0 = seg_ev0 = 0;
+        head = tail = 0;
         coder_reset();
-        model_reset();
+        state = 0; ctx = 0; lp_rebuild = 0;
         rep[0] = rep[1] = rep[2] = rep[3] = S.cfg.wnd_size;   // csc_lz.cpp:46-49
+    }
+    CSC_HD void parse_stream() {
         u32 a = 0;
         for (u32 s = 0; s < S.nseg && !err; s++) {
             compress_segment(s, a, S.seg_size[s]);
             a += S.seg_size[s];
         }
+    }
+    // whole stream in one warp (optimal parser, host simulation)
+    CSC_HD void run() {
+        ring = nullptr;
+        init_common();
+        model_reset();
+        parse_stream();
         if (CSC_LANE == 0) {
             *S.status = err;
             if (S.trace_n) *S.trace_n = tr_n;
         }
     }
+#if defined(__CUDACC__)
+    // pair mode: this warp parses and feeds the ring
+    __device__ void run_parser() {
+        init_common();
+        parse_stream();
+        ring_push(OP_END, (u32)err, 0, 0);
+    }
+    // pair mode: this warp owns the model and the coder
+    __device__ void run_coder() {
+        init_common();
+        model_reset();
+        for (;;) {
+            uint4 c = ring_pop();
+            if (c.x == OP_END) { if (!err && (i32)c.y < 0) err = (i32)c.y; break; }
+            exec(c.x, c.y, c.z, c.w);
+        }
+        if (CSC_LANE == 0) *S.status = err;
+    }
+#endif
 };
 
 }  // namespace cscb

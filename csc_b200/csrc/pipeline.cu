@@ -85,7 +85,7 @@ struct Ctx {
     u32 *d_p2bits = nullptr;
     DevBuf lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
-        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr;
+        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings;
     PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta;
     Timer tm;
     CSCB200_Stats stats;
@@ -327,8 +327,15 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     // ---- serial engines, one stream per warp
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, C.dev);
-    u32 grid = std::min<u32>((ns + kEncWarps - 1) / kEncWarps, (u32)nsm * 8);
-    k_encode<<<grid, kEncWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns, d_queue, C.d_p2bits);
+    const bool pair_mode = es[0].cfg.lz_mode == 2 && !getenv("CSC_B200_NO_PAIR");
+    if (pair_mode) {
+        u32 grid = std::min<u32>((ns + kEncWarps / 2 - 1) / (kEncWarps / 2), (u32)nsm * 16);
+        if (C.rings.ensure((size_t)grid * (kEncWarps / 2) * kRingCap * sizeof(uint4))) return kErrCuda;
+        k_encode_pair<<<grid, kEncWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns, C.rings.as<uint4>());
+    } else {
+        u32 grid = std::min<u32>((ns + kEncWarps - 1) / kEncWarps, (u32)nsm * 8);
+        k_encode<<<grid, kEncWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns, d_queue, C.d_p2bits);
+    }
     T.mark(st);                                                                   // 8
     launches += 1;
     CK(cudaGetLastError());
