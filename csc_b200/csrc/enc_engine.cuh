@@ -118,7 +118,7 @@ struct Encoder {
         q_push((u32)(&pr - reinterpret_cast<u16 *>(&M)), bit);
     }
     CSC_HDF void enc_bit_g(u32 gidx, u32 bit) { q_push(kSlotGlobal | gidx, bit); }   // p_lit / p_delta entry
-    CSC_HD void flush_bits() {
+    CSC_HDN void flush_bits() {
         const u32 n = bq_n;
         if (!n) return;
         const u32 bits = bq_bits;
@@ -140,16 +140,20 @@ struct Encoder {
             M.bq_p[k] = (u16)v;
         }
 #endif
+        u64 lo = low;
+        u32 rg = range;
+#pragma unroll 1
         for (u32 k = 0; k < n; k++) {
-            u32 bound = (range >> 12) * M.bq_p[k];
-            if ((bits >> k) & 1) range = bound;
-            else { low += bound; range -= bound; }
-            if (range < (1u << 24)) { range <<= 8; shift_low(); }
+            u32 bound = (rg >> 12) * M.bq_p[k];
+            if ((bits >> k) & 1) rg = bound;
+            else { lo += bound; rg -= bound; }
+            if (rg < (1u << 24)) { rg <<= 8; low = lo; shift_low(); lo = low; }
         }
+        low = lo; range = rg;
         w_sync();
         bq_n = 0; bq_bits = 0;
     }
-    CSC_HD void direct16(u32 val, u32 len) {   // csc_coder.cpp:76-87
+    CSC_HDN void direct16(u32 val, u32 len) {   // csc_coder.cpp:76-87
         flush_bits();   // keep RC decisions ahead of later raw bits (block-event order)
         bc_val = (bc_val << len) | val;
         bc_bits += len;
@@ -195,12 +199,12 @@ struct Encoder {
     }
 
     // 8 literal bits under the order-1 row `row` (index of the row start in p_lit/p_delta, csc_model.cpp:176-182)
-    CSC_HD void lit_bits(u32 row, u32 c) {
+    CSC_HDN void lit_bits(u32 row, u32 c) {
         u32 cc = c | 0x100;
 #pragma unroll
         for (int k = 0; k < 8; k++) enc_bit_g(row + (cc >> (8 - k)), (cc >> (7 - k)) & 1);
     }
-    CSC_HD void encode_literal(u32 c) {   // csc_model.cpp:169-183
+    CSC_HDN void encode_literal(u32 c) {   // csc_model.cpp:169-183
         trace(0, c, 0);
         enc_bit(M.p_state[state * 3 + 0], 0);
         state = (state * 4) & 0x3F;
@@ -209,7 +213,7 @@ struct Encoder {
         lit_bits(row, c);
         flush_bits();
     }
-    CSC_HD void encode_matchlen_1(u32 len) {   // csc_model.cpp:113-145
+    CSC_HDN void encode_matchlen_1(u32 len) {   // csc_model.cpp:113-145
         if (len < 16) {
             u16 *p;
             if (len < 8) {
@@ -230,7 +234,7 @@ struct Encoder {
             do { enc_bit(M.p_matchlen_extra3[c >> 7], (c >> 6) & 1); c <<= 1; } while (c < 0x4000);
         }
     }
-    CSC_HD void encode_matchlen_2(u32 len) {   // csc_model.cpp:147-159
+    CSC_HDN void encode_matchlen_2(u32 len) {   // csc_model.cpp:147-159
         if (len >= 143) {
             encode_matchlen_1(143);
             flush_bits();
@@ -241,7 +245,7 @@ struct Encoder {
         }
         encode_matchlen_1(len);
     }
-    CSC_HD void encode_rep0len1() {   // csc_model.cpp:198-207
+    CSC_HDN void encode_rep0len1() {   // csc_model.cpp:198-207
         trace(2, 0, 0);
         enc_bit(M.p_state[state * 3 + 0], 1);
         enc_bit(M.p_state[state * 3 + 1], 0);
@@ -250,7 +254,7 @@ struct Encoder {
         state = (state * 4 + 2) & 0x3F;
         flush_bits();
     }
-    CSC_HD void encode_rep(u32 idx, u32 lencode) {   // csc_model.cpp:218-232
+    CSC_HDN void encode_rep(u32 idx, u32 lencode) {   // csc_model.cpp:218-232
         trace(3, lencode, idx);
         enc_bit(M.p_state[state * 3 + 0], 1);
         enc_bit(M.p_state[state * 3 + 1], 0);
@@ -262,7 +266,7 @@ struct Encoder {
         state = (state * 4 + 3) & 0x3F;
         flush_bits();
     }
-    CSC_HD void encode_match(u32 dist, u32 lencode) {   // csc_model.cpp:301-366
+    CSC_HDN void encode_match(u32 dist, u32 lencode) {   // csc_model.cpp:301-366
         trace(1, lencode, dist);
         enc_bit(M.p_state[state * 3 + 0], 1);
         enc_bit(M.p_state[state * 3 + 1], 1);
@@ -287,7 +291,7 @@ struct Encoder {
         state = (state * 4 + 1) & 0x3F;
         flush_bits();
     }
-    CSC_HD void encode_int(u32 num) {   // csc_model.cpp:389-414
+    CSC_HDN void encode_int(u32 num) {   // csc_model.cpp:389-414
         u32 slot = num ? ilog2(num) : 0;
         direct(slot, 5);
         if (slot == 0) direct(num, 1);
@@ -296,7 +300,7 @@ struct Encoder {
 
     // ------------------------------------------------------------------ prices
     CSC_HD u32 bitprice(u32 p, u32 bit) const { return M.p2bits[(bit ? p : 4096u - p) >> 3]; }
-    CSC_HD u32 literal_price(u32 fstate, u32 fctx, u32 c) const {   // csc_model.cpp:185-196
+    CSC_HDN u32 literal_price(u32 fstate, u32 fctx, u32 c) const {   // csc_model.cpp:185-196
         u32 r = bitprice(M.p_state[fstate * 3], 0);
         const u16 *row = S.p_lit + fctx * 256;
         u32 cc = c | 0x100;
@@ -334,7 +338,7 @@ struct Encoder {
         }
         return r;
     }
-    CSC_HD u32 matchlen_price(u32 lencode) {   // csc_model.cpp:286-299
+    CSC_HDN u32 matchlen_price(u32 lencode) {   // csc_model.cpp:286-299
         if (lencode >= 32) return 128 * 6;
         if (lp_rebuild-- == 0) {
             w_sync();
@@ -363,7 +367,7 @@ struct Encoder {
 
     // newest position < bound on the 6-byte chain of x that is still in the table
     // (= slot 0 of the reference bucket at the time the window ended at `bound`)
-    CSC_HD u32 newest_alive6(u32 x, u32 bound) const {
+    CSC_HDN u32 newest_alive6(u32 x, u32 bound) const {
         u32 src = x, k = 0;
         for (;;) {
             u32 e = S.P6[(size_t)src * K + k];
@@ -375,7 +379,7 @@ struct Encoder {
     }
 
     // warm the lines the next find_match(y) will need while the coder is busy with a packet
-    CSC_HD void prefetch_fm(u32 y, u32 sb_end) {
+    CSC_HDN void prefetch_fm(u32 y, u32 sb_end) {
         if (y >= sb_end) return;
         if (W) { pf_l2(S.P6 + (size_t)y * K); pf_l2(S.L6 + (size_t)y * K); }
         u32 w = word_at(y, sb_end);
@@ -551,7 +555,7 @@ struct Encoder {
         if (u2.len < u1.len && u2.len + 2 >= u1.len && u1.dist > 4 && (u1.dist >> (4 * (u1.len - u2.len))) > u2.dist) return true;
         return false;
     }
-    CSC_HD Cand find_best(u32 x, u32 limit) {   // FindMatch, csc_mf.cpp:497-524
+    CSC_HDN Cand find_best(u32 x, u32 limit) {   // FindMatch, csc_mf.cpp:497-524
         u32 n = find_match(x, limit, rep[0], rep[1], rep[2], rep[3]);
         Cand best; best.len = 1; best.dist = 0;
         for (u32 i = 0; i < n; i++) {
@@ -566,15 +570,13 @@ struct Encoder {
         if (len <= 1) return;
         u32 i0 = 1;
         while (i0 + 128 < len) i0 += 4;
-        for (u32 i = 1 + 4 * CSC_LANE; i < i0; i += 4 * CSC_NLANES) {
+#pragma unroll 1
+        for (u32 i = 1 + CSC_LANE; i < len; i += CSC_NLANES) {
+            if (i < i0 && ((i - 1) & 3)) continue;   // inside the skip zone only every 4th position (:140-145)
             u32 q = s + i;
-            g_max(&S.ht2[hash2_at(q, sb_end)], vld + q);
-            g_max(&S.ht3[hash3_at(q, sb_end)], vld + q);
-        }
-        for (u32 i = i0 + CSC_LANE; i < len; i += CSC_NLANES) {
-            u32 q = s + i;
-            g_max(&S.ht2[hash2_at(q, sb_end)], vld + q);
-            g_max(&S.ht3[hash3_at(q, sb_end)], vld + q);
+            u32 w = word_at(q, sb_end);
+            g_max(&S.ht2[h2_of(w)], vld + q);
+            g_max(&S.ht3[h3_of(w)], vld + q);
         }
         w_sync();
         if (W) {
@@ -584,6 +586,7 @@ struct Encoder {
                 u32 e = newest_alive6(first, first);
                 if (e != kNone) kill6(e);
             }
+#pragma unroll 1
             for (u32 i = i0 + 1 + CSC_LANE; i < len; i += CSC_NLANES) {
                 u32 q = s + i;
                 if (S.P6[(size_t)q * K] == q - 1) kill6(q - 1);   // same hash as the previous slid position
@@ -663,7 +666,7 @@ struct Encoder {
     }
 
     // ------------------------------------------------------------- lazy parser
-    CSC_HD void encode_nonlit(Cand u, u32 newctx) {   // csc_lz.cpp:127-154 (+ SetLiteralCtx of the caller)
+    CSC_HDN void encode_nonlit(Cand u, u32 newctx) {   // csc_lz.cpp:127-154 (+ SetLiteralCtx of the caller)
         if (u.dist <= 4) {
             if (u.len == 1 && u.dist == 1) { emit(OP_REP01, 0, 0, newctx); return; }
             emit(OP_REP, u.dist - 1, u.len - 2, newctx);
@@ -713,7 +716,7 @@ struct Encoder {
     // ---------------------------------------------------------- optimal parser
     // FindMatchWithPrice (csc_mf.cpp:584-625): t[0] longest candidate, t[1] rep0len1,
     // t[2..] price per length.
-    CSC_HD void find_match_price(u32 x, u32 limit, u32 fstate, const u32 *rp, Cand *t) {
+    CSC_HDN void find_match_price(u32 x, u32 limit, u32 fstate, const u32 *rp, Cand *t) {
         u32 n = find_match(x, limit, rp[0], rp[1], rp[2], rp[3]);
         if (n == 0) { t[0].len = 1; t[0].dist = 0; }
         else { t[0].len = M.cl[n - 1]; t[0].dist = M.cd[n - 1]; }
@@ -743,7 +746,7 @@ struct Encoder {
         }
     }
 
-    CSC_HD void ap_backward(u32 endi) {   // csc_lz.cpp:335-362
+    CSC_HDN void ap_backward(u32 endi) {   // csc_lz.cpp:335-362
         ApUnit *ap = S.ap;
         for (u32 i = endi; i;) {
             u32 b = ap[i].back_pos;
@@ -979,7 +982,7 @@ struct Encoder {
         return hit;
     }
 
-    CSC_HD void compress_run(u32 a, u32 size, u32 type, u32 first_blk) {   // compress_block, csc_encoder_main.cpp:35-83
+    CSC_HDN void compress_run(u32 a, u32 size, u32 type, u32 first_blk) {   // compress_block, csc_encoder_main.cpp:35-83
         if (!size) return;
         if (type == DT_NORMAL || type == DT_FAST) {
             emit(OP_INT, DT_NORMAL, 0, 0);

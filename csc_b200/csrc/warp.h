@@ -98,7 +98,7 @@ CSC_HDF bool bit_get(const u32 *map, u32 i) { return (g_ld(&map[i >> 5]) >> (i &
 CSC_HDF bool bit_get_ro(const u32 *map, u32 i) { return (map[i >> 5] >> (i & 31)) & 1u; }
 
 // set bits [a, b) of a bitmap (lane-strided over words)
-CSC_HD void bits_set_range(u32 *map, u32 a, u32 b) {
+CSC_HDN void bits_set_range(u32 *map, u32 a, u32 b) {
     if (a >= b) return;
     u32 w0 = a >> 5, w1 = (b - 1) >> 5;
     for (u32 w = w0 + CSC_LANE; w <= w1; w += CSC_NLANES) {
@@ -111,7 +111,7 @@ CSC_HD void bits_set_range(u32 *map, u32 a, u32 b) {
 }
 
 // dst[a,b) |= ~src[a,b)
-CSC_HD void bits_or_not_range(u32 *dst, const u32 *src, u32 a, u32 b) {
+CSC_HDN void bits_or_not_range(u32 *dst, const u32 *src, u32 a, u32 b) {
     if (a >= b) return;
     u32 w0 = a >> 5, w1 = (b - 1) >> 5;
     for (u32 w = w0 + CSC_LANE; w <= w1; w += CSC_NLANES) {
