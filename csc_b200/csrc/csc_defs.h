@@ -129,6 +129,13 @@ struct EncStream {
     const u32 *Z2;         // bitmap: HASH2 % 16 == 0 (SlidePosFast / TestFind sampling)
     const u32 *Z6;         // bitmap: HASH6 == 0 (lasth6 start value, csc_mf.cpp:136)
     u32 *D6;               // bitmap: position not (or no longer) in the 6-byte table
+    // 2-/3-byte single-slot tables as chains: nearest earlier position with equal HASH3 / HASH2 among
+    // the blocks the analyzer typed as LZ-parsed, + forward match length; D23 marks positions that
+    // the reference never inserted (SlidePos skip zone, SlidePosFast runs)
+    const u32 *P3; const u16 *L3;
+    const u32 *P2; const u16 *L2;
+    u32 *D23;
+    const u8 *blk_nolz;    // [nblk] block left out of the 2-/3-byte chains (statically typed BAD/ENTROPY/DLT)
     u32 *ht2;              // [16 Ki] 2-byte table, emulated directly (csc_mf.h:17-18)
     u32 *ht3;              // [64 Ki] 3-byte table
     // model in global memory

@@ -54,6 +54,7 @@ struct Encoder {
     i32 err;
     u32 tr_n;
     u32 vld, W, K, good;
+    bool tmode, want_tables;   // 2-/3-byte tables: false = chains + liveness bits, true = real tables (after a flip)
     // parser -> coder command ring (two-warp pipeline of the lazy modes); null = execute in place
     uint4 *ring;
     volatile u32 *vhead, *vtail;
@@ -391,6 +392,20 @@ struct Encoder {
 
     CSC_HDF void push_cand(u32 &cnt, u32 len, u32 dist) { M.cl[cnt] = len; M.cd[cnt] = dist; cnt++; }
 
+    // a table candidate whose full match length ml is already known: same bookkeeping as probe()
+    CSC_HDF bool take(u32 ml, u32 d, u32 &minlen, u32 &cnt) {
+        if (ml <= minlen) return false;
+        minlen = ml;
+        if (ml <= 6 && d >= mf_bound(ml)) return false;
+        push_cand(cnt, ml, 4 + d);
+        return ml >= good;
+    }
+    // first entry at or behind e on a 2-/3-byte chain that the reference really inserted
+    CSC_HDN u32 alive23(const u32 *chain, u32 e) const {
+        while (e != kNone && bit_get(S.D23, e)) e = chain[e];
+        return e;
+    }
+
     // one table / rep probe once the candidate is known to be in range: reference semantics of
     // "pre-check byte at minlen, full compare, update minlen, bound filter, record, good_len stop"
     // returns true when every further probe is disabled (dist poisoned)
@@ -411,13 +426,13 @@ struct Encoder {
         const u32 pos = vld + x;
         const u32 sb_end = x + limit;
         u32 cnt = 0, minlen = 1, dist = 0;
-        // ---- issue every independent load first: tables, candidate row, first probe bytes
-        const u32 w0 = word_at(x, sb_end);
-        const u32 h2 = h2_of(w0), h3 = h3_of(w0);
-        const u32 e2 = g_ld(&S.ht2[h2]), e3 = g_ld(&S.ht3[h3]);
-        // candidate row: entry k, its length and its liveness bit are fetched by lane k
+        // ---- issue every independent load first: candidate row, 2-/3-byte candidates, first probe bytes
+        // candidate row: entry k, its length and its liveness bit are fetched by lane k; in chain mode
+        // lanes 8 / 9 fetch the 3-byte / 2-byte chain candidates the same way
         u32 re = kNone, rl = 0;
         bool rdead = false;
+        u32 e2 = 0, e3 = 0, l2 = 0, l3 = 0, h2 = 0, h3 = 0;   // table entries as reference pos_ values (0 = empty)
+        bool known2 = false, known3 = false;                    // match length already known (chain mode)
 #if defined(__CUDA_ARCH__)
         if (CSC_LANE < K) {
             const size_t at = (size_t)x * K + CSC_LANE;
@@ -425,17 +440,54 @@ struct Encoder {
             rl = S.L6[at];
             if (re != kNone) rdead = dead6(re);
         }
+        if (!tmode) {
+            u32 ce = kNone, cl = 0;
+            bool cdead = false;
+            if (CSC_LANE == 8) { ce = S.P3[x]; cl = S.L3[x]; }
+            if (CSC_LANE == 9) { ce = S.P2[x]; cl = S.L2[x]; }
+            if (ce != kNone) cdead = bit_get(S.D23, ce);
+            const u32 x3 = __shfl_sync(0xFFFFFFFFu, ce, 8), x2 = __shfl_sync(0xFFFFFFFFu, ce, 9);
+            l3 = __shfl_sync(0xFFFFFFFFu, cl, 8); l2 = __shfl_sync(0xFFFFFFFFu, cl, 9);
+            const u32 deadm = __ballot_sync(0xFFFFFFFFu, cdead);
+            known3 = known2 = true;
+            e3 = x3; e2 = x2;
+            if (deadm & 0x100) { e3 = alive23(S.P3, x3); known3 = false; }
+            if (deadm & 0x200) { e2 = alive23(S.P2, x2); known2 = false; }
+            e3 = (e3 == kNone) ? 0 : vld + e3;
+            e2 = (e2 == kNone) ? 0 : vld + e2;
+        }
+#else
+        if (!tmode) {
+            u32 x3 = S.P3[x], x2 = S.P2[x];
+            l3 = S.L3[x]; l2 = S.L2[x];
+            known3 = known2 = true;
+            if (x3 != kNone && bit_get(S.D23, x3)) { x3 = alive23(S.P3, x3); known3 = false; }
+            if (x2 != kNone && bit_get(S.D23, x2)) { x2 = alive23(S.P2, x2); known2 = false; }
+            e3 = (x3 == kNone) ? 0 : vld + x3;
+            e2 = (x2 == kNone) ? 0 : vld + x2;
+        }
 #endif
         const bool deep = limit > 1;
-        const u32 c1 = (w0 >> 8) & 0xFF;
+        u32 c1;
+        if (tmode) {
+            const u32 w0 = word_at(x, sb_end);
+            h2 = h2_of(w0); h3 = h3_of(w0);
+            e2 = g_ld(&S.ht2[h2]); e3 = g_ld(&S.ht3[h3]);
+            c1 = (w0 >> 8) & 0xFF;
+        } else {
+            c1 = deep ? cur[1] : 0;
+        }
         const bool v0 = deep && r0 < vld, v1 = deep && r1 < vld, v2 = deep && r2 < vld, v3 = deep && r3 < vld;
         const u32 b0 = v0 ? (cur - r0)[1] : 0x100, b1 = v1 ? (cur - r1)[1] : 0x100;
         const u32 b2 = v2 ? (cur - r2)[1] : 0x100, b3 = v3 ? (cur - r3)[1] : 0x100;
         const u32 d2 = pos - e2, d3 = pos - e3;
         const bool q2 = deep && d2 < vld && x > d2, q3 = deep && d3 < vld && x >= d3;
-        const u32 t2 = q2 ? (cur - d2)[1] : 0x100, t3 = q3 ? (cur - d3)[1] : 0x100;
-        S.ht2[h2] = pos;
-        S.ht3[h3] = pos;
+        u32 t2 = 0x100, t3 = 0x100;
+        if (tmode) {
+            t2 = q2 ? (cur - d2)[1] : 0x100; t3 = q3 ? (cur - d3)[1] : 0x100;
+            S.ht2[h2] = pos;
+            S.ht3[h3] = pos;
+        }
         bool stop = false;
         // rep-distance probes (:266-299); rep0 also yields the 1-byte match when it matches >= 2
         if (v0 && b0 == c1) {
@@ -451,11 +503,17 @@ struct Encoder {
         // at window offset 0 is dropped but still poisons dist.
         if (d2 > dist) {
             dist = d2;
-            if (q2 && minlen < limit && probe(cur, d2, limit, t2, c1, 4 + d2, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+            if (q2 && minlen < limit) {
+                if (known2) { if (take(l2, d2, minlen, cnt)) dist = 0xFFFFFFFFu; }
+                else if (probe(cur, d2, limit, tmode ? t2 : (u32)(cur - d2)[1], c1, 4 + d2, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+            }
         }
         if (d3 > dist) {
             dist = d3;
-            if (q3 && minlen < limit && probe(cur, d3, limit, t3, c1, 4 + d3, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+            if (q3 && minlen < limit) {
+                if (known3) { if (take(l3, d3, minlen, cnt)) dist = 0xFFFFFFFFu; }
+                else if (probe(cur, d3, limit, tmode ? t3 : (u32)(cur - d3)[1], c1, 4 + d3, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+            }
         }
         // 6-byte table of width W (:453-485): the first W live entries of the chain
         if (W && dist != 0xFFFFFFFFu) {
@@ -570,13 +628,20 @@ struct Encoder {
         if (len <= 1) return;
         u32 i0 = 1;
         while (i0 + 128 < len) i0 += 4;
+        if (tmode) {
 #pragma unroll 1
-        for (u32 i = 1 + CSC_LANE; i < len; i += CSC_NLANES) {
-            if (i < i0 && ((i - 1) & 3)) continue;   // inside the skip zone only every 4th position (:140-145)
-            u32 q = s + i;
-            u32 w = word_at(q, sb_end);
-            g_max(&S.ht2[h2_of(w)], vld + q);
-            g_max(&S.ht3[h3_of(w)], vld + q);
+            for (u32 i = 1 + CSC_LANE; i < len; i += CSC_NLANES) {
+                if (i < i0 && ((i - 1) & 3)) continue;   // inside the skip zone only every 4th position (:140-145)
+                u32 q = s + i;
+                u32 w = word_at(q, sb_end);
+                g_max(&S.ht2[h2_of(w)], vld + q);
+                g_max(&S.ht3[h3_of(w)], vld + q);
+            }
+        } else if (i0 > 1) {
+            // chain mode: everything is "inserted" by default; only the 3 of 4 skipped zone positions are not
+#pragma unroll 1
+            for (u32 i = 1 + CSC_LANE; i < i0; i += CSC_NLANES)
+                if ((i - 1) & 3) g_or(&S.D23[(s + i) >> 5], 1u << ((s + i) & 31));
         }
         w_sync();
         if (W) {
@@ -889,6 +954,29 @@ struct Encoder {
     }
     CSC_HDN void skip_run(u32 a, u32 size) {   // mode 5: SlidePosFast (csc_mf.cpp:208-241)
         if (W) bits_or_not_range(S.D6, S.Z2, a, a + size);
+        bits_set_range(S.D23, a, a + size);   // never enters the 2-/3-byte tables
+    }
+    // A statically excluded block is LZ-parsed after all (duplicate-block flip): the chains do not know its
+    // positions, so rebuild the real 2-/3-byte tables from the history [0, upto) and use them from here on.
+    CSC_HDN void enter_table_mode(u32 upto) {
+        u32 a = 0;
+        for (u32 sg = 0; sg < S.nseg && a < upto; sg++) {
+            u32 sz = S.seg_size[sg];
+            for (u32 off = 0; off < sz && a + off < upto; off += kBlock) {
+                u32 sb_end = a + off + (sz - off < kBlock ? sz - off : kBlock);
+                u32 stop_at = sb_end < upto ? sb_end : upto;
+#pragma unroll 1
+                for (u32 y = a + off + CSC_LANE; y < stop_at; y += CSC_NLANES) {
+                    if (bit_get(S.D23, y)) continue;
+                    u32 w = word_at(y, sb_end);
+                    g_max(&S.ht2[h2_of(w)], vld + y);
+                    g_max(&S.ht3[h3_of(w)], vld + y);
+                }
+            }
+            a += sz;
+        }
+        w_sync();
+        tmode = true;
     }
     CSC_HDN void bad_run(u32 a, u32 size) {   // CompressBad, csc_model.cpp:463-469
         encode_int(size);
@@ -984,6 +1072,7 @@ struct Encoder {
 
     CSC_HDN void compress_run(u32 a, u32 size, u32 type, u32 first_blk) {   // compress_block, csc_encoder_main.cpp:35-83
         if (!size) return;
+        if (want_tables && !tmode && type < DT_NO_LZ) enter_table_mode(a);
         if (type == DT_NORMAL || type == DT_FAST) {
             emit(OP_INT, DT_NORMAL, 0, 0);
             lz_run(a, size);
@@ -1039,6 +1128,10 @@ struct Encoder {
             if (t >= DT_NO_LZ) {
                 if (dup_block(a + i, cur, a + last_begin)) t = DT_NORMAL;
             }
+            if (t < DT_NO_LZ && S.blk_nolz[blk] && !want_tables) {
+                // the pending run (if it continues into this block) must already be parsed with tables
+                want_tables = true;
+            }
             if (last_type != t) {   // (size limit of :128 cannot trigger inside one Read())
                 if (last_size) {
                     compress_run(a + last_begin, last_size, last_type, last_blk);
@@ -1063,6 +1156,7 @@ struct Encoder {
     CSC_HD void init_common() {
         vld = S.cfg.vld_rge; W = S.cfg.ht_width; K = S.K; good = S.cfg.good_len;
         err = 0; tr_n = 0;
+        tmode = false; want_tables = false;
         rc_n = bc_n = ev_n = 0;
         seg_rc0 = seg_bc0 = seg_ev0 = 0;
         head = tail = 0;

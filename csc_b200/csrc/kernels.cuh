@@ -158,12 +158,12 @@ k_analyze(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, u32 nblk
 
 // -------------------------------------------------------------- plan + filters
 __global__ void k_plan(const SegDesc *__restrict__ segs, u32 nseg, const u32 *__restrict__ binfo, FilterRun *scratch,
-                       GRun *runs, u32 *nruns) {
+                       GRun *runs, u32 *nruns, u8 *nolz) {
     u32 s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseg) return;
     const SegDesc sd = segs[s];
     FilterRun *mine = scratch + sd.blk0;
-    u32 nr = plan_segment(binfo, sd.blk0, 0, sd.size, sd.flt & 1, (sd.flt >> 1) & 1, (sd.flt >> 2) & 1, mine);
+    u32 nr = plan_segment(binfo, sd.blk0, 0, sd.size, sd.flt & 1, (sd.flt >> 1) & 1, (sd.flt >> 2) & 1, mine, nolz);
     if (!nr) return;
     u32 at = atomicAdd(nruns, nr);
     for (u32 i = 0; i < nr; i++) {
@@ -369,7 +369,7 @@ static const int kMfThreads = 256;
 __global__ void __launch_bounds__(kMfThreads)
 k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u32 *__restrict__ stream_bits,
           const u64 *__restrict__ stream_goff, u32 key_shift, u64 *__restrict__ keys, u32 *__restrict__ vals,
-          u32 *Z2, u32 *Z6) {
+          u32 *Z2, u32 *Z6, u32 which, const u8 *__restrict__ nolz) {
     __shared__ u8 s[kBlock + 16];
     const BlockDesc bd = blk[blockIdx.x];
     const u8 *src = lz + bd.goff;
@@ -383,8 +383,13 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
         u32 v2 = p[4] | (p[5] << 8);
         u32 h6 = bits ? ((v ^ (v2 << 13)) * 2654435761u) >> (32 - bits) : 0;
         u32 h2 = ((v & 0xFFFF) * 65521u) & 0x3FFF;
-        keys[bd.cpos + i] = ((u64)bd.stream << key_shift) | h6;
         vals[bd.cpos + i] = bd.x + i;
+        if (which != 6) {   // 3-byte / 2-byte chains (HASH3 csc_mf.cpp:30-33, HASH2 :23-28); excluded blocks sort apart
+            u32 h = which == 3 ? ((v & 0xFF) << 8) ^ (((v >> 8) & 0xFF) << 5) ^ ((v >> 16) & 0xFF) : h2;
+            keys[bd.cpos + i] = nolz[blockIdx.x] ? ~0ull : (((u64)bd.stream << key_shift) | h);
+            continue;
+        }
+        keys[bd.cpos + i] = ((u64)bd.stream << key_shift) | h6;
         u64 bit = bitbase + i;
         if ((h2 & 15) == 0) atomicOr(&Z2[bit >> 5], 1u << (bit & 31));
         if (bits && h6 == 0) atomicOr(&Z6[bit >> 5], 1u << (bit & 31));
@@ -392,12 +397,14 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
 }
 
 __global__ void k_mf_rows(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u32 n, u32 key_shift,
-                          const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_K, u32 *__restrict__ P6) {
+                          const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_K, u32 *__restrict__ P6,
+                          const u32 *__restrict__ pos_stream, u32 kforce) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 k = keys[i];
+    if (k == ~0ull) return;   // position of a block left out of this chain (array pre-filled with kNone)
     const u32 s = (u32)(k >> key_shift);
-    const u32 K = stream_K[s];
+    const u32 K = kforce ? kforce : stream_K[s];
     if (!K) return;
     u32 *row = P6 + (stream_goff[s] + vals[i]) * K;
     bool live = true;

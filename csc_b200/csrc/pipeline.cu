@@ -85,7 +85,7 @@ struct Ctx {
     u32 *d_p2bits = nullptr;
     DevBuf lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
-        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings;
+        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz;
     PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta;
     Timer tm;
     CSCB200_Stats stats;
@@ -212,7 +212,9 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     r |= C.vals0.ensure((size_t)npos * 4 + 16); r |= C.vals1.ensure((size_t)npos * 4 + 16);
     r |= C.P6.ensure(total * K * 4); r |= C.L6.ensure(total * K * 2);
     const size_t bmbytes = total / 8 + 64;
-    r |= C.Z2.ensure(bmbytes); r |= C.Z6.ensure(bmbytes); r |= C.D6.ensure(bmbytes);
+    r |= C.Z2.ensure(bmbytes); r |= C.Z6.ensure(bmbytes); r |= C.D6.ensure(bmbytes); r |= C.D23.ensure(bmbytes);
+    r |= C.P3.ensure(total * 4); r |= C.P2.ensure(total * 4); r |= C.L3.ensure(total * 2); r |= C.L2.ensure(total * 2);
+    r |= C.nolz.ensure(nblk + 16);
     r |= C.ht.ensure((size_t)ns * 81920 * 4);
     r |= C.plit.ensure((size_t)ns * 131072 * 2);
     r |= C.ap.ensure((size_t)ns * (kApLimit + 2) * sizeof(ApUnit));
@@ -247,6 +249,9 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         S.tail_dlt = C.taildlt.as<u32>() + (size_t)seg0[s] * 5; S.dict_ok = C.dictok.as<u8>();
         S.P6 = C.P6.as<u32>() + goff[s] * K; S.L6 = C.L6.as<u16>() + goff[s] * K; S.K = K;
         S.Z2 = C.Z2.as<u32>() + goff[s] / 32; S.Z6 = C.Z6.as<u32>() + goff[s] / 32; S.D6 = C.D6.as<u32>() + goff[s] / 32;
+        S.P3 = C.P3.as<u32>() + goff[s]; S.L3 = C.L3.as<u16>() + goff[s];
+        S.P2 = C.P2.as<u32>() + goff[s]; S.L2 = C.L2.as<u16>() + goff[s];
+        S.D23 = C.D23.as<u32>() + goff[s] / 32; S.blk_nolz = C.nolz.as<u8>();
         S.ht2 = C.ht.as<u32>() + (size_t)s * 81920; S.ht3 = S.ht2 + 16384;
         S.p_lit = C.plit.as<u16>() + (size_t)s * 131072; S.p_delta = S.p_lit + 65536;
         S.ap = C.ap.as<ApUnit>() + (size_t)s * (kApLimit + 2);
@@ -275,6 +280,9 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     CK(cudaMemsetAsync(C.Z2.p, 0, bmbytes, st));
     CK(cudaMemsetAsync(C.Z6.p, 0, bmbytes, st));
     CK(cudaMemsetAsync(C.D6.p, 0, bmbytes, st));
+    CK(cudaMemsetAsync(C.D23.p, 0, bmbytes, st));
+    CK(cudaMemsetAsync(C.P3.p, 0xFF, total * 4, st));
+    CK(cudaMemsetAsync(C.P2.p, 0xFF, total * 4, st));
     CK(cudaMemsetAsync(C.ht.p, 0, (size_t)ns * 81920 * 4, st));
     CK(cudaMemsetAsync(C.status.p, 0, (size_t)ns * 4, st));
     CK(cudaMemsetAsync(C.counters.p, 0, 64, st));
@@ -291,26 +299,39 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     u32 *d_nruns = C.counters.as<u32>();
     u32 *d_queue = C.counters.as<u32>() + 1;
     k_plan<<<(nseg + 127) / 128, 128, 0, st>>>(C.segdesc.as<SegDesc>(), nseg, C.binfo.as<u32>(), C.planscratch.as<FilterRun>(),
-                                               C.runs.as<GRun>(), d_nruns);
+                                               C.runs.as<GRun>(), d_nruns, C.nolz.as<u8>());
     k_filter_runs<<<std::min<u32>(nblk, 148 * 8), kFltThreads, 0, st>>>(C.lz.as<u8>(), C.tmp.as<u8>(), C.runs.as<GRun>(), d_nruns, C.d_DT, C.dictok.as<u8>());
     T.mark(st);                                                                   // 3
     launches += 3;
-    // ---- match finder precomputation
+    // ---- match finder precomputation: 6-byte rows, then the 3-byte and 2-byte chains
+    const u32 *pos_stream = nullptr;
     k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), key_shift,
-                                           C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>());
+                                           C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), 6, C.nolz.as<u8>());
     T.mark(st);                                                                   // 4
     cub::DeviceRadixSort::SortPairs(C.cubtmp.p, cub_bytes, C.keys0.as<u64>(), C.keys1.as<u64>(), C.vals0.as<u32>(), C.vals1.as<u32>(),
                                     (int)npos, 0, end_bit, st);
     T.mark(st);                                                                   // 5
     k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(C.keys1.as<u64>(), C.vals1.as<u32>(), npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(),
-                                                  C.P6.as<u32>());
+                                                  C.P6.as<u32>(), pos_stream, 0);
     T.mark(st);                                                                   // 6
     if (K == 1) k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else if (K == 2) k_mf_extend<2><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else if (K == 8) k_mf_extend<8><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else return kErrUnsupported;
+    for (u32 which = 3; which >= 2; which--) {
+        const u32 shift = which == 3 ? 16 : 14;
+        u32 *P = which == 3 ? C.P3.as<u32>() : C.P2.as<u32>();
+        u16 *L = which == 3 ? C.L3.as<u16>() : C.L2.as<u16>();
+        k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), shift,
+                                               C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which, C.nolz.as<u8>());
+        cub::DeviceRadixSort::SortPairs(C.cubtmp.p, cub_bytes, C.keys0.as<u64>(), C.keys1.as<u64>(), C.vals0.as<u32>(), C.vals1.as<u32>(),
+                                        (int)npos, 0, (int)(shift + stream_bits), st);
+        k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(C.keys1.as<u64>(), C.vals1.as<u32>(), npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P,
+                                                      pos_stream, 1);
+        k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
+    }
     T.mark(st);                                                                   // 7
-    launches += 3 + (u32)((end_bit + 7) / 8) * 2 + 1;
+    launches += 3 + (u32)((end_bit + 7) / 8) * 2 + 1 + 2 * (3 + 8);
     if (g_dump.on && ns == 1) {
         CK(cudaStreamSynchronize(st));
         u32 n1 = jobs[0]->n;
@@ -406,7 +427,7 @@ size_t framed_size(const EncJob &J, bool with_props) {
 }
 
 size_t per_stream_bytes() { return 81920 * 4 + 131072 * 2 + (kApLimit + 2) * sizeof(ApUnit) + 140000 * 2 + 4096; }
-size_t per_pos_bytes(u32 K) { return 2 + 24 + 6 * (size_t)K + 1 + 3; }
+size_t per_pos_bytes(u32 K) { return 2 + 24 + 6 * (size_t)K + 12 + 1 + 3; }
 
 // ----------------------------------------------------------------------------- decode
 struct DecJob {

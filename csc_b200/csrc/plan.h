@@ -14,15 +14,27 @@ struct FilterRun { u32 kind; u32 off; u32 size; u32 first_blk; };   // kind: DT_
 
 // Walks the blocks of one segment and appends its EXE / ENGTXT runs.
 // Returns the number of runs appended (runs must have room for nblk entries).
+// nolz[blk] = 1 for blocks the analyzer statically types as not LZ-parsed (BAD / ENTROPY / DLT that pass the
+// delta-bpb veto): they are left out of the 2-/3-byte chains.  A duplicate-block flip of such a block
+// (csc_encoder_main.cpp:123-126) makes the engine fall back to real tables for the rest of the stream.
 CSC_HD u32 plan_segment(const u32 *binfo, u32 blk0, u32 seg_off, u32 seg_size, u32 flt_dlt, u32 flt_txt, u32 flt_exe,
-                        FilterRun *runs) {
+                        FilterRun *runs, u8 *nolz) {
     u32 nruns = 0;
-    if (flt_dlt + flt_txt + flt_exe == 0) return 0;
+    if (flt_dlt + flt_txt + flt_exe == 0) {
+        u32 b = blk0;
+        for (u32 i = 0; i < seg_size; i += kBlock, b++) nolz[b] = 0;
+        return 0;
+    }
     u32 last = DT_NORMAL, run_begin = 0, run_size = 0, run_blk = blk0;
     u32 blk = blk0;
     for (u32 i = 0; i < seg_size; blk++) {
         u32 cur = seg_size - i < kBlock ? seg_size - i : kBlock;
         u32 t = binfo[blk] & 0xFF;
+        {
+            u32 st = t;
+            if (st >= DT_DLT && st != DT_SKIP && (!flt_dlt || ((binfo[blk] >> 8) & 1))) st = DT_NORMAL;
+            nolz[blk] = (st != DT_SKIP && st >= DT_NO_LZ) ? 1 : 0;
+        }
         if (t == DT_SKIP) t = last;
         if (t == DT_EXE && !flt_exe) t = DT_NORMAL;
         else if (t == DT_ENGTXT && !flt_txt) t = DT_NORMAL;
@@ -54,6 +66,10 @@ CSC_HD u32 hash6_padded(const u8 *p, u32 avail, u32 bits) {   // HASH6, csc_mf.c
     u32 v = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
     u32 v2 = b[4] | (b[5] << 8);
     return ((v ^ (v2 << 13)) * 2654435761u) >> (32 - bits);
+}
+CSC_HD u32 hash3_padded(const u8 *p, u32 avail) {   // HASH3, csc_mf.cpp:30-33
+    u32 b0 = p[0], b1 = avail > 1 ? p[1] : 0, b2 = avail > 2 ? p[2] : 0;
+    return (b0 << 8) ^ (b1 << 5) ^ b2;
 }
 CSC_HD u32 hash2_padded(const u8 *p, u32 avail) {   // HASH2, csc_mf.cpp:23-28
     u32 b0 = p[0], b1 = avail > 1 ? p[1] : 0;

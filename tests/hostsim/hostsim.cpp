@@ -63,6 +63,35 @@ void build_mf_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, u32 bits, u3
     }
 }
 
+// nearest earlier position with equal (padded) HASH3 / HASH2 among the blocks not statically excluded
+void build_chain23_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, const std::vector<u32> &seg_blk0,
+                       const std::vector<u8> &nolz, int which, std::vector<u32> &P, std::vector<u16> &L) {
+    P.assign(n + 1, kNone);
+    L.assign(n + 1, 0);
+    std::vector<u32> last(which == 3 ? 65536 : 16384, kNone);
+    u32 a = 0;
+    for (u32 s = 0; s < seg.size(); s++) {
+        u32 b = seg_blk0[s];
+        for (u32 off = 0; off < seg[s]; off += kBlock, b++) {
+            u32 sb = seg[s] - off < kBlock ? seg[s] - off : kBlock;
+            u32 sb_end = a + off + sb;
+            if (nolz[b]) continue;
+            for (u32 x = a + off; x < sb_end; x++) {
+                u32 avail = sb_end - x;
+                u32 h = which == 3 ? hash3_padded(lz + x, avail) : hash2_padded(lz + x, avail);
+                u32 e = last[h];
+                last[h] = x;
+                if (e == kNone) continue;
+                P[x] = e;
+                u32 l = 0;
+                while (l < avail && lz[x + l] == lz[e + l]) l++;
+                L[x] = (u16)l;
+            }
+        }
+        a += seg[s];
+    }
+}
+
 }  // namespace
 
 struct StageDump { u32 *binfo, *bbpb; u8 *lz; u32 *P6; u16 *L6; u32 *Z2, *Z6; u8 *dict_ok; u32 *tail_dlt; bool on; };
@@ -109,7 +138,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         DictTables DT;
         build_dict_tables(DT);
         std::vector<u32> binfo(nblk), bbpb(nblk), tail_dlt(seg.size() * 5, 0);
-        std::vector<u8> dict_ok(nblk, 0);
+        std::vector<u8> dict_ok(nblk, 0), nolz(nblk, 0);
         u32 a = 0;
         bool use_filters = (cfg.flt_dlt + cfg.flt_txt + cfg.flt_exe) != 0;
         for (u32 s = 0; s < seg.size(); s++) {
@@ -120,7 +149,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
                 else { binfo[b] = DT_NORMAL; bbpb[b] = 0; }
             }
             std::vector<FilterRun> runs((seg[s] + kBlock - 1) / kBlock + 1);
-            u32 nr = plan_segment(binfo.data(), seg_blk0[s], a, seg[s], cfg.flt_dlt, cfg.flt_txt, cfg.flt_exe, runs.data());
+            u32 nr = plan_segment(binfo.data(), seg_blk0[s], a, seg[s], cfg.flt_dlt, cfg.flt_txt, cfg.flt_exe, runs.data(), nolz.data());
             std::vector<u8> tmp;
             for (u32 r = 0; r < nr; r++) {
                 if (runs[r].kind == DT_EXE) e8e9_run(lz.data() + runs[r].off, runs[r].size, false);
@@ -135,6 +164,11 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         std::vector<u16> L6;
         u32 K = cfg.ht_width;
         build_mf_cpu(lz.data(), n, seg, cfg.ht_bits, K, P6, L6, Z2, Z6);
+        std::vector<u32> P3, P2;
+        std::vector<u16> L3, L2;
+        build_chain23_cpu(lz.data(), n, seg, seg_blk0, nolz, 3, P3, L3);
+        build_chain23_cpu(lz.data(), n, seg, seg_blk0, nolz, 2, P2, L2);
+        std::vector<u32> D23((n + 31) / 32 + 1, 0);
         if (g_dump.on) {
             memcpy(g_dump.binfo, binfo.data(), nblk * 4); memcpy(g_dump.bbpb, bbpb.data(), nblk * 4);
             memcpy(g_dump.lz, lz.data(), n); memcpy(g_dump.P6, P6.data(), (size_t)n * K * 4);
@@ -156,6 +190,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         S.seg_size = seg.data(); S.seg_blk0 = seg_blk0.data(); S.binfo = binfo.data(); S.bbpb = bbpb.data();
         S.tail_dlt = tail_dlt.data(); S.dict_ok = dict_ok.data();
         S.P6 = P6.data(); S.L6 = L6.data(); S.K = K ? K : 1; S.Z2 = Z2.data(); S.Z6 = Z6.data(); S.D6 = D6.data();
+        S.P3 = P3.data(); S.L3 = L3.data(); S.P2 = P2.data(); S.L2 = L2.data(); S.D23 = D23.data(); S.blk_nolz = nolz.data();
         S.ht2 = ht2.data(); S.ht3 = ht3.data(); S.p_lit = p_lit.data(); S.p_delta = p_lit.data() + 65536; S.ap = ap.data();
         S.rc_out = rc.data(); S.rc_cap = rc_cap; S.bc_out = bc.data(); S.bc_cap = bc_cap;
         S.events = ev.data(); S.ev_cap = (u32)ev.size(); S.segout = so.data(); S.status = &status;
