@@ -38,6 +38,16 @@ CSC_HD u32 dist_slot(u32 d) { return d < 3 ? d : 2u + ilog2(d - 1); }
 
 CSC_HD u32 rev4(u32 v) { return ((v & 1) << 3) | ((v & 2) << 1) | ((v & 4) >> 1) | ((v & 8) >> 3); }
 
+// read-mostly context of the match-finder hot loop; a local copy lives in registers inside the parser
+struct MfCtx {
+    const u8 *lz;
+    const u32 *P6; const u16 *L6; const u32 *P3; const u16 *L3; const u32 *P2; const u16 *L2;
+    const u32 *Z6;
+    u32 *D6, *D23, *ht2, *ht3, *cl, *cd;
+    u32 vld, W, K, good;
+    bool tmode;
+};
+
 struct Encoder {
     const EncStream &S;
     ModelSmall &M;
@@ -62,6 +72,13 @@ struct Encoder {
     u32 seg_rc0, seg_bc0, seg_ev0;
 
     CSC_HD Encoder(const EncStream &s, ModelSmall &m) : S(s), M(m) {}
+    CSC_HDF MfCtx mfctx() const {
+        MfCtx h;
+        h.lz = S.lz; h.P6 = S.P6; h.L6 = S.L6; h.P3 = S.P3; h.L3 = S.L3; h.P2 = S.P2; h.L2 = S.L2; h.Z6 = S.Z6;
+        h.D6 = S.D6; h.D23 = S.D23; h.ht2 = S.ht2; h.ht3 = S.ht3; h.cl = M.cl; h.cd = M.cd;
+        h.vld = vld; h.W = W; h.K = K; h.good = good; h.tmode = tmode;
+        return h;
+    }
 
     // ------------------------------------------------------------------ output
     CSC_HD void event(u32 kind) {
@@ -353,77 +370,80 @@ struct Encoder {
     // ----------------------------------------------------- match finder (state)
     // HASH2 / HASH3 (csc_mf.cpp:23-33) of position x from one unaligned word; window bytes at or
     // beyond the sub-block end have not been written yet and read as 0
-    CSC_HDF u32 word_at(u32 x, u32 sb_end) const {
-        u32 w = ld32u(S.lz + x);
+    CSC_HDF static u32 word_at(const MfCtx &h, u32 x, u32 sb_end) {
+        u32 w = ld32u(h.lz + x);
         u32 avail = sb_end - x;
         if (avail < 4) w &= 0xFFFFFFFFu >> ((4 - avail) * 8);
         return w;
     }
     CSC_HDF static u32 h2_of(u32 w) { return ((w & 0xFFFF) * 65521u) & 0x3FFF; }
     CSC_HDF static u32 h3_of(u32 w) { return ((w & 0xFF) << 8) ^ (((w >> 8) & 0xFF) << 5) ^ ((w >> 16) & 0xFF); }
-    CSC_HD u32 hash2_at(u32 x, u32 sb_end) const { return h2_of(word_at(x, sb_end)); }
-    CSC_HD u32 hash3_at(u32 x, u32 sb_end) const { return h3_of(word_at(x, sb_end)); }
-    CSC_HDF bool dead6(u32 e) const { return bit_get(S.D6, e); }
-    CSC_HDF void kill6(u32 e) { g_or(&S.D6[e >> 5], 1u << (e & 31)); }
+    CSC_HDF static bool dead6(const MfCtx &h, u32 e) { return bit_get(h.D6, e); }
+    CSC_HDF static void kill6(const MfCtx &h, u32 e) { g_or(&h.D6[e >> 5], 1u << (e & 31)); }
 
     // newest position < bound on the 6-byte chain of x that is still in the table
     // (= slot 0 of the reference bucket at the time the window ended at `bound`)
-    CSC_HDN u32 newest_alive6(u32 x, u32 bound) const {
+    CSC_HDN static u32 newest_alive6(const MfCtx &h, u32 x, u32 bound) {
         u32 src = x, k = 0;
         for (;;) {
-            u32 e = S.P6[(size_t)src * K + k];
+            u32 e = h.P6[(size_t)src * h.K + k];
             if (e == kNone) return kNone;
-            if (++k == K) { src = e; k = 0; }
+            if (++k == h.K) { src = e; k = 0; }
             if (e >= bound) continue;
-            if (!dead6(e)) return e;
+            if (!dead6(h, e)) return e;
         }
     }
 
     // warm the lines the next find_match(y) will need while the coder is busy with a packet
-    CSC_HDN void prefetch_fm(u32 y, u32 sb_end) {
+    CSC_HDF static void prefetch_core(const MfCtx &h, u32 y, u32 sb_end) {
         if (y >= sb_end) return;
-        if (W) { pf_l2(S.P6 + (size_t)y * K); pf_l2(S.L6 + (size_t)y * K); }
-        u32 w = word_at(y, sb_end);
-        pf_l2(S.ht2 + h2_of(w));
-        pf_l2(S.ht3 + h3_of(w));
+        if (h.W) { pf_l2(h.P6 + (size_t)y * h.K); pf_l2(h.L6 + (size_t)y * h.K); }
+        if (h.tmode) {
+            u32 w = word_at(h, y, sb_end);
+            pf_l2(h.ht2 + h2_of(w));
+            pf_l2(h.ht3 + h3_of(w));
+        } else {
+            pf_l2(h.P3 + y); pf_l2(h.P2 + y);
+        }
     }
+    CSC_HDN void prefetch_fm(u32 y, u32 sb_end) { const MfCtx h = mfctx(); prefetch_core(h, y, sb_end); }
 
     CSC_HDF static u32 mf_bound(u32 len) { return len < 2 ? 0u : 1u << (4 * len - 2); }   // bound[] csc_mf.cpp:245
 
-    CSC_HDF void push_cand(u32 &cnt, u32 len, u32 dist) { M.cl[cnt] = len; M.cd[cnt] = dist; cnt++; }
+    CSC_HDF static void push_cand(const MfCtx &h, u32 &cnt, u32 len, u32 dist) { h.cl[cnt] = len; h.cd[cnt] = dist; cnt++; }
 
-    // a table candidate whose full match length ml is already known: same bookkeeping as probe()
-    CSC_HDF bool take(u32 ml, u32 d, u32 &minlen, u32 &cnt) {
+    // a table candidate whose full match length ml is already known: same bookkeeping as probe(h, )
+    CSC_HDF static bool take(const MfCtx &h, u32 ml, u32 d, u32 &minlen, u32 &cnt) {
         if (ml <= minlen) return false;
         minlen = ml;
         if (ml <= 6 && d >= mf_bound(ml)) return false;
-        push_cand(cnt, ml, 4 + d);
-        return ml >= good;
+        push_cand(h, cnt, ml, 4 + d);
+        return ml >= h.good;
     }
     // first entry at or behind e on a 2-/3-byte chain that the reference really inserted
-    CSC_HDN u32 alive23(const u32 *chain, u32 e) const {
-        while (e != kNone && bit_get(S.D23, e)) e = chain[e];
+    CSC_HDN static u32 alive23(const MfCtx &h, const u32 *chain, u32 e) {
+        while (e != kNone && bit_get(h.D23, e)) e = chain[e];
         return e;
     }
 
     // one table / rep probe once the candidate is known to be in range: reference semantics of
     // "pre-check byte at minlen, full compare, update minlen, bound filter, record, good_len stop"
     // returns true when every further probe is disabled (dist poisoned)
-    CSC_HDF bool probe(const u8 *cur, u32 d, u32 limit, u32 pre, u32 c1, u32 code, bool bounded, u32 &minlen, u32 &cnt) {
+    CSC_HDF static bool probe(const MfCtx &h, const u8 *cur, u32 d, u32 limit, u32 pre, u32 c1, u32 code, bool bounded, u32 &minlen, u32 &cnt) {
         const u8 *m = cur - d;
         if (minlen == 1 ? (pre != c1) : (m[minlen] != cur[minlen])) return false;
         u32 ml = lcp_bytes(cur, m, limit);
         if (ml <= minlen) return false;
         minlen = ml;
         if (bounded && ml <= 6 && d >= mf_bound(ml)) return false;
-        push_cand(cnt, ml, code);
-        return ml >= good;
+        push_cand(h, cnt, ml, code);
+        return ml >= h.good;
     }
 
     // find_match (csc_mf.cpp:243-495): candidate list (M.cl / M.cd) in reference probe order.
-    CSC_HDN u32 find_match(u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
-        const u8 *cur = S.lz + x;
-        const u32 pos = vld + x;
+    CSC_HDF static u32 fm_core(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
+        const u8 *cur = h.lz + x;
+        const u32 pos = h.vld + x;
         const u32 sb_end = x + limit;
         u32 cnt = 0, minlen = 1, dist = 0;
         // ---- issue every independent load first: candidate row, 2-/3-byte candidates, first probe bytes
@@ -434,89 +454,89 @@ struct Encoder {
         u32 e2 = 0, e3 = 0, l2 = 0, l3 = 0, h2 = 0, h3 = 0;   // table entries as reference pos_ values (0 = empty)
         bool known2 = false, known3 = false;                    // match length already known (chain mode)
 #if defined(__CUDA_ARCH__)
-        if (CSC_LANE < K) {
-            const size_t at = (size_t)x * K + CSC_LANE;
-            re = S.P6[at];
-            rl = S.L6[at];
-            if (re != kNone) rdead = dead6(re);
+        if (CSC_LANE < h.K) {
+            const size_t at = (size_t)x * h.K + CSC_LANE;
+            re = h.P6[at];
+            rl = h.L6[at];
+            if (re != kNone) rdead = dead6(h, re);
         }
-        if (!tmode) {
+        if (!h.tmode) {
             u32 ce = kNone, cl = 0;
             bool cdead = false;
-            if (CSC_LANE == 8) { ce = S.P3[x]; cl = S.L3[x]; }
-            if (CSC_LANE == 9) { ce = S.P2[x]; cl = S.L2[x]; }
-            if (ce != kNone) cdead = bit_get(S.D23, ce);
+            if (CSC_LANE == 8) { ce = h.P3[x]; cl = h.L3[x]; }
+            if (CSC_LANE == 9) { ce = h.P2[x]; cl = h.L2[x]; }
+            if (ce != kNone) cdead = bit_get(h.D23, ce);
             const u32 x3 = __shfl_sync(0xFFFFFFFFu, ce, 8), x2 = __shfl_sync(0xFFFFFFFFu, ce, 9);
             l3 = __shfl_sync(0xFFFFFFFFu, cl, 8); l2 = __shfl_sync(0xFFFFFFFFu, cl, 9);
             const u32 deadm = __ballot_sync(0xFFFFFFFFu, cdead);
             known3 = known2 = true;
             e3 = x3; e2 = x2;
-            if (deadm & 0x100) { e3 = alive23(S.P3, x3); known3 = false; }
-            if (deadm & 0x200) { e2 = alive23(S.P2, x2); known2 = false; }
-            e3 = (e3 == kNone) ? 0 : vld + e3;
-            e2 = (e2 == kNone) ? 0 : vld + e2;
+            if (deadm & 0x100) { e3 = alive23(h, h.P3, x3); known3 = false; }
+            if (deadm & 0x200) { e2 = alive23(h, h.P2, x2); known2 = false; }
+            e3 = (e3 == kNone) ? 0 : h.vld + e3;
+            e2 = (e2 == kNone) ? 0 : h.vld + e2;
         }
 #else
-        if (!tmode) {
-            u32 x3 = S.P3[x], x2 = S.P2[x];
-            l3 = S.L3[x]; l2 = S.L2[x];
+        if (!h.tmode) {
+            u32 x3 = h.P3[x], x2 = h.P2[x];
+            l3 = h.L3[x]; l2 = h.L2[x];
             known3 = known2 = true;
-            if (x3 != kNone && bit_get(S.D23, x3)) { x3 = alive23(S.P3, x3); known3 = false; }
-            if (x2 != kNone && bit_get(S.D23, x2)) { x2 = alive23(S.P2, x2); known2 = false; }
-            e3 = (x3 == kNone) ? 0 : vld + x3;
-            e2 = (x2 == kNone) ? 0 : vld + x2;
+            if (x3 != kNone && bit_get(h.D23, x3)) { x3 = alive23(h, h.P3, x3); known3 = false; }
+            if (x2 != kNone && bit_get(h.D23, x2)) { x2 = alive23(h, h.P2, x2); known2 = false; }
+            e3 = (x3 == kNone) ? 0 : h.vld + x3;
+            e2 = (x2 == kNone) ? 0 : h.vld + x2;
         }
 #endif
         const bool deep = limit > 1;
         u32 c1;
-        if (tmode) {
-            const u32 w0 = word_at(x, sb_end);
+        if (h.tmode) {
+            const u32 w0 = word_at(h, x, sb_end);
             h2 = h2_of(w0); h3 = h3_of(w0);
-            e2 = g_ld(&S.ht2[h2]); e3 = g_ld(&S.ht3[h3]);
+            e2 = g_ld(&h.ht2[h2]); e3 = g_ld(&h.ht3[h3]);
             c1 = (w0 >> 8) & 0xFF;
         } else {
             c1 = deep ? cur[1] : 0;
         }
-        const bool v0 = deep && r0 < vld, v1 = deep && r1 < vld, v2 = deep && r2 < vld, v3 = deep && r3 < vld;
+        const bool v0 = deep && r0 < h.vld, v1 = deep && r1 < h.vld, v2 = deep && r2 < h.vld, v3 = deep && r3 < h.vld;
         const u32 b0 = v0 ? (cur - r0)[1] : 0x100, b1 = v1 ? (cur - r1)[1] : 0x100;
         const u32 b2 = v2 ? (cur - r2)[1] : 0x100, b3 = v3 ? (cur - r3)[1] : 0x100;
         const u32 d2 = pos - e2, d3 = pos - e3;
-        const bool q2 = deep && d2 < vld && x > d2, q3 = deep && d3 < vld && x >= d3;
+        const bool q2 = deep && d2 < h.vld && x > d2, q3 = deep && d3 < h.vld && x >= d3;
         u32 t2 = 0x100, t3 = 0x100;
-        if (tmode) {
+        if (h.tmode) {
             t2 = q2 ? (cur - d2)[1] : 0x100; t3 = q3 ? (cur - d3)[1] : 0x100;
-            S.ht2[h2] = pos;
-            S.ht3[h3] = pos;
+            h.ht2[h2] = pos;
+            h.ht3[h3] = pos;
         }
         bool stop = false;
         // rep-distance probes (:266-299); rep0 also yields the 1-byte match when it matches >= 2
         if (v0 && b0 == c1) {
             u32 ml = lcp_bytes(cur, cur - r0, limit);
-            if (ml) push_cand(cnt, 1, 1);
-            if (ml > minlen) { minlen = ml; push_cand(cnt, ml, 1); stop = ml >= good; }
+            if (ml) push_cand(h, cnt, 1, 1);
+            if (ml > minlen) { minlen = ml; push_cand(h, cnt, ml, 1); stop = ml >= h.good; }
         }
-        if (!stop && v1 && minlen < limit) stop = probe(cur, r1, limit, b1, c1, 2, false, minlen, cnt);
-        if (!stop && v2 && minlen < limit) stop = probe(cur, r2, limit, b2, c1, 3, false, minlen, cnt);
-        if (!stop && v3 && minlen < limit) stop = probe(cur, r3, limit, b3, c1, 4, false, minlen, cnt);
+        if (!stop && v1 && minlen < limit) stop = probe(h, cur, r1, limit, b1, c1, 2, false, minlen, cnt);
+        if (!stop && v2 && minlen < limit) stop = probe(h, cur, r2, limit, b2, c1, 3, false, minlen, cnt);
+        if (!stop && v3 && minlen < limit) stop = probe(h, cur, r3, limit, b3, c1, 4, false, minlen, cnt);
         if (stop) dist = 0xFFFFFFFFu;
         // 2-byte and 3-byte single-slot tables (:303-366).  `wpos > dist` (:306): a 2-byte candidate
         // at window offset 0 is dropped but still poisons dist.
         if (d2 > dist) {
             dist = d2;
             if (q2 && minlen < limit) {
-                if (known2) { if (take(l2, d2, minlen, cnt)) dist = 0xFFFFFFFFu; }
-                else if (probe(cur, d2, limit, tmode ? t2 : (u32)(cur - d2)[1], c1, 4 + d2, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+                if (known2) { if (take(h, l2, d2, minlen, cnt)) dist = 0xFFFFFFFFu; }
+                else if (probe(h, cur, d2, limit, h.tmode ? t2 : (u32)(cur - d2)[1], c1, 4 + d2, true, minlen, cnt)) dist = 0xFFFFFFFFu;
             }
         }
         if (d3 > dist) {
             dist = d3;
             if (q3 && minlen < limit) {
-                if (known3) { if (take(l3, d3, minlen, cnt)) dist = 0xFFFFFFFFu; }
-                else if (probe(cur, d3, limit, tmode ? t3 : (u32)(cur - d3)[1], c1, 4 + d3, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+                if (known3) { if (take(h, l3, d3, minlen, cnt)) dist = 0xFFFFFFFFu; }
+                else if (probe(h, cur, d3, limit, h.tmode ? t3 : (u32)(cur - d3)[1], c1, 4 + d3, true, minlen, cnt)) dist = 0xFFFFFFFFu;
             }
         }
-        // 6-byte table of width W (:453-485): the first W live entries of the chain
-        if (W && dist != 0xFFFFFFFFu) {
+        // 6-byte table of width h.W (:453-485): the first h.W live entries of the chain
+        if (h.W && dist != 0xFFFFFFFFu) {
 #if defined(__CUDA_ARCH__)
             // lanes 0..K-1 evaluate their entry; the running minlen is a prefix maximum and the
             // strictly increasing distances make the `<= dist` filter a compare with the entry value
@@ -524,8 +544,8 @@ struct Encoder {
             const u32 alivem = __ballot_sync(0xFFFFFFFFu, re != kNone && !rdead);
             const u32 lt = (1u << CSC_LANE) - 1;
             const u32 d = x - re;
-            const bool cons = ((alivem >> CSC_LANE) & 1) && (u32)__popc(alivem & lt) < W;
-            const bool passd = cons && d > dist && d < vld && minlen < limit;
+            const bool cons = ((alivem >> CSC_LANE) & 1) && (u32)__popc(alivem & lt) < h.W;
+            const bool passd = cons && d > dist && d < h.vld && minlen < limit;
             u32 pm = passd ? rl : 0;
 #pragma unroll
             for (int sft = 1; sft < 8; sft <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, pm, sft); if (CSC_LANE >= (u32)sft) pm = max(pm, t); }
@@ -533,15 +553,15 @@ struct Encoder {
             if (CSC_LANE == 0) excl = 0;
             const u32 run = max(minlen, excl);
             bool acc = passd && rl > run && !(rl <= 6 && d >= mf_bound(rl));
-            const u32 stopm = __ballot_sync(0xFFFFFFFFu, acc && rl >= good);
+            const u32 stopm = __ballot_sync(0xFFFFFFFFu, acc && rl >= h.good);
             if (stopm && CSC_LANE > (u32)__ffs((int)stopm) - 1) acc = false;
             const u32 accm = __ballot_sync(0xFFFFFFFFu, acc);
-            if (acc) { u32 idx = cnt + (u32)__popc(accm & lt); M.cl[idx] = rl; M.cd[idx] = 4 + d; }
+            if (acc) { u32 idx = cnt + (u32)__popc(accm & lt); h.cl[idx] = rl; h.cd[idx] = 4 + d; }
             cnt += (u32)__popc(accm);
             __syncwarp();
             // a dead entry inside a full row leaves the bucket short: keep walking behind the row (rare)
-            const u32 full = (K >= 32) ? 0xFFFFFFFFu : ((1u << K) - 1);
-            if (!stopm && validm == full && (u32)__popc(alivem) < W) {
+            const u32 full = (h.K >= 32) ? 0xFFFFFFFFu : ((1u << h.K) - 1);
+            if (!stopm && validm == full && (u32)__popc(alivem) < h.W) {
                 u32 found = (u32)__popc(alivem);
                 u32 last_d = 0, last_l = 0;   // state after the row: dist / minlen
                 {
@@ -554,38 +574,38 @@ struct Encoder {
                 }
                 if (last_d > dist) dist = last_d;
                 if (last_l > minlen) minlen = last_l;
-                u32 src = __shfl_sync(0xFFFFFFFFu, re, K - 1), kk = 0;
-                while (found < W) {
-                    u32 e = S.P6[(size_t)src * K + kk];
+                u32 src = __shfl_sync(0xFFFFFFFFu, re, h.K - 1), kk = 0;
+                while (found < h.W) {
+                    u32 e = h.P6[(size_t)src * h.K + kk];
                     if (e == kNone) break;
-                    if (++kk == K) { src = e; kk = 0; }
-                    if (dead6(e)) continue;
+                    if (++kk == h.K) { src = e; kk = 0; }
+                    if (dead6(h, e)) continue;
                     found++;
                     u32 dd = x - e;
                     if (dd <= dist) continue;
                     dist = dd;
-                    if (dist >= vld || minlen >= limit) continue;
-                    if (probe(cur, dd, limit, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
+                    if (dist >= h.vld || minlen >= limit) continue;
+                    if (probe(h, cur, dd, limit, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
                 }
             }
 #else
             u32 found = 0, src = x, k = 0;
-            while (found < W) {
-                size_t at = (size_t)src * K + k;
-                u32 e = S.P6[at];
+            while (found < h.W) {
+                size_t at = (size_t)src * h.K + k;
+                u32 e = h.P6[at];
                 if (e == kNone) break;
                 bool inrow = (src == x);
-                if (++k == K) { src = e; k = 0; }
-                if (dead6(e)) continue;
+                if (++k == h.K) { src = e; k = 0; }
+                if (dead6(h, e)) continue;
                 found++;
                 u32 d = x - e;
                 if (d <= dist) continue;
                 dist = d;
-                if (dist >= vld) continue;
+                if (dist >= h.vld) continue;
                 if (minlen >= limit) continue;
                 u32 ml;
                 if (inrow) {
-                    ml = S.L6[at];
+                    ml = h.L6[at];
                 } else {
                     const u8 *m = cur - dist;
                     if (m[minlen] != cur[minlen]) continue;
@@ -594,8 +614,8 @@ struct Encoder {
                 if (ml > minlen) {
                     minlen = ml;
                     if (ml <= 6 && dist >= mf_bound(ml)) continue;
-                    push_cand(cnt, ml, 4 + dist);
-                    if (ml >= good) break;
+                    push_cand(h, cnt, ml, 4 + dist);
+                    if (ml >= h.good) break;
                 }
             }
 #endif
@@ -613,48 +633,51 @@ struct Encoder {
         if (u2.len < u1.len && u2.len + 2 >= u1.len && u1.dist > 4 && (u1.dist >> (4 * (u1.len - u2.len))) > u2.dist) return true;
         return false;
     }
-    CSC_HDN Cand find_best(u32 x, u32 limit) {   // FindMatch, csc_mf.cpp:497-524
-        u32 n = find_match(x, limit, rep[0], rep[1], rep[2], rep[3]);
+    CSC_HDF static Cand best_of(const MfCtx &h, u32 n) {   // fold of FindMatch, csc_mf.cpp:497-524
         Cand best; best.len = 1; best.dist = 0;
         for (u32 i = 0; i < n; i++) {
-            Cand c; c.len = M.cl[i]; c.dist = M.cd[i];
+            Cand c; c.len = h.cl[i]; c.dist = h.cd[i];
             if (i == 0 || second_better(best, c)) best = c;
         }
         return best;
     }
+    // out-of-line entry points for the cold callers (optimal parser, typing)
+    CSC_HDN u32 find_match(u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) { const MfCtx h = mfctx(); return fm_core(h, x, limit, r0, r1, r2, r3); }
+    CSC_HDN void slide(u32 s, u32 len, u32 sb_end) { const MfCtx h = mfctx(); slide_core(h, s, len, sb_end); }
+    CSC_HDN u32 newest_alive6(u32 x, u32 bound) const { const MfCtx h = mfctx(); return newest_alive6(h, x, bound); }
 
     // SlidePos (csc_mf.cpp:134-206): positions s+1 .. s+len-1 are passed over by a match.
-    CSC_HDN void slide(u32 s, u32 len, u32 sb_end) {
+    CSC_HDF static void slide_core(const MfCtx &h, u32 s, u32 len, u32 sb_end) {
         if (len <= 1) return;
         u32 i0 = 1;
         while (i0 + 128 < len) i0 += 4;
-        if (tmode) {
+        if (h.tmode) {
 #pragma unroll 1
             for (u32 i = 1 + CSC_LANE; i < len; i += CSC_NLANES) {
                 if (i < i0 && ((i - 1) & 3)) continue;   // inside the skip zone only every 4th position (:140-145)
                 u32 q = s + i;
-                u32 w = word_at(q, sb_end);
-                g_max(&S.ht2[h2_of(w)], vld + q);
-                g_max(&S.ht3[h3_of(w)], vld + q);
+                u32 w = word_at(h, q, sb_end);
+                g_max(&h.ht2[h2_of(w)], h.vld + q);
+                g_max(&h.ht3[h3_of(w)], h.vld + q);
             }
         } else if (i0 > 1) {
             // chain mode: everything is "inserted" by default; only the 3 of 4 skipped zone positions are not
 #pragma unroll 1
             for (u32 i = 1 + CSC_LANE; i < i0; i += CSC_NLANES)
-                if ((i - 1) & 3) g_or(&S.D23[(s + i) >> 5], 1u << ((s + i) & 31));
+                if ((i - 1) & 3) g_or(&h.D23[(s + i) >> 5], 1u << ((s + i) & 31));
         }
         w_sync();
-        if (W) {
-            bits_set_range(S.D6, s + 1, s + i0);          // never inserted (:145)
+        if (h.W) {
+            bits_set_range(h.D6, s + 1, s + i0);          // never inserted (:145)
             u32 first = s + i0;
-            if (i0 < len && bit_get_ro(S.Z6, first)) {    // h6 == lasth6 (== 0): slot 0 overwritten (:147-156)
-                u32 e = newest_alive6(first, first);
-                if (e != kNone) kill6(e);
+            if (i0 < len && bit_get_ro(h.Z6, first)) {    // h6 == lasth6 (== 0): slot 0 overwritten (:147-156)
+                u32 e = newest_alive6(h, first, first);
+                if (e != kNone) kill6(h, e);
             }
 #pragma unroll 1
             for (u32 i = i0 + 1 + CSC_LANE; i < len; i += CSC_NLANES) {
                 u32 q = s + i;
-                if (S.P6[(size_t)q * K] == q - 1) kill6(q - 1);   // same hash as the previous slid position
+                if (h.P6[(size_t)q * h.K] == q - 1) kill6(h, q - 1);   // same hash as the previous slid position
             }
             w_sync();
         }
@@ -745,34 +768,34 @@ struct Encoder {
         }
     }
     CSC_HDN void parse_lazy(u32 x0, u32 size) {   // compress_normal(size, true), csc_lz.cpp:156-199
+        const MfCtx h = mfctx();   // pointers and constants of the hot loop stay in registers
         const u32 end = x0 + size;
         u32 x = x0;
         Cand u1;
         u1.len = 1; u1.dist = 0;
         bool have = false;
         while (x < end) {
-            if (!have || !(u1.len == 1 || u1.len >= good)) {
+            if (!have || !(u1.len == 1 || u1.len >= h.good)) {
                 // the one probe site: u1 at x, or the lazy look-ahead u2 at x + 1
                 const u32 px = have ? x + 1 : x;
-                prefetch_fm(px + 1, end);
-                Cand c = find_best(px, end - px);
+                Cand c = best_of(h, fm_core(h, px, end - px, rep[0], rep[1], rep[2], rep[3]));
                 if (!have) { u1 = c; have = true; continue; }
                 if (second_better(u1, c)) {
-                    emit(OP_LIT, S.lz[x], 0, 0);
+                    emit(OP_LIT, h.lz[x], 0, 0);
                     x++;
                     u1 = c;
                 } else {
-                    prefetch_fm(x + u1.len, end);
-                    encode_nonlit(u1, S.lz[x + u1.len - 1]);
-                    slide(x + 1, u1.len - 1, end);
+                    prefetch_core(h, x + u1.len, end);
+                    encode_nonlit(u1, h.lz[x + u1.len - 1]);
+                    slide_core(h, x + 1, u1.len - 1, end);
                     x += u1.len;
                     have = false;
                 }
                 continue;
             }
-            if (u1.dist == 0) emit(OP_LIT, S.lz[x], 0, 0);
-            else { prefetch_fm(x + u1.len, end); encode_nonlit(u1, S.lz[x + u1.len - 1]); }
-            slide(x, u1.len, end);
+            if (u1.dist == 0) emit(OP_LIT, h.lz[x], 0, 0);
+            else { prefetch_core(h, x + u1.len, end); encode_nonlit(u1, h.lz[x + u1.len - 1]); }
+            slide_core(h, x, u1.len, end);
             x += u1.len;
             have = false;
         }
@@ -968,7 +991,7 @@ struct Encoder {
 #pragma unroll 1
                 for (u32 y = a + off + CSC_LANE; y < stop_at; y += CSC_NLANES) {
                     if (bit_get(S.D23, y)) continue;
-                    u32 w = word_at(y, sb_end);
+                    u32 w = word_at(mfctx(), y, sb_end);
                     g_max(&S.ht2[h2_of(w)], vld + y);
                     g_max(&S.ht3[h3_of(w)], vld + y);
                 }
