@@ -428,16 +428,42 @@ __device__ __forceinline__ u32 ld_u32_unaligned(const u8 *p) {
 // L >= 1 then LCP(p, e) = L - 1 exactly (same cap), which is the common case in repetitive
 // data where whole phrases repeat.  Only strip heads and fresh chain entries touch the window,
 // 4 bytes per step through aligned loads + funnel shift.
+__device__ __forceinline__ u64 ld_u64_unaligned(const u8 *p) {
+    const u64 *a = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    u32 sh = (u32)(reinterpret_cast<uintptr_t>(p) & 7) * 8;
+    u64 lo = a[0];
+    if (!sh) return lo;
+    return (lo >> sh) | (a[1] << (64 - sh));
+}
 __device__ __forceinline__ u32 lcp_words(const u8 *a, const u8 *m, u32 limit) {
     u32 l = 0;
-    while (l + 4 <= limit) {
-        u32 d = ld_u32_unaligned(a + l) ^ ld_u32_unaligned(m + l);
-        if (d) return l + ((__ffs((int)d) - 1) >> 3);
-        l += 4;
+    while (l + 8 <= limit) {
+        u64 d = ld_u64_unaligned(a + l) ^ ld_u64_unaligned(m + l);
+        if (d) return l + ((__ffsll((long long)d) - 1) >> 3);
+        l += 8;
     }
     while (l < limit && a[l] == m[l]) l++;
     return l;
 }
+
+template <int K> struct RowIO;
+template <> struct RowIO<1> {
+    static __device__ __forceinline__ void load(const u32 *p, u32 *e) { e[0] = p[0]; }
+    static __device__ __forceinline__ void store(u16 *p, const u32 *l, const u32 *) { p[0] = (u16)l[0]; }
+};
+template <> struct RowIO<2> {
+    static __device__ __forceinline__ void load(const u32 *p, u32 *e) { uint2 v = *reinterpret_cast<const uint2 *>(p); e[0] = v.x; e[1] = v.y; }
+    static __device__ __forceinline__ void store(u16 *p, const u32 *l, const u32 *) { *reinterpret_cast<u32 *>(p) = l[0] | (l[1] << 16); }
+};
+template <> struct RowIO<8> {
+    static __device__ __forceinline__ void load(const u32 *p, u32 *e) {
+        uint4 a = reinterpret_cast<const uint4 *>(p)[0], b = reinterpret_cast<const uint4 *>(p)[1];
+        e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(u16 *p, const u32 *l, const u32 *) {
+        *reinterpret_cast<uint4 *>(p) = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+    }
+};
 
 template <int K>
 __global__ void __launch_bounds__(kMfThreads)
@@ -452,27 +478,34 @@ k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const 
     u32 pe[K], pl[K];
 #pragma unroll
     for (int k = 0; k < K; k++) { pe[k] = kNone; pl[k] = 0; }
+    u32 e[K], en[K];
+    RowIO<K>::load(P6 + (sg + bd.x + i0) * K, en);
     for (u32 i = i0; i < i1; i++) {
         const u32 x = bd.x + i;
         const u32 limit = bd.size - i;
         const u64 at = (sg + x) * K;
-        u32 e[K], l[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) e[k] = P6[at + k];
+        for (int k = 0; k < K; k++) e[k] = en[k];
+        if (i + 1 < i1) RowIO<K>::load(P6 + at + K, en);   // next row in flight while this one is resolved
+        u32 l[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
             l[k] = 0;
             if (e[k] == kNone) continue;
             bool got = false;
             if (e[k] > 0) {
+                if (pe[k] == e[k] - 1 && pl[k] >= 1) { l[k] = pl[k] - 1; got = true; }   // usual case: same rank
+                else {
 #pragma unroll
-                for (int j = 0; j < K; j++)
-                    if (!got && pe[j] == e[k] - 1 && pl[j] >= 1) { l[k] = pl[j] - 1; got = true; }
+                    for (int j = 0; j < K; j++)
+                        if (!got && pe[j] == e[k] - 1 && pl[j] >= 1) { l[k] = pl[j] - 1; got = true; }
+                }
             }
             if (!got) l[k] = lcp_words(base + x, base + e[k], limit);
         }
+        RowIO<K>::store(L6 + at, l, e);
 #pragma unroll
-        for (int k = 0; k < K; k++) { if (e[k] != kNone) L6[at + k] = (u16)l[k]; pe[k] = e[k]; pl[k] = l[k]; }
+        for (int k = 0; k < K; k++) { pe[k] = e[k]; pl[k] = l[k]; }
     }
 }
 
