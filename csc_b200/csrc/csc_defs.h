@@ -78,6 +78,7 @@ struct ApUnit {
     u16 pad;
 };
 
+
 struct Cand { u32 len; u32 dist; };   // MFUnit: dist code 0 literal, 1..4 rep, 4+d match
 
 // ---- small adaptive-probability tables (csc_model.h:95-123), 12-bit in u16 --
@@ -98,6 +99,7 @@ struct ModelSmall {
     u32 row_l[8];
     u32 cl[kMaxCand];     // scratch: candidate list of the current find_match (len, dist code)
     u32 cd[kMaxCand];
+    Cand pt[64];          // scratch: price table of the optimal parser (FindMatchWithPrice output)
     u32 bq[32];           // pending range-coder decisions of the current packet: probability slot ids
     u16 bq_p[32];         //   ... and the probabilities fetched for them (lane-parallel)
 };

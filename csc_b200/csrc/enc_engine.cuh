@@ -860,7 +860,7 @@ struct Encoder {
     CSC_HDN void parse_optimal(u32 x0, u32 size) {   // compress_advanced, csc_lz.cpp:207-333
         const u32 end = x0 + size;
         ApUnit *ap = S.ap;
-        Cand t[64];
+        Cand *t = M.pt;   // per-warp scratch instead of 32 private copies on the stack
         u32 x = x0;          // wnd_curpos_
         u32 i = 0;           // bytes of the sub-block already emitted
         while (i < size) {

@@ -348,7 +348,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     // ---- serial engines, one stream per warp
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, C.dev);
-    const bool pair_mode = es[0].cfg.lz_mode == 2 && !getenv("CSC_B200_NO_PAIR");
+    const bool pair_mode = es[0].cfg.lz_mode == 2 && getenv("CSC_B200_PAIR");   // experimental: measured slower in round 1
     if (pair_mode) {
         u32 grid = std::min<u32>((ns + kEncWarps / 2 - 1) / (kEncWarps / 2), (u32)nsm * 16);
         if (C.rings.ensure((size_t)grid * (kEncWarps / 2) * kRingCap * sizeof(uint4))) return kErrCuda;
