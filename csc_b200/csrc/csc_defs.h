@@ -117,6 +117,7 @@ struct EncStream {
     EncCfg cfg;
     const u8 *lz;          // LZ stream: input after the static e8e9/dict filters
     u32 n;                 // stream bytes
+    u8 *tmp;               // scratch of n bytes (dictionary filter staging, delta-filtered runs)
     u32 nseg;
     const u32 *seg_size;   // [nseg] Read() sizes
     const u32 *seg_blk0;   // [nseg] first block index of each segment

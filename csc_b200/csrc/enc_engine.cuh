@@ -136,38 +136,61 @@ struct Encoder {
         q_push((u32)(&pr - reinterpret_cast<u16 *>(&M)), bit);
     }
     CSC_HDF void enc_bit_g(u32 gidx, u32 bit) { q_push(kSlotGlobal | gidx, bit); }   // p_lit / p_delta entry
+    CSC_HDN void rc_block_full() { event(1); }   // cold: a 64 KiB RC block completed (csc_coder.cpp:97-104)
     CSC_HDN void flush_bits() {
         const u32 n = bq_n;
         if (!n) return;
         const u32 bits = bq_bits;
+        u32 v = 0;   // probability of decision `lane` (device) / scratch (host)
 #if defined(__CUDA_ARCH__)
         if (CSC_LANE < n) {
             u32 slot = M.bq[CSC_LANE];
             u16 *pp = (slot & kSlotGlobal) ? S.p_lit + (slot & ~kSlotGlobal) : reinterpret_cast<u16 *>(&M) + slot;
-            u32 v = *pp;
+            v = *pp;
             *pp = (u16)(((bits >> CSC_LANE) & 1) ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
-            M.bq_p[CSC_LANE] = (u16)v;
         }
-        __syncwarp();
 #else
         for (u32 k = 0; k < n; k++) {
             u32 slot = M.bq[k];
             u16 *pp = (slot & kSlotGlobal) ? S.p_lit + (slot & ~kSlotGlobal) : reinterpret_cast<u16 *>(&M) + slot;
-            u32 v = *pp;
-            *pp = (u16)(((bits >> k) & 1) ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
-            M.bq_p[k] = (u16)v;
+            u32 pv = *pp;
+            *pp = (u16)(((bits >> k) & 1) ? pv + ((0xFFFu - pv) >> 5) : pv - (pv >> 5));
+            M.bq_p[k] = (u16)pv;
         }
 #endif
+        // the serial part: range/low recurrence with the whole coder state in registers
         u64 lo = low;
-        u32 rg = range;
+        u32 rg = range, cs = cachesize, ca = cache, on = rc_n, ob = rc_blk;
+        u8 *const out = S.rc_out;
+        const u32 cap = S.rc_cap, bsz = S.cfg.csc_blocksize;
 #pragma unroll 1
         for (u32 k = 0; k < n; k++) {
-            u32 bound = (rg >> 12) * M.bq_p[k];
+#if defined(__CUDA_ARCH__)
+            const u32 p = __shfl_sync(0xFFFFFFFFu, v, k);
+#else
+            const u32 p = M.bq_p[k];
+#endif
+            const u32 bound = (rg >> 12) * p;
             if ((bits >> k) & 1) rg = bound;
             else { lo += bound; rg -= bound; }
-            if (rg < (1u << 24)) { rg <<= 8; low = lo; shift_low(); lo = low; }
+            if (rg < (1u << 24)) {   // RC_ShiftLow, csc_coder.cpp:89-112
+                rg <<= 8;
+                if ((u32)lo < 0xFF000000u || (u32)(lo >> 32) != 0) {
+                    u32 t = ca;
+                    const u32 carry = (u32)(lo >> 32);
+                    do {
+                        if (on < cap) out[on] = (u8)(t + carry); else err = kErrOverflow;
+                        on++;
+                        if (++ob == bsz) { rc_n = on; rc_block_full(); ob = 0; }
+                        t = 0xFF;
+                    } while (--cs != 0);
+                    ca = ((u32)lo >> 24) & 0xFF;
+                }
+                cs++;
+                lo = (u64)((u32)lo << 8);
+            }
         }
-        low = lo; range = rg;
+        low = lo; range = rg; cachesize = cs; cache = ca; rc_n = on; rc_blk = ob;
         w_sync();
         bq_n = 0; bq_bits = 0;
     }
@@ -1035,22 +1058,24 @@ struct Encoder {
         return (S.lz[a + j] - prev) & 0xFF;
     }
     CSC_HDN void delta_run(u32 a, u32 size, u32 chn) {   // Forward_Delta + CompressRLE, csc_model.cpp:471-513
+        // the filtered run is materialised lane-parallel into the stream's scratch, then coded serially
+        u8 *f = S.tmp + a;
+#pragma unroll 1
+        for (u32 k = CSC_LANE; k < size; k += CSC_NLANES) f[k] = (u8)delta_byte(a, size, chn, k);
+        w_sync();
         encode_int(size);
         u32 sctx = 0;
-        u32 pm1 = 0;   // src[i-1]
         for (u32 i = 0; i < size;) {
-            u32 c0 = delta_byte(a, size, chn, i);
-            if (i > 0 && size - i > 3 && pm1 == c0 && c0 == delta_byte(a, size, chn, i + 1) &&
-                c0 == delta_byte(a, size, chn, i + 2)) {
-                u32 j = i + 3, len = 3;
-                while (j < size && delta_byte(a, size, chn, j) == c0) { len++; j++; }
-                if (len > 10) {
+            const u32 c0 = f[i];
+            if (i > 0 && size - i > 3 && f[i - 1] == c0 && c0 == f[i + 1] && c0 == f[i + 2]) {
+                u32 j = i + 3;
+                while (j < size && f[j] == c0) j++;
+                if (j - i > 10) {
                     sctx = c0;
                     enc_bit(M.p_rle_flag, 1);
-                    encode_matchlen_2(len - 11);
+                    encode_matchlen_2(j - i - 11);
                     flush_bits();
                     i = j;
-                    pm1 = c0;
                     continue;
                 }
             }
@@ -1058,7 +1083,6 @@ struct Encoder {
             lit_bits(65536 + sctx * 256, c0);   // p_delta follows p_lit
             flush_bits();
             sctx = c0;
-            pm1 = c0;
             i++;
         }
     }

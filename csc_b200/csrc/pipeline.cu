@@ -243,7 +243,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         EncStream &S = es[s];
         memset(&S, 0, sizeof(S));
         S.cfg = cfg_from_props(&J.props);
-        S.lz = C.lz.as<u8>() + goff[s]; S.n = J.n; S.nseg = (u32)J.segs.size();
+        S.lz = C.lz.as<u8>() + goff[s]; S.n = J.n; S.tmp = C.tmp.as<u8>() + goff[s]; S.nseg = (u32)J.segs.size();
         S.seg_size = C.segsize.as<u32>() + seg0[s]; S.seg_blk0 = C.segblk0.as<u32>() + seg0[s];
         S.binfo = C.binfo.as<u32>(); S.bbpb = C.bbpb.as<u32>();
         S.tail_dlt = C.taildlt.as<u32>() + (size_t)seg0[s] * 5; S.dict_ok = C.dictok.as<u8>();

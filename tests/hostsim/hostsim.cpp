@@ -186,6 +186,8 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         u32 tn = 0;
         EncStream S;
         memset(&S, 0, sizeof(S));
+        std::vector<u8> tmpbuf(n + 64);
+        S.tmp = tmpbuf.data();
         S.cfg = cfg; S.lz = lz.data(); S.n = n; S.nseg = (u32)seg.size();
         S.seg_size = seg.data(); S.seg_blk0 = seg_blk0.data(); S.binfo = binfo.data(); S.bbpb = bbpb.data();
         S.tail_dlt = tail_dlt.data(); S.dict_ok = dict_ok.data();
