@@ -463,8 +463,135 @@ struct Encoder {
         return ml >= h.good;
     }
 
+#if defined(__CUDACC__)
+    // ---- lane-parallel find_match (device) ------------------------------------------------------
+    // Lane c owns candidate c of the reference probe order: 0-3 rep distances, 4 the 2-byte table,
+    // 5 the 3-byte table, 8..8+K-1 the 6-byte bucket.  The reference's running state turns into two
+    // prefix maxima over the lanes: `dist` (a table candidate is entered iff its distance exceeds all
+    // earlier table distances) and `minlen` (a candidate is recorded iff its length exceeds all earlier
+    // usable lengths); the good_len cut drops every lane behind the first long candidate.
+    static __device__ __forceinline__ u32 lane_lcp(const u8 *a, const u8 *m, u32 lim) {
+        u32 l = 0;
+        while (l + 4 <= lim) {
+            u32 dd = ld32u(a + l) ^ ld32u(m + l);
+            if (dd) return l + (((u32)__ffs((int)dd) - 1) >> 3);
+            l += 4;
+        }
+        while (l < lim && a[l] == m[l]) l++;
+        return l;
+    }
+    static __device__ __forceinline__ u32 scan_max_excl(u32 v, u32 lane) {
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, v, sft); if (lane >= (u32)sft) v = max(v, t); }
+        u32 e = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        return lane ? e : 0;
+    }
+    static __device__ __forceinline__ u32 fm_lanes(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
+        const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
+        const u8 *cur = h.lz + x;
+        const u32 pos = h.vld + x;
+        const bool is_rep = lane < 4, is_tab = lane == 4 || lane == 5, is_row = lane >= 8 && lane < 8 + h.K;
+        u32 d = 0, L = 0;
+        bool cand = false, need_cmp = false;
+        if (is_rep) {
+            d = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : r3;
+            cand = d < h.vld;
+            need_cmp = cand;
+        } else if (is_tab) {
+            const bool three = lane == 5;
+            if (!h.tmode) {
+                const u32 *P = three ? h.P3 : h.P2;
+                u32 e = P[x];
+                L = three ? h.L3[x] : h.L2[x];
+                if (e != kNone && bit_get(h.D23, e)) { e = alive23(h, P, e); need_cmp = true; }
+                d = (e == kNone) ? pos : x - e;
+            } else {
+                const u32 w = word_at(h, x, x + limit);
+                u32 *T = three ? h.ht3 : h.ht2;
+                const u32 hh = three ? h3_of(w) : h2_of(w);
+                d = pos - g_ld(&T[hh]);
+                T[hh] = pos;
+                need_cmp = true;
+            }
+            cand = true;
+        } else if (is_row) {
+            const size_t at = (size_t)x * h.K + (lane - 8);
+            const u32 e = h.P6[at];
+            L = h.L6[at];
+            cand = e != kNone && !dead6(h, e);
+            d = e != kNone ? x - e : 0;
+        }
+        const u32 validrow = __ballot_sync(FULL, is_row && d != 0) >> 8;
+        const u32 alivem = __ballot_sync(FULL, is_row && cand);
+        if (limit <= 1) return 0;
+        const u32 lt = (1u << lane) - 1;
+        const bool cons = is_row && cand && (u32)__popc(alivem & lt) < h.W;
+        // distance filter: running maximum over the table candidates that are looked at
+        const u32 dm = (is_tab || cons) ? d : 0;
+        const bool entered = dm > scan_max_excl(dm, lane);
+        bool usable;
+        if (is_rep) usable = cand;
+        else if (lane == 4) usable = entered && d < h.vld && x > d;      // `wpos > dist` (csc_mf.cpp:306)
+        else if (lane == 5) usable = entered && d < h.vld && x >= d;
+        else usable = cons && entered && d < h.vld;
+        // lengths that are not precomputed: rep distances, table-mode / re-walked table candidates
+        if (need_cmp && usable) {
+            const u8 *m = cur - d;
+            L = 0;
+            if (m[1] == cur[1]) L = lane_lcp(cur, m, limit < 64 ? limit : 64);
+        }
+        u32 more = __ballot_sync(FULL, need_cmp && usable && L == 64 && limit > 64);
+        while (more) {   // long matches are finished by the whole warp
+            const u32 src = (u32)__ffs((int)more) - 1;
+            more &= more - 1;
+            const u32 dd = __shfl_sync(FULL, d, src);
+            const u32 ext = 64 + lcp_bytes(cur + 64, cur - dd + 64, limit - 64);
+            if (lane == src) L = ext;
+        }
+        // length filter: running maximum of the usable lengths (starts at 1)
+        const u32 lu = usable ? L : 0;
+        const u32 run = max(1u, scan_max_excl(lu, lane));
+        bool acc = usable && L > run && !(!is_rep && L <= 6 && d >= mf_bound(L));
+        const u32 stopm = __ballot_sync(FULL, acc && L >= h.good);
+        if (stopm && lane > (u32)__ffs((int)stopm) - 1) acc = false;
+        const u32 has11 = __ballot_sync(FULL, lane == 0 && usable && L >= 2) & 1u;   // rep0-len1 rides on a >= 2 rep0 match
+        const u32 accm = __ballot_sync(FULL, acc);
+        if (has11 && lane == 0) { h.cl[0] = 1; h.cd[0] = 1; }
+        if (acc) { const u32 idx = has11 + (u32)__popc(accm & lt); h.cl[idx] = L; h.cd[idx] = is_rep ? 1 + lane : 4 + d; }
+        u32 cnt = has11 + (u32)__popc(accm);
+        __syncwarp();
+        // a dead entry inside a full row leaves the bucket short: keep walking the chain behind the row (rare)
+        const u32 full = (1u << h.K) - 1;
+        if (h.W && !stopm && validrow == full && (u32)__popc(alivem) < h.W) {
+            u32 dist = dm, minlen = lu;
+#pragma unroll
+            for (int sft = 16; sft; sft >>= 1) { dist = max(dist, __shfl_xor_sync(FULL, dist, sft)); minlen = max(minlen, __shfl_xor_sync(FULL, minlen, sft)); }
+            minlen = max(minlen, 1u);
+            u32 found = (u32)__popc(alivem);
+            u32 src = __shfl_sync(FULL, x - d, 8 + h.K - 1), kk = 0;
+            const u32 c1 = cur[1];
+            while (found < h.W) {
+                u32 e = h.P6[(size_t)src * h.K + kk];
+                if (e == kNone) break;
+                if (++kk == h.K) { src = e; kk = 0; }
+                if (dead6(h, e)) continue;
+                found++;
+                u32 dd = x - e;
+                if (dd <= dist) continue;
+                dist = dd;
+                if (dist >= h.vld || minlen >= limit) continue;
+                if (probe(h, cur, dd, limit, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
+            }
+        }
+        return cnt;
+    }
+#endif
+
     // find_match (csc_mf.cpp:243-495): candidate list (M.cl / M.cd) in reference probe order.
     CSC_HDF static u32 fm_core(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
+#if defined(__CUDA_ARCH__)
+        return fm_lanes(h, x, limit, r0, r1, r2, r3);
+#endif
         const u8 *cur = h.lz + x;
         const u32 pos = h.vld + x;
         const u32 sb_end = x + limit;

@@ -19,7 +19,7 @@ tile = 32 << 20
 data = np.empty(total, np.uint8)
 for i, off in enumerate(range(0, total, tile)):
     n = min(tile, total - off)
-    data[off:off + n] = synth.text(n, 12345 + i) if kind == "text" else synth.mixed(n, 12345 + i)
+    data[off:off + n] = {"text": synth.text, "mixed": synth.mixed, "exe": synth.exe}[kind](n, 12345 + i)
 d = torch.from_numpy(data).cuda()
 n = (total + chunk - 1) // chunk
 ptrs = [d.data_ptr() + i * chunk for i in range(n)]
