@@ -108,7 +108,7 @@ struct Encoder {
         bc_bits = 0; bc_val = 0; rc_blk = 0; bc_blk = 0;
         bq_n = 0; bq_bits = 0;
     }
-    CSC_HD void shift_low() {   // csc_coder.cpp:89-112
+    CSC_HDN void shift_low() {   // csc_coder.cpp:89-112
         if ((u32)low < 0xFF000000u || (u32)(low >> 32) != 0) {
             u32 t = cache;
             u32 carry = (u32)(low >> 32);
@@ -247,12 +247,41 @@ struct Encoder {
     }
     CSC_HDN void encode_literal(u32 c) {   // csc_model.cpp:169-183
         trace(0, c, 0);
+#if defined(__CUDA_ARCH__)
+        // device fast path: the 9 decisions (flag + 8 tree nodes) are known up front, lane k owns decision k;
+        // probabilities are fetched/adapted in parallel and the range recurrence is unrolled over shuffles
+        const u32 cc = c | 0x100;
+        const u32 lane = CSC_LANE;
+        u32 v = 0;
+        if (lane < 9) {
+            u16 *pp = lane == 0 ? &M.p_state[state * 3] : S.p_lit + ctx * 256 + (cc >> (9 - lane));
+            v = *pp;
+            const u32 bit = lane == 0 ? 0u : (cc >> (8 - lane)) & 1u;
+            *pp = (u16)(bit ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
+        }
+        state = (state * 4) & 0x3F;
+        ctx = c;
+        u64 lo = low;
+        u32 rg = range;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const u32 p = __shfl_sync(0xFFFFFFFFu, v, k);
+            const u32 bound = (rg >> 12) * p;
+            const bool bit = k == 0 ? false : ((cc >> (8 - k)) & 1u) != 0;
+            if (bit) rg = bound;
+            else { lo += bound; rg -= bound; }
+            if (rg < (1u << 24)) { rg <<= 8; low = lo; shift_low(); lo = low; }
+        }
+        low = lo; range = rg;
+        __syncwarp();
+#else
         enc_bit(M.p_state[state * 3 + 0], 0);
         state = (state * 4) & 0x3F;
         u32 row = ctx * 256;
         ctx = c;
         lit_bits(row, c);
         flush_bits();
+#endif
     }
     CSC_HDN void encode_matchlen_1(u32 len) {   // csc_model.cpp:113-145
         if (len < 16) {

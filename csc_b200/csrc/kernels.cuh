@@ -22,6 +22,7 @@
 #include "plan.h"
 #include "enc_engine.cuh"
 #include "dec_engine.cuh"
+#include "radix_sort.cuh"
 
 namespace cscb {
 
@@ -386,7 +387,8 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
         vals[bd.cpos + i] = bd.x + i;
         if (which != 6) {   // 3-byte / 2-byte chains (HASH3 csc_mf.cpp:30-33, HASH2 :23-28); excluded blocks sort apart
             u32 h = which == 3 ? ((v & 0xFF) << 8) ^ (((v >> 8) & 0xFF) << 5) ^ ((v >> 16) & 0xFF) : h2;
-            keys[bd.cpos + i] = nolz[blockIdx.x] ? ~0ull : (((u64)bd.stream << key_shift) | h);
+            // blocks left out of the chain carry flag bit 63 and sort into the all-ones bucket, where k_mf_rows skips them
+            keys[bd.cpos + i] = nolz[blockIdx.x] ? ((1ull << 63) | ((u64)bd.stream << key_shift) | ((1u << key_shift) - 1)) : (((u64)bd.stream << key_shift) | h);
             continue;
         }
         keys[bd.cpos + i] = ((u64)bd.stream << key_shift) | h6;
@@ -402,15 +404,19 @@ __global__ void k_mf_rows(const u64 *__restrict__ keys, const u32 *__restrict__ 
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 k = keys[i];
-    if (k == ~0ull) return;   // position of a block left out of this chain (array pre-filled with kNone)
+    if (k >> 63) return;   // position of a block left out of this chain (array pre-filled with kNone)
     const u32 s = (u32)(k >> key_shift);
     const u32 K = kforce ? kforce : stream_K[s];
     if (!K) return;
     u32 *row = P6 + (stream_goff[s] + vals[i]) * K;
     bool live = true;
-    for (u32 j = 0; j < K; j++) {
-        live = live && (i > j) && keys[i - 1 - j] == k;
-        row[j] = live ? vals[i - 1 - j] : kNone;
+    u32 j = i;
+    for (u32 c = 0; c < K; c++) {
+        // previous element of the same (stream, hash) run; flagged entries only occur in the all-ones bucket
+        while (live && j > 0 && (keys[j - 1] >> 63) && ((keys[j - 1] ^ k) << 1) == 0) j--;
+        live = live && j > 0 && keys[j - 1] == k;
+        row[c] = live ? vals[j - 1] : kNone;
+        if (live) j--;
     }
 }
 

@@ -85,7 +85,7 @@ struct Ctx {
     u32 *d_p2bits = nullptr;
     DevBuf lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
-        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz;
+        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB;
     PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta;
     Timer tm;
     CSCB200_Stats stats;
@@ -203,6 +203,21 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         if (rctot >= 0xFFFF0000ull || total >= 0xFFFF0000ull) return kErrUnsupported;
     }
     const u32 nblk = (u32)blks.size(), nseg = (u32)segs.size(), npos = cpos;
+    // radix-sort tiles: never across streams; histogram laid out [stream][digit][tile-of-stream]
+    std::vector<RsTile> rst;
+    {
+        u32 cstart = 0, hb = 0;
+        for (u32 s = 0; s < ns; s++) {
+            const u32 n_s = jobs[s]->n, nts = (n_s + kRsTile - 1) / kRsTile;
+            for (u32 j = 0; j < nts; j++) {
+                RsTile t;
+                t.start = cstart + j * kRsTile; t.count = std::min(kRsTile, n_s - j * kRsTile); t.hbase = hb + j; t.nts = nts;
+                rst.push_back(t);
+            }
+            cstart += n_s; hb += 256 * nts;
+        }
+    }
+    const u32 nrst = (u32)rst.size(), rsHn = 256 * nrst, rsNb = (rsHn + kScanChunk - 1) / kScanChunk;
     total += 256;
     C.stats.mf_positions += npos;
     // ---- device memory
@@ -235,6 +250,36 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, C.keys0.as<u64>(), C.keys1.as<u64>(), C.vals0.as<u32>(),
                                     C.vals1.as<u32>(), (int)npos, 0, end_bit, st);
     if (C.cubtmp.ensure(cub_bytes + 16)) return kErrCuda;
+    if (C.rstiles.ensure((size_t)nrst * sizeof(RsTile)) || C.rsH.ensure((size_t)rsHn * 4 + 64) || C.rsB.ensure((size_t)rsNb * 4 + 64)) return kErrCuda;
+    u32 launches = 1;
+    static const bool use_cub = getenv("CSC_B200_CUB_SORT") != nullptr;   // library sort only for A/B timing
+    static bool smem_opt_in = false;
+    if (!smem_opt_in) {
+        CK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRsTile * 12)));
+        smem_opt_in = true;
+    }
+    // sorts (keys0,vals0) by the low `hbits` key bits inside every stream; returns the buffers holding the result
+    auto sort_pairs = [&](u32 hbits, int cub_end_bit, u64 *&kres, u32 *&vres) -> int {
+        u64 *ka = C.keys0.as<u64>(), *kb = C.keys1.as<u64>();
+        u32 *va = C.vals0.as<u32>(), *vb = C.vals1.as<u32>();
+        if (use_cub) {
+            cub::DeviceRadixSort::SortPairs(C.cubtmp.p, cub_bytes, ka, kb, va, vb, (int)npos, 0, cub_end_bit, st);
+            kres = kb; vres = vb;
+            return 0;
+        }
+        for (u32 shift = 0; shift < hbits; shift += 8) {
+            const u32 bits = std::min<u32>(8, hbits - shift), mask = (1u << bits) - 1;
+            rs_hist<<<nrst, kRsThreads, 0, st>>>(ka, C.rstiles.as<RsTile>(), shift, mask, C.rsH.as<u32>());
+            rs_scan_a<<<rsNb, kRsThreads, 0, st>>>(C.rsH.as<u32>(), rsHn, C.rsB.as<u32>());
+            rs_scan_b<<<1, kRsThreads, 0, st>>>(C.rsB.as<u32>(), rsNb);
+            rs_scan_c<<<rsNb, kRsThreads, 0, st>>>(C.rsH.as<u32>(), rsHn, C.rsB.as<u32>());
+            rs_scatter<<<nrst, kRsThreads, kRsTile * 12, st>>>(ka, va, kb, vb, C.rstiles.as<RsTile>(), shift, mask, C.rsH.as<u32>());
+            std::swap(ka, kb); std::swap(va, vb);
+            launches += 5;
+        }
+        kres = ka; vres = va;
+        return 0;
+    };
 
     // ---- stream descriptors
     std::vector<EncStream> es(ns);
@@ -271,6 +316,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
                                jobs[s]->in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.blkdesc.p, blks.data(), (size_t)nblk * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.segdesc.p, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.rstiles.p, rst.data(), (size_t)nrst * sizeof(RsTile), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.segsize.p, segsize.data(), (size_t)nseg * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.segblk0.p, segblk0.data(), (size_t)nseg * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.sbits.p, sbits.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
@@ -291,7 +337,6 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     CK(cudaMemsetAsync(C.segout.p, 0, (size_t)nseg * sizeof(SegOut), st));
     k_fill_u16<<<592, 256, 0, st>>>(C.plit.as<u16>(), (u64)ns * 131072, 2048);
     T.mark(st);                                                                   // 1
-    u32 launches = 1;
     // ---- analyzer, static plan, filters
     k_analyze<<<(nblk + kAnWarps - 1) / kAnWarps, kAnWarps * 32, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), nblk, C.d_AT,
                                                                            C.binfo.as<u32>(), C.bbpb.as<u32>(), C.taildlt.as<u32>());
@@ -308,10 +353,11 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), key_shift,
                                            C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), 6, C.nolz.as<u8>());
     T.mark(st);                                                                   // 4
-    cub::DeviceRadixSort::SortPairs(C.cubtmp.p, cub_bytes, C.keys0.as<u64>(), C.keys1.as<u64>(), C.vals0.as<u32>(), C.vals1.as<u32>(),
-                                    (int)npos, 0, end_bit, st);
+    u64 *ksorted = nullptr;
+    u32 *vsorted = nullptr;
+    sort_pairs(key_shift, end_bit, ksorted, vsorted);
     T.mark(st);                                                                   // 5
-    k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(C.keys1.as<u64>(), C.vals1.as<u32>(), npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(),
+    k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(),
                                                   C.P6.as<u32>(), pos_stream, 0);
     T.mark(st);                                                                   // 6
     if (K == 1) k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
@@ -324,14 +370,12 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         u16 *L = which == 3 ? C.L3.as<u16>() : C.L2.as<u16>();
         k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), shift,
                                                C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which, C.nolz.as<u8>());
-        cub::DeviceRadixSort::SortPairs(C.cubtmp.p, cub_bytes, C.keys0.as<u64>(), C.keys1.as<u64>(), C.vals0.as<u32>(), C.vals1.as<u32>(),
-                                        (int)npos, 0, (int)(shift + stream_bits), st);
-        k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(C.keys1.as<u64>(), C.vals1.as<u32>(), npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P,
-                                                      pos_stream, 1);
+        sort_pairs(shift, (int)(shift + stream_bits), ksorted, vsorted);
+        k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P, pos_stream, 1);
         k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
     }
     T.mark(st);                                                                   // 7
-    launches += 3 + (u32)((end_bit + 7) / 8) * 2 + 1 + 2 * (3 + 8);
+    launches += 3 + 1 + 2 * 3;
     if (g_dump.on && ns == 1) {
         CK(cudaStreamSynchronize(st));
         u32 n1 = jobs[0]->n;
