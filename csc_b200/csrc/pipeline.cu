@@ -364,6 +364,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     else if (K == 2) k_mf_extend<2><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else if (K == 8) k_mf_extend<8><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else return kErrUnsupported;
+    T.mark(st);                                                                   // 7
     for (u32 which = 3; which >= 2; which--) {
         const u32 shift = which == 3 ? 16 : 14;
         u32 *P = which == 3 ? C.P3.as<u32>() : C.P2.as<u32>();
@@ -374,7 +375,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P, pos_stream, 1);
         k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
     }
-    T.mark(st);                                                                   // 7
+    T.mark(st);                                                                   // 8
     launches += 3 + 1 + 2 * 3;
     if (g_dump.on && ns == 1) {
         CK(cudaStreamSynchronize(st));
@@ -401,7 +402,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         u32 grid = std::min<u32>((ns + kEncWarps - 1) / kEncWarps, (u32)nsm * 8);
         k_encode<<<grid, kEncWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns, d_queue, C.d_p2bits);
     }
-    T.mark(st);                                                                   // 8
+    T.mark(st);                                                                   // 9
     launches += 1;
     CK(cudaGetLastError());
     // ---- results
@@ -439,12 +440,12 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         jobs[s]->bc = C.h_bc.as<u8>() + hbcoff[s];
         jobs[s]->ev = C.h_ev.as<u8>() + evoff[s];
     }
-    T.mark(st);                                                                   // 9
+    T.mark(st);                                                                   // 10
     CK(cudaStreamSynchronize(st));
     CSCB200_Stats &S = C.stats;
     S.ms_h2d += T.ms(0, 1); S.ms_analyze += T.ms(1, 2); S.ms_filters += T.ms(2, 3); S.ms_mf_hash += T.ms(3, 4);
-    S.ms_mf_sort += T.ms(4, 5); S.ms_mf_rows += T.ms(5, 6); S.ms_mf_extend += T.ms(6, 7); S.ms_encode += T.ms(7, 8);
-    S.ms_d2h += T.ms(8, 9); S.ms_total_gpu += T.ms(0, 9);
+    S.ms_mf_sort += T.ms(4, 5); S.ms_mf_rows += T.ms(5, 6); S.ms_mf_extend += T.ms(6, 7); S.ms_mf_chains += T.ms(7, 8);
+    S.ms_encode += T.ms(8, 9); S.ms_d2h += T.ms(9, 10); S.ms_total_gpu += T.ms(0, 10);
     S.kernel_launches += launches; S.streams += ns; S.waves += 1;
     return ret;
 }
