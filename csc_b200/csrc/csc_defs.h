@@ -67,15 +67,15 @@ struct EncCfg {
 };
 
 // ---- optimal-parser unit (role of APUnit, csc_lz.h:33-41) -------------------
-struct ApUnit {
-    u32 dist;
-    u32 price;
+struct alignas(16) ApUnit {   // one position of the optimal parser's path (APUnit, csc_lz.h:45-60); 2 x 16 bytes
     u32 rep[4];
+    u32 dist;
     u16 back_pos;
     u16 next_pos;
     u8 state;
     u8 lit;
     u16 pad;
+    u32 pad2;              // prices of the look-ahead window live in lanes, not here
 };
 
 
@@ -99,7 +99,6 @@ struct ModelSmall {
     u32 row_l[8];
     u32 cl[kMaxCand];     // scratch: candidate list of the current find_match (len, dist code)
     u32 cd[kMaxCand];
-    Cand pt[64];          // scratch: price table of the optimal parser (FindMatchWithPrice output)
     u32 bq[32];           // pending range-coder decisions of the current packet: probability slot ids
     u16 bq_p[32];         //   ... and the probabilities fetched for them (lane-parallel)
 };

@@ -370,14 +370,6 @@ struct Encoder {
 
     // ------------------------------------------------------------------ prices
     CSC_HD u32 bitprice(u32 p, u32 bit) const { return M.p2bits[(bit ? p : 4096u - p) >> 3]; }
-    CSC_HDN u32 literal_price(u32 fstate, u32 fctx, u32 c) const {   // csc_model.cpp:185-196
-        u32 r = bitprice(M.p_state[fstate * 3], 0);
-        const u16 *row = S.p_lit + fctx * 256;
-        u32 cc = c | 0x100;
-#pragma unroll
-        for (int k = 0; k < 8; k++) r += bitprice(row[cc >> (8 - k)], (cc >> (7 - k)) & 1);
-        return r;
-    }
     CSC_HD u32 rep0len1_price(u32 fs) const {   // csc_model.cpp:209-216
         return bitprice(M.p_state[fs * 3], 1) + bitprice(M.p_state[fs * 3 + 1], 0) + bitprice(M.p_state[fs * 3 + 2], 0);
     }
@@ -407,16 +399,6 @@ struct Encoder {
             do { r += bitprice(M.p_matchlen_extra3[c >> 7], (c >> 6) & 1); c <<= 1; } while (c < 0x4000);
         }
         return r;
-    }
-    CSC_HDN u32 matchlen_price(u32 lencode) {   // csc_model.cpp:286-299
-        if (lencode >= 32) return 128 * 6;
-        if (lp_rebuild-- == 0) {
-            w_sync();
-            for (u32 i = CSC_LANE; i < 32; i += CSC_NLANES) M.len_price[i] = len_price_one(i);
-            w_sync();
-            lp_rebuild = 4096;
-        }
-        return M.len_price[lencode];
     }
 
     // ----------------------------------------------------- match finder (state)
@@ -981,36 +963,64 @@ struct Encoder {
     }
 
     // ---------------------------------------------------------- optimal parser
-    // FindMatchWithPrice (csc_mf.cpp:584-625): t[0] longest candidate, t[1] rep0len1,
-    // t[2..] price per length.
-    CSC_HDN void find_match_price(u32 x, u32 limit, u32 fstate, const u32 *rp, Cand *t) {
-        u32 n = find_match(x, limit, rp[0], rp[1], rp[2], rp[3]);
-        if (n == 0) { t[0].len = 1; t[0].dist = 0; }
-        else { t[0].len = M.cl[n - 1]; t[0].dist = M.cd[n - 1]; }
-        if (t[0].len >= good) return;
-        t[1].dist = 0;
-        u32 lpos = 1;
-        for (u32 i = 0; i < n; i++) {
-            const u32 clen = M.cl[i], cdist = M.cd[i];
-            u32 dprice, rdist;
-            if (clen == 1 && cdist == 1) {
-                t[1].len = rep0len1_price(fstate);
-                t[1].dist = 1;
-                continue;
-            } else if (cdist <= 4) {
-                dprice = repdist_price(fstate, cdist - 1);
-                rdist = 0;
-            } else {
-                dprice = matchdist_price(fstate, cdist - 5);
-                rdist = cdist - 4;
+    // Written over 32 virtual lanes (warp.h: Lv).  Lane L of the price table holds the entry for match
+    // length L; lane j of the look-ahead window holds the best known (price, dist, back_pos) of position
+    // apcur + j.  good_len <= 24 in every optimal-parser level (csc_enc.cpp:70-82), so lengths and the
+    // window both fit 32 lanes; the window moves down one lane per position.
+    //
+    // FindMatchWithPrice (csc_mf.cpp:584-625) after find_match: t0 = longest candidate, t1 = rep0len1,
+    // td/tp[L] = candidate and price for length L (the first candidate that reaches L; lengths in the
+    // candidate list strictly increase).  GetMatchLenPrice rebuilds its table every 4096 calls
+    // (csc_model.cpp:286-299): the calls of one invocation are the priced lengths in ascending order, so
+    // the entry of rank r sees the old table iff r < lp_rebuild.
+    CSC_HDF void price_table(u32 n, u32 fstate, Cand &t0, Lv &td, Lv &tp, u32 &t1d, u32 &t1p) {
+        if (n == 0) { t0.len = 1; t0.dist = 0; }
+        else { t0.len = M.cl[n - 1]; t0.dist = M.cd[n - 1]; }
+        if (t0.len >= good) return;
+        t1d = 0;
+        u32 i0 = 0;
+        if (n && M.cl[0] == 1 && M.cd[0] == 1) { t1d = 1; t1p = rep0len1_price(fstate); i0 = 1; }
+        Lv need;
+        LV_FOR(L) {
+            u32 dist = 0, price = 0, nd = 0;
+            if (L >= 2 && L <= t0.len) {
+                u32 c = i0;
+                while (M.cl[c] < L) c++;
+                const u32 cdist = M.cd[c];
+                const u32 rdist = cdist <= 4 ? 0 : cdist - 4;
+                if (!(L <= 6 && rdist >= mf_bound(L))) {
+                    dist = cdist;
+                    nd = 1;
+                    price = cdist <= 4 ? repdist_price(fstate, cdist - 1) : matchdist_price(fstate, cdist - 5);
+                }
             }
-            while (lpos < clen) {
-                lpos++;
-                if (lpos <= 6 && rdist >= mf_bound(lpos)) { t[lpos].dist = 0; continue; }
-                t[lpos].dist = cdist;
-                t[lpos].len = dprice + matchlen_price(lpos - 2);   // .len doubles as price (MFUnit union)
-            }
+            td.v[LV_AT(L)] = dist; tp.v[LV_AT(L)] = price; need.v[LV_AT(L)] = nd;
         }
+        const u32 needm = lv_ballot(need);
+        const u32 calls = popc32(needm), k = lp_rebuild;
+        if (calls <= k) {
+            lp_rebuild = k - calls;
+            LV_FOR(L) if (need.v[LV_AT(L)]) tp.v[LV_AT(L)] += M.len_price[L - 2];
+        } else {
+            LV_FOR(L) if (need.v[LV_AT(L)] && popc32(needm & ((1u << L) - 1)) < k) tp.v[LV_AT(L)] += M.len_price[L - 2];
+            w_sync();
+            for (u32 i = CSC_LANE; i < 32; i += CSC_NLANES) M.len_price[i] = len_price_one(i);
+            w_sync();
+            LV_FOR(L) if (need.v[LV_AT(L)] && popc32(needm & ((1u << L) - 1)) >= k) tp.v[LV_AT(L)] += M.len_price[L - 2];
+            lp_rebuild = 4096 - (calls - k - 1);
+        }
+    }
+    CSC_HDF u32 literal_price_w(u32 fstate, u32 fctx, u32 c) const {   // csc_model.cpp:185-196, one bit per lane
+        const u16 *row = S.p_lit + fctx * 256;
+        const u32 cc = c | 0x100;
+        Lv a;
+        LV_FOR(kk) {
+            u32 r = 0;
+            if (kk < 8) r = bitprice(row[cc >> (8 - kk)], (cc >> (7 - kk)) & 1);
+            else if (kk == 8) r = bitprice(M.p_state[fstate * 3], 0);
+            a.v[LV_AT(kk)] = r;
+        }
+        return lv_sum(a);
     }
 
     CSC_HDN void ap_backward(u32 endi) {   // csc_lz.cpp:335-362
@@ -1036,109 +1046,116 @@ struct Encoder {
         for (int j = 0; j < 4; j++) rep[j] = ap[endi].rep[j];
     }
 
-    CSC_HDN void parse_optimal(u32 x0, u32 size) {   // compress_advanced, csc_lz.cpp:207-333
+    // compress_advanced (csc_lz.cpp:207-333) as one flat loop with a single match-finder site: outside a
+    // round a position is either a literal or starts a round; inside, position apcur is finalised (state
+    // and rep distances from its best predecessor, :236-262), searched, and relaxes the window (:296-329).
+    CSC_HDN void parse_optimal(u32 x0, u32 size) {
+        const MfCtx h = mfctx();
         const u32 end = x0 + size;
-        ApUnit *ap = S.ap;
-        Cand *t = M.pt;   // per-warp scratch instead of 32 private copies on the stack
+        ApUnit *const ap = S.ap;
         u32 x = x0;          // wnd_curpos_
         u32 i = 0;           // bytes of the sub-block already emitted
-        while (i < size) {
-            prefetch_fm(x + 1, end);
-            find_match_price(x, end - x, state, rep, t);
-            if (t[0].dist == 0) {
-                emit(OP_LIT, S.lz[x], 0, 0);
-                i++; x++;
+        bool in_round = false;
+        u32 apcur = 0, apend = 1, aplimit = 0;
+        Lv wp, wd, wb, td, tp;
+        u32 t1d = 0, t1p = 0;
+        Cand t0;
+        t0.len = 1; t0.dist = 0;
+        LV_FOR(j) { wp.v[LV_AT(j)] = 0; wd.v[LV_AT(j)] = 0; wb.v[LV_AT(j)] = 0; td.v[LV_AT(j)] = 0; tp.v[LV_AT(j)] = 0; }
+        while (in_round || i < size) {
+            const u32 lit = h.lz[x];
+            u32 ns = state, r0 = rep[0], r1 = rep[1], r2 = rep[2], r3 = rep[3];
+            if (in_round) {   // apcur >= 1
+                const u32 d = lv_get(wd, 0), l = lv_get(wb, 0);
+                const ApUnit pl = ap[l];
+                r0 = pl.rep[0]; r1 = pl.rep[1]; r2 = pl.rep[2]; r3 = pl.rep[3];
+                const u32 ls = pl.state;
+                if (d == 0) {
+                    ns = (ls * 4) & 0x3F;
+                } else if (d <= 4) {
+                    if (apcur - l == 1 && d == 1) {
+                        ns = (ls * 4 + 2) & 0x3F;
+                    } else {
+                        ns = (ls * 4 + 3) & 0x3F;
+                        // (csc_lz.cpp:246-256: the cases fall through, idx 0 leaves the queue untouched)
+                        if (d == 4) { const u32 t = r3; r3 = r2; r2 = r1; r1 = r0; r0 = t; }
+                        else if (d == 3) { const u32 t = r2; r2 = r1; r1 = r0; r0 = t; }
+                        else if (d == 2) { const u32 t = r1; r1 = r0; r0 = t; }
+                    }
+                } else {
+                    ns = (ls * 4 + 1) & 0x3F;
+                    r3 = r2; r2 = r1; r1 = r0; r0 = d - 4;
+                }
+                ApUnit u;
+                u.rep[0] = r0; u.rep[1] = r1; u.rep[2] = r2; u.rep[3] = r3;
+                u.dist = d; u.back_pos = (u16)l; u.next_pos = 0; u.state = (u8)ns; u.lit = (u8)lit; u.pad = 0; u.pad2 = 0;
+                ap[apcur] = u;
+                w_sync();
+            }
+            if (!in_round || apcur < aplimit) {
+                prefetch_core(h, x + 1, end);
+                const u32 n = fm_core(h, x, end - x, r0, r1, r2, r3);
+                price_table(n, ns, t0, td, tp, t1d, t1p);
+            }
+            if (!in_round) {
+                if (t0.dist == 0) {
+                    emit(OP_LIT, lit, 0, 0);
+                    i++; x++;
+                    continue;
+                }
+                in_round = true;
+                apcur = 0; apend = 1;
+                aplimit = (size - i) < kApLimit ? (size - i) : kApLimit;
+                LV_FOR(j) wp.v[LV_AT(j)] = j ? 0xFFFFFFFFu : 0u;
+                ApUnit u;
+                u.rep[0] = r0; u.rep[1] = r1; u.rep[2] = r2; u.rep[3] = r3;
+                u.dist = 0; u.back_pos = 0; u.next_pos = 0; u.state = (u8)ns; u.lit = (u8)lit; u.pad = 0; u.pad2 = 0;
+                ap[0] = u;
+                w_sync();
+            } else if (apcur == aplimit) {
+                ap_backward(apcur);
+                i += apcur;
+                in_round = false;
                 continue;
             }
-            u32 apcur = 0, apend = 1;
-            ap[0].price = 0;
-            ap[0].back_pos = 0;
-            for (int j = 0; j < 4; j++) ap[0].rep[j] = rep[j];
-            ap[0].state = (u8)state;
-            const u32 aplimit = (size - i) < kApLimit ? (size - i) : kApLimit;
-            for (;;) {
-                ap[apcur].lit = S.lz[x];
-                if (apcur) {
-                    u32 l = ap[apcur].back_pos;
-                    u32 r0 = ap[l].rep[0], r1 = ap[l].rep[1], r2 = ap[l].rep[2], r3 = ap[l].rep[3];
-                    u32 ls = ap[l].state, d = ap[apcur].dist, ns;
-                    if (d == 0) {
-                        ns = (ls * 4) & 0x3F;
-                    } else if (d <= 4) {
-                        u32 len = apcur - l;
-                        if (len == 1 && d == 1) {
-                            ns = (ls * 4 + 2) & 0x3F;
-                        } else {
-                            ns = (ls * 4 + 3) & 0x3F;
-                            // note (csc_lz.cpp:246-256): case 2 also performs the
-                            // rep[0] assignment; idx 0 leaves the queue untouched
-                            u32 r[4] = {r0, r1, r2, r3};
-                            u32 tmp = r[d - 1];
-                            if (d == 4) { r[3] = r[2]; r[2] = r[1]; r[1] = r[0]; r[0] = tmp; }
-                            else if (d == 3) { r[2] = r[1]; r[1] = r[0]; r[0] = tmp; }
-                            else if (d == 2) { r[1] = r[0]; r[0] = tmp; }
-                            r0 = r[0]; r1 = r[1]; r2 = r[2]; r3 = r[3];
-                        }
-                    } else {
-                        ns = (ls * 4 + 1) & 0x3F;
-                        r3 = r2; r2 = r1; r1 = r0; r0 = d - 4;
-                    }
-                    ap[apcur].state = (u8)ns;
-                    ap[apcur].rep[0] = r0; ap[apcur].rep[1] = r1; ap[apcur].rep[2] = r2; ap[apcur].rep[3] = r3;
-                    if (apcur < aplimit) {
-                        u32 rr[4] = {r0, r1, r2, r3};
-                        prefetch_fm(x + 1, end);
-                        find_match_price(x, end - x, ns, rr, t);
-                    }
-                }
-                if (apcur == aplimit) {
-                    ap_backward(apcur);
-                    i += apcur;
-                    break;
-                }
-                if (t[0].len == 1 && apcur + 1 == apend) {
-                    ap_backward(apcur);
-                    emit(OP_LIT, ap[apcur].lit, 0, 0);
-                    i += apcur;
-                    x++; i++;
-                    break;
-                }
-                if (apcur + 1 >= apend) ap[apend++].price = 0xFFFFFFFFu;
-                if (t[0].len >= good || (t[0].len > 1 && t[0].len + apcur >= aplimit)) {
-                    ap_backward(apcur);
-                    i += apcur;
-                    encode_nonlit(t[0], S.lz[x + t[0].len - 1]);
-                    slide(x, t[0].len, end);
-                    i += t[0].len;
-                    x += t[0].len;
-                    break;
-                }
-                u32 base = ap[apcur].price;
-                u32 lit_ctx = x ? S.lz[x - 1] : 0;
-                u32 cprice = literal_price(ap[apcur].state, lit_ctx, S.lz[x]);
-                if (cprice + base < ap[apcur + 1].price) {
-                    ap[apcur + 1].dist = 0;
-                    ap[apcur + 1].back_pos = (u16)apcur;
-                    ap[apcur + 1].price = cprice + base;
-                }
-                if (t[1].dist && t[1].len + base < ap[apcur + 1].price) {
-                    ap[apcur + 1].dist = 1;
-                    ap[apcur + 1].back_pos = (u16)apcur;
-                    ap[apcur + 1].price = t[1].len + base;
-                }
-                u32 len = t[0].len;
-                while (apcur + len >= apend) ap[apend++].price = 0xFFFFFFFFu;
-                while (len > 1) {
-                    if (t[len].dist && t[len].len + base < ap[apcur + len].price) {
-                        ap[apcur + len].dist = t[len].dist;
-                        ap[apcur + len].back_pos = (u16)apcur;
-                        ap[apcur + len].price = t[len].len + base;
-                    }
-                    len--;
-                }
-                apcur++;
+            if (t0.len == 1 && apcur + 1 == apend) {
+                ap_backward(apcur);
+                emit(OP_LIT, lit, 0, 0);
+                i += apcur + 1;
                 x++;
+                in_round = false;
+                continue;
             }
+            if (apcur + 1 >= apend) apend++;   // (the window already holds 0xFFFFFFFF there)
+            if (t0.len >= good || (t0.len > 1 && t0.len + apcur >= aplimit)) {
+                ap_backward(apcur);
+                encode_nonlit(t0, h.lz[x + t0.len - 1]);
+                slide_core(h, x, t0.len, end);
+                i += apcur + t0.len;
+                x += t0.len;
+                in_round = false;
+                continue;
+            }
+            const u32 base = lv_get(wp, 0);
+            const u32 cprice = literal_price_w(ns, x ? h.lz[x - 1] : 0, lit);
+            const u32 len = t0.len;
+            if (apcur + len >= apend) apend = apcur + len + 1;
+            LV_FOR(j) {
+                u32 p = wp.v[LV_AT(j)], dd = wd.v[LV_AT(j)], bb = wb.v[LV_AT(j)];
+                if (j == 1) {
+                    if (cprice + base < p) { dd = 0; bb = apcur; p = cprice + base; }
+                    if (t1d && t1p + base < p) { dd = 1; bb = apcur; p = t1p + base; }
+                } else if (j >= 2 && j <= len) {
+                    const u32 tdd = td.v[LV_AT(j)], tpp = tp.v[LV_AT(j)];
+                    if (tdd && tpp + base < p) { dd = tdd; bb = apcur; p = tpp + base; }
+                }
+                wp.v[LV_AT(j)] = p; wd.v[LV_AT(j)] = dd; wb.v[LV_AT(j)] = bb;
+            }
+            lv_shift_down(wp, 0xFFFFFFFFu);
+            lv_shift_down(wd, 0);
+            lv_shift_down(wb, 0);
+            apcur++;
+            x++;
         }
     }
 

@@ -24,6 +24,7 @@ CSC_HDF void g_or(u32 *p, u32 m) { atomicOr(p, m); }
 CSC_HDF void g_max(u32 *p, u32 v) { atomicMax(p, v); }
 CSC_HDF u32 g_ld(const u32 *p) { return __ldcg(p); }   // L2-coherent read of lane-written data
 CSC_HDF u32 ffs32(u32 m) { return (u32)__ffs((int)m); }
+CSC_HDF u32 popc32(u32 m) { return (u32)__popc(m); }
 CSC_HDF void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
 #define CSC_LANE 0u
@@ -37,6 +38,7 @@ CSC_HDF void g_or(u32 *p, u32 m) { *p |= m; }
 CSC_HDF void g_max(u32 *p, u32 v) { if (v > *p) *p = v; }
 CSC_HDF u32 g_ld(const u32 *p) { return *p; }
 CSC_HDF u32 ffs32(u32 m) { return (u32)__builtin_ffs((int)m); }
+CSC_HDF u32 popc32(u32 m) { return (u32)__builtin_popcount(m); }
 CSC_HDF void pf_l2(const void *) {}
 #endif
 
@@ -49,6 +51,56 @@ CSC_HDF u32 ld32u(const u8 *p) {   // unaligned little-endian u32 through two al
 #else
 CSC_HDF u32 ld32u(const u8 *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
 #endif
+
+// ---- lane vectors ------------------------------------------------------------------------------------
+// A few parts of the engine are written over 32 "virtual lanes" (the optimal parser's look-ahead window and
+// its price table).  On the device element j of a lane vector is a register of lane j and the helpers are
+// shuffles / ballots; the host simulation keeps the 32 elements in an array and loops, so the same source is
+// validated against the reference on the CPU.
+#if defined(__CUDA_ARCH__)
+#define CSC_VL 1
+#define LV_FOR(j) for (u32 j = CSC_LANE, j##_once = 1; j##_once; j##_once = 0)
+#define LV_AT(j) 0
+#else
+#define CSC_VL 32
+#define LV_FOR(j) for (u32 j = 0; j < 32; j++)
+#define LV_AT(j) (j)
+#endif
+struct Lv { u32 v[CSC_VL]; };
+CSC_HDF u32 lv_get(const Lv &a, u32 k) {   // element k, to every lane
+#if defined(__CUDA_ARCH__)
+    return __shfl_sync(0xFFFFFFFFu, a.v[0], k);
+#else
+    return a.v[k];
+#endif
+}
+CSC_HDF void lv_shift_down(Lv &a, u32 fill) {   // a[j] = a[j + 1], a[31] = fill
+#if defined(__CUDA_ARCH__)
+    const u32 t = __shfl_down_sync(0xFFFFFFFFu, a.v[0], 1);
+    a.v[0] = CSC_LANE == 31 ? fill : t;
+#else
+    for (u32 j = 0; j < 31; j++) a.v[j] = a.v[j + 1];
+    a.v[31] = fill;
+#endif
+}
+CSC_HDF u32 lv_ballot(const Lv &a) {   // bit j = (a[j] != 0)
+#if defined(__CUDA_ARCH__)
+    return __ballot_sync(0xFFFFFFFFu, a.v[0] != 0);
+#else
+    u32 m = 0;
+    for (u32 j = 0; j < 32; j++) m |= (a.v[j] != 0 ? 1u : 0u) << j;
+    return m;
+#endif
+}
+CSC_HDF u32 lv_sum(const Lv &a) {
+#if defined(__CUDA_ARCH__)
+    return __reduce_add_sync(0xFFFFFFFFu, a.v[0]);
+#else
+    u32 s = 0;
+    for (u32 j = 0; j < 32; j++) s += a.v[j];
+    return s;
+#endif
+}
 
 // Longest common prefix of a[0..limit) and b[0..limit): the byte-compare loop of
 // every probe in find_match (csc_mf.cpp:279,317,348,470), done 128 bytes per
