@@ -47,6 +47,10 @@ enum : u32 {
 static const u32 kBlock = 8192;          // MinBlockSize
 static const u32 kNone = 0xFFFFFFFFu;    // "no earlier occurrence" in chain arrays
 static const u32 kApLimit = 2048;        // AP_LIMIT (csc_lz.h:43)
+// -m5: the binary-tree search is replaced by a bounded per-position search: the nearest earlier positions
+// with equal 6-byte hash (kBtKA), equal 8-byte context hash (kBtKB) and equal 12-byte context hash (kBtKC),
+// merged by distance into one row of kBtRowK candidates.
+static const u32 kBtKA = 5, kBtKB = 5, kBtKC = 6, kBtRowK = 16, kBtCtxB = 8, kBtCtxC = 12, kBtHashBits = 24;
 static const u32 kMaxCand = 32;          // MF_CAND_LIMIT (csc_mf.h:33)
 
 CSC_HD u32 dlt_channels(u32 idx) {       // DltIndex[] (csc_typedef.h:35)
@@ -63,7 +67,8 @@ struct EncCfg {
     u32 lz_mode;       // 2 lazy, 3 price-optimal
     u32 flt_dlt, flt_txt, flt_exe;
     u32 csc_blocksize; // RC/BC framing block, 64 KiB default
-    u32 bt_bits, bt_size, bt_cyc;  // -m5 (bounded search)
+    u32 bt_bits, bt_size, bt_cyc;  // -m5 as configured by the reference (zeroed once mapped to the bounded search)
+    u32 bounded;       // 1: -m5 bounded multi-context search (ratio-gated, not stream-identical)
 };
 
 // ---- optimal-parser unit (role of APUnit, csc_lz.h:33-41) -------------------

@@ -135,6 +135,15 @@ inline EncCfg cfg_from_props(const CSCProps *p) {   // LZ::Init / MatchFinder::I
     c.bt_bits = (p->bt_hash_bits && p->bt_size) ? p->bt_hash_bits : 0;
     c.bt_size = c.bt_bits ? p->bt_size : 0;
     c.bt_cyc = p->bt_cyc;
+    if (c.bt_bits && !c.ht_width) {
+        // -m5 (csc_enc.cpp:84-91): the binary-tree search becomes a bounded per-position search over the
+        // kBtRowK nearest earlier positions with equal 6-byte hash (ratio-gated, not stream-identical).
+        c.ht_width = kBtRowK;
+        c.ht_bits = kBtHashBits;
+        c.bounded = 1;
+        if (c.good_len > 32) c.good_len = 32;   // the optimal parser's 32 virtual lanes
+        c.bt_bits = 0; c.bt_size = 0;
+    }
     return c;
 }
 

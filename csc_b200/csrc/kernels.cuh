@@ -367,40 +367,90 @@ k_filter_runs(u8 *lz, u8 *tmp, const GRun *__restrict__ runs, const u32 *__restr
 // (stream << key_shift) | HASH6 so that one batch-wide stable sort groups equal hashes of
 // one stream in position order.
 static const int kMfThreads = 256;
+// Each thread hashes 4 consecutive positions from three staged words (funnel shifts instead of byte loads)
+// and writes its keys / positions as 16-byte vectors; the HASH2%16 / HASH6==0 bitmaps are assembled per
+// 32 positions with shuffles (one atomic per non-empty word instead of one per set bit).
 __global__ void __launch_bounds__(kMfThreads)
 k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u32 *__restrict__ stream_bits,
           const u64 *__restrict__ stream_goff, u32 key_shift, u64 *__restrict__ keys, u32 *__restrict__ vals,
           u32 *Z2, u32 *Z6, u32 which, const u8 *__restrict__ nolz) {
-    __shared__ u8 s[kBlock + 16];
+    __shared__ __align__(16) u32 sw[kBlock / 4 + 8];
     const BlockDesc bd = blk[blockIdx.x];
-    const u8 *src = lz + bd.goff;
-    for (u32 i = threadIdx.x; i < kBlock + 16; i += kMfThreads) s[i] = i < bd.size ? src[i] : (u8)0;   // zero padding (H2)
+    {   // stage the block, zero padding behind its end (H2); blocks start 4-byte aligned in the batch buffer
+        // only when the stream offset is, so go through bytes when it is not
+        const u8 *src = lz + bd.goff;
+        u8 *sb = reinterpret_cast<u8 *>(sw);
+        if ((bd.goff & 15) == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            for (u32 i = threadIdx.x; i < kBlock / 16 + 2; i += kMfThreads) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (i * 16 < bd.size) v = s4[i];   // buffers are padded, reads beyond the block stay inside the batch
+                reinterpret_cast<uint4 *>(sw)[i] = v;
+            }
+            __syncthreads();
+            // zero the bytes behind the block end inside the last staged vector
+            for (u32 i = bd.size + threadIdx.x; i < ((bd.size + 15) & ~15u); i += kMfThreads) sb[i] = 0;
+        } else {
+            for (u32 i = threadIdx.x; i < kBlock + 32; i += kMfThreads) sb[i] = i < bd.size ? src[i] : (u8)0;
+        }
+    }
     __syncthreads();
     const u32 bits = stream_bits[bd.stream];
     const u64 bitbase = (stream_goff[bd.stream]) + bd.x;   // bitmaps are indexed by batch byte offset
-    for (u32 i = threadIdx.x; i < bd.size; i += kMfThreads) {
-        const u8 *p = s + i;
-        u32 v = p[0] | (p[1] << 8) | (p[2] << 16) | ((u32)p[3] << 24);
-        u32 v2 = p[4] | (p[5] << 8);
-        u32 h6 = bits ? ((v ^ (v2 << 13)) * 2654435761u) >> (32 - bits) : 0;
-        u32 h2 = ((v & 0xFFFF) * 65521u) & 0x3FFF;
-        vals[bd.cpos + i] = bd.x + i;
-        if (which != 6) {   // 3-byte / 2-byte chains (HASH3 csc_mf.cpp:30-33, HASH2 :23-28); excluded blocks sort apart
-            u32 h = which == 3 ? ((v & 0xFF) << 8) ^ (((v >> 8) & 0xFF) << 5) ^ ((v >> 16) & 0xFF) : h2;
-            // blocks left out of the chain carry flag bit 63 and sort into the all-ones bucket, where k_mf_rows skips them
-            keys[bd.cpos + i] = nolz[blockIdx.x] ? ((1ull << 63) | ((u64)bd.stream << key_shift) | ((1u << key_shift) - 1)) : (((u64)bd.stream << key_shift) | h);
-            continue;
+    const u64 skey = (u64)bd.stream << key_shift;
+    const bool excluded = which < 6 && nolz[blockIdx.x];
+    const bool vec = (bd.cpos & 3) == 0;
+    const u32 lane = threadIdx.x & 31;
+    for (u32 i0 = threadIdx.x * 4; i0 < ((bd.size + 127) & ~127u); i0 += kMfThreads * 4) {
+        const bool in = i0 < bd.size;
+        u32 w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        if (in) { w0 = sw[i0 >> 2]; w1 = sw[(i0 >> 2) + 1]; w2 = sw[(i0 >> 2) + 2]; w3 = sw[(i0 >> 2) + 3]; }
+        u64 k[4];
+        u32 z2 = 0, z6 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const u32 v = __funnelshift_r(w0, w1, 8 * j), u = __funnelshift_r(w1, w2, 8 * j), t = __funnelshift_r(w2, w3, 8 * j);
+            const u32 h2 = ((v & 0xFFFF) * 65521u) & 0x3FFF;
+            u32 h;
+            if (which >= 8) h = hash_ctx_words(v, u, which == 12 ? t : 0, key_shift);          // -m5 context hashes (plan.h)
+            else if (which == 6) h = bits ? ((v ^ ((u & 0xFFFF) << 13)) * 2654435761u) >> (32 - bits) : 0;   // HASH6 csc_mf.cpp:35-42
+            else if (which == 3) h = ((v & 0xFF) << 8) ^ (((v >> 8) & 0xFF) << 5) ^ ((v >> 16) & 0xFF);   // HASH3 :30-33
+            else h = h2;                                                                          // HASH2 :23-28
+            // blocks left out of a 2-/3-byte chain carry flag bit 63 and sort into the all-ones bucket, where k_mf_rows skips them
+            k[j] = excluded ? ((1ull << 63) | skey | ((1u << key_shift) - 1)) : (skey | h);
+            if (in && i0 + j < bd.size) {
+                if ((h2 & 15) == 0) z2 |= 1u << j;
+                if (bits && h == 0) z6 |= 1u << j;
+            }
         }
-        keys[bd.cpos + i] = ((u64)bd.stream << key_shift) | h6;
-        u64 bit = bitbase + i;
-        if ((h2 & 15) == 0) atomicOr(&Z2[bit >> 5], 1u << (bit & 31));
-        if (bits && h6 == 0) atomicOr(&Z6[bit >> 5], 1u << (bit & 31));
+        if (in) {
+            const u32 c = bd.cpos + i0, x = bd.x + i0;
+            if (vec && i0 + 4 <= bd.size) {
+                reinterpret_cast<ulonglong2 *>(keys + c)[0] = make_ulonglong2(k[0], k[1]);
+                reinterpret_cast<ulonglong2 *>(keys + c)[1] = make_ulonglong2(k[2], k[3]);
+                *reinterpret_cast<uint4 *>(vals + c) = make_uint4(x, x + 1, x + 2, x + 3);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (i0 + j < bd.size) { keys[c + j] = k[j]; vals[c + j] = x + j; }
+            }
+        }
+        if (which == 6) {   // 8 lanes x 4 positions = one bitmap word (when the block is 32-aligned in the bitmap)
+            u32 m2 = z2 << (4 * (lane & 7)), m6 = z6 << (4 * (lane & 7));
+#pragma unroll
+            for (int sft = 1; sft < 8; sft <<= 1) { m2 |= __shfl_xor_sync(0xFFFFFFFFu, m2, sft); m6 |= __shfl_xor_sync(0xFFFFFFFFu, m6, sft); }
+            if ((lane & 7) == 0 && in) {
+                const u64 bit = bitbase + (i0 & ~31u);
+                const u32 sh = (u32)(bit & 31);
+                if (m2) { atomicOr(&Z2[bit >> 5], m2 << sh); if (sh) atomicOr(&Z2[(bit >> 5) + 1], m2 >> (32 - sh)); }
+                if (m6) { atomicOr(&Z6[bit >> 5], m6 << sh); if (sh) atomicOr(&Z6[(bit >> 5) + 1], m6 >> (32 - sh)); }
+            }
+        }
     }
 }
 
 __global__ void k_mf_rows(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u32 n, u32 key_shift,
                           const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_K, u32 *__restrict__ P6,
-                          const u32 *__restrict__ pos_stream, u32 kforce) {
+                          const u32 *__restrict__ pos_stream, u32 kforce, u32 row_stride, u32 col0) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 k = keys[i];
@@ -408,7 +458,8 @@ __global__ void k_mf_rows(const u64 *__restrict__ keys, const u32 *__restrict__ 
     const u32 s = (u32)(k >> key_shift);
     const u32 K = kforce ? kforce : stream_K[s];
     if (!K) return;
-    u32 *row = P6 + (stream_goff[s] + vals[i]) * K;
+    // row_stride != 0: write K entries at column col0 of a wider row (-m5 merges several such lists)
+    u32 *row = P6 + (stream_goff[s] + vals[i]) * (row_stride ? row_stride : K) + col0;
     bool live = true;
     u32 j = i;
     for (u32 c = 0; c < K; c++) {
@@ -452,7 +503,56 @@ __device__ __forceinline__ u32 lcp_words(const u8 *a, const u8 *m, u32 limit) {
     return l;
 }
 
+// -m5: every 16-entry row holds three lists (nearest by 6-byte hash, 8- and 12-byte context); order it by
+// distance (position descending), drop duplicates, absent entries last.  Entries are sorted as e + 1 so that
+// kNone becomes 0; two passes of a 16-input bitonic network in registers.
+__device__ __forceinline__ void sort16_desc(u32 *v) {
+#pragma unroll
+    for (int k = 2; k <= 16; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool desc = (i & k) == 0;
+                    const u32 a = v[i], b = v[l];
+                    const bool sw = desc ? a < b : a > b;
+                    v[i] = sw ? b : a; v[l] = sw ? a : b;
+                }
+            }
+}
+__global__ void __launch_bounds__(256)
+k_mf_merge(const BlockDesc *__restrict__ blk, const u64 *__restrict__ stream_goff, u32 *__restrict__ P6) {
+    const BlockDesc bd = blk[blockIdx.x];
+    const u64 sg = stream_goff[bd.stream];
+    for (u32 i = threadIdx.x; i < bd.size; i += 256) {
+        uint4 *row = reinterpret_cast<uint4 *>(P6 + (sg + bd.x + i) * 16);
+        u32 v[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { uint4 t = row[q]; v[4 * q] = t.x + 1; v[4 * q + 1] = t.y + 1; v[4 * q + 2] = t.z + 1; v[4 * q + 3] = t.w + 1; }
+        sort16_desc(v);
+#pragma unroll
+        for (int q = 15; q > 0; q--) if (v[q] == v[q - 1]) v[q] = 0;
+        sort16_desc(v);
+#pragma unroll
+        for (int q = 0; q < 4; q++) row[q] = make_uint4(v[4 * q] - 1, v[4 * q + 1] - 1, v[4 * q + 2] - 1, v[4 * q + 3] - 1);
+    }
+}
+
 template <int K> struct RowIO;
+template <> struct RowIO<16> {
+    static __device__ __forceinline__ void load(const u32 *p, u32 *e) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) { uint4 a = reinterpret_cast<const uint4 *>(p)[q]; e[4 * q] = a.x; e[4 * q + 1] = a.y; e[4 * q + 2] = a.z; e[4 * q + 3] = a.w; }
+    }
+    static __device__ __forceinline__ void store(u16 *p, const u32 *l, const u32 *) {
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+            reinterpret_cast<uint4 *>(p)[q] = make_uint4(l[8 * q] | (l[8 * q + 1] << 16), l[8 * q + 2] | (l[8 * q + 3] << 16),
+                                                          l[8 * q + 4] | (l[8 * q + 5] << 16), l[8 * q + 6] | (l[8 * q + 7] << 16));
+    }
+};
 template <> struct RowIO<1> {
     static __device__ __forceinline__ void load(const u32 *p, u32 *e) { e[0] = p[0]; }
     static __device__ __forceinline__ void store(u16 *p, const u32 *l, const u32 *) { p[0] = (u16)l[0]; }
@@ -504,7 +604,7 @@ k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const 
                 else {
 #pragma unroll
                     for (int j = 0; j < K; j++)
-                        if (!got && pe[j] == e[k] - 1 && pl[j] >= 1) { l[k] = pl[j] - 1; got = true; }
+                        if ((K <= 8 || (j >= k - 2 && j <= k + 2)) && !got && pe[j] == e[k] - 1 && pl[j] >= 1) { l[k] = pl[j] - 1; got = true; }
                 }
             }
             if (!got) l[k] = lcp_words(base + x, base + e[k], limit);

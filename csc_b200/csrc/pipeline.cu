@@ -166,12 +166,13 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     std::vector<u32> segsize, segblk0;
     u64 total = 0, rctot = 0, evtot = 0;
     u32 cpos = 0, K = 0, key_shift = 0;
+    bool bounded = false;   // -m5: bounded multi-context search rows
     for (u32 s = 0; s < ns; s++) {
         EncJob &J = *jobs[s];
         EncCfg cfg = cfg_from_props(&J.props);
         if (J.n > cfg.wnd_size || cfg.bt_bits || !cfg.ht_width) { J.status = kErrUnsupported; return kErrUnsupported; }
-        if (s == 0) K = cfg.ht_width;
-        if (cfg.ht_width != K) return kErrUnsupported;   // one level per wave
+        if (s == 0) { K = cfg.ht_width; bounded = cfg.bounded != 0; }
+        if (cfg.ht_width != K || (cfg.bounded != 0) != bounded) return kErrUnsupported;   // one level per wave
         goff[s] = total;
         seg0[s] = (u32)segs.size();
         sbits[s] = cfg.ht_bits; sK[s] = cfg.ht_width;
@@ -358,11 +359,23 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     sort_pairs(key_shift, end_bit, ksorted, vsorted);
     T.mark(st);                                                                   // 5
     k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(),
-                                                  C.P6.as<u32>(), pos_stream, 0);
+                                                  C.P6.as<u32>(), pos_stream, bounded ? kBtKA : 0, bounded ? kBtRowK : 0, 0);
+    if (bounded) {   // two more candidate lists by 8- and 12-byte context, then one distance-ordered row
+        for (u32 which = kBtCtxB; which <= kBtCtxC; which += kBtCtxC - kBtCtxB) {
+            k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), key_shift,
+                                                   C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which, C.nolz.as<u8>());
+            sort_pairs(key_shift, end_bit, ksorted, vsorted);
+            k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
+                                                          pos_stream, which == kBtCtxB ? kBtKB : kBtKC, kBtRowK, which == kBtCtxB ? kBtKA : kBtKA + kBtKB);
+        }
+        k_mf_merge<<<nblk, 256, 0, st>>>(C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>());
+        launches += 5;
+    }
     T.mark(st);                                                                   // 6
     if (K == 1) k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else if (K == 2) k_mf_extend<2><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else if (K == 8) k_mf_extend<8><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
+    else if (K == 16) k_mf_extend<16><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else return kErrUnsupported;
     T.mark(st);                                                                   // 7
     for (u32 which = 3; which >= 2; which--) {
@@ -372,7 +385,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), shift,
                                                C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which, C.nolz.as<u8>());
         sort_pairs(shift, (int)(shift + stream_bits), ksorted, vsorted);
-        k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P, pos_stream, 1);
+        k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P, pos_stream, 1, 0, 0);
         k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
     }
     T.mark(st);                                                                   // 8

@@ -76,4 +76,17 @@ CSC_HD u32 hash2_padded(const u8 *p, u32 avail) {   // HASH2, csc_mf.cpp:23-28
     return ((b0 | (b1 << 8)) * 65521u) & 0x3FFF;
 }
 
+// -m5 bounded search: hash of an 8- or 12-byte context (three little-endian words, w2 = 0 for 8 bytes), bytes
+// beyond the sub-block end read as 0 like the reference hashes above
+CSC_HD u32 hash_ctx_words(u32 w0, u32 w1, u32 w2, u32 bits) {
+    u32 a = w0 * 0x9E3779B1u, b = w1 * 0x85EBCA77u, c = w2 * 0xC2B2AE3Du;
+    u32 h = a ^ ((b << 15) | (b >> 17)) ^ ((c << 7) | (c >> 25));
+    return (h * 0x27D4EB2Fu) >> (32 - bits);
+}
+CSC_HD u32 hash_ctx_padded(const u8 *p, u32 avail, u32 len, u32 bits) {
+    u32 w[3] = {0, 0, 0};
+    for (u32 k = 0; k < len; k++) w[k >> 2] |= (u32)(k < avail ? p[k] : 0) << (8 * (k & 3));
+    return hash_ctx_words(w[0], w[1], w[2], bits);
+}
+
 }  // namespace cscb

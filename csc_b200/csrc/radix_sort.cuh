@@ -94,36 +94,38 @@ __global__ void __launch_bounds__(kRsThreads) rs_scan_c(u32 *H, u32 n, const u32
 }
 
 // ---- stable scatter of one tile -------------------------------------------------------------------
-__global__ void __launch_bounds__(kRsThreads)
+// Register-lean on purpose (4 CTAs per SM): phase 1 keeps only the 16 ranks of a thread; the keys and
+// positions are read again in phase 3, when they still sit in L1/L2.
+__global__ void __launch_bounds__(kRsThreads, 4)
 rs_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout, u32 *__restrict__ vout,
            const RsTile *__restrict__ tiles, u32 shift, u32 mask, const u32 *__restrict__ Hs) {
     extern __shared__ __align__(16) unsigned char dyn[];
     u64 *skey = reinterpret_cast<u64 *>(dyn);                      // [kRsTile]
     u32 *sval = reinterpret_cast<u32 *>(dyn + kRsTile * 8);        // [kRsTile]
-    __shared__ u32 wcnt[kRsThreads / 32][256];
+    __shared__ u16 wcnt[kRsThreads / 32][256];
     __shared__ u32 gofs[256], lbase[256], s_w[kRsThreads / 32];
     const RsTile t = tiles[blockIdx.x];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     gofs[threadIdx.x] = Hs[t.hbase + threadIdx.x * t.nts];
+#pragma unroll
     for (u32 w = 0; w < kRsThreads / 32; w++) wcnt[w][threadIdx.x] = 0;
     __syncthreads();
     // phase 1: each warp ranks its 512 consecutive elements, 32 at a time, in order
-    u64 k[kRsPerThread];
-    u32 v[kRsPerThread], rk[kRsPerThread];
+    u32 rk[kRsPerThread];
     const u32 wbeg = warp * (kRsTile / (kRsThreads / 32));
+    const u64 *kt = kin + t.start;
+    const u32 *vt = vin + t.start;
 #pragma unroll
     for (u32 r = 0; r < kRsPerThread; r++) {
         const u32 i = wbeg + r * 32 + lane;
         const bool live = i < t.count;
-        k[r] = live ? kin[t.start + i] : 0;
-        v[r] = live ? vin[t.start + i] : 0;
-        const u32 dg = live ? ((u32)(k[r] >> shift) & mask) : 0xFFFFFFFFu;
+        const u32 dg = live ? ((u32)(kt[i] >> shift) & mask) : 0xFFFFFFFFu;
         const u32 peers = __match_any_sync(0xFFFFFFFFu, dg);
         const u32 below = __popc(peers & ((1u << lane) - 1));
         u32 base = 0;
         if (live) base = wcnt[warp][dg];
         __syncwarp();
-        if (live && below == 0) wcnt[warp][dg] = base + __popc(peers);
+        if (live && below == 0) wcnt[warp][dg] = (u16)(base + __popc(peers));
         __syncwarp();
         rk[r] = base + below;
     }
@@ -131,7 +133,7 @@ rs_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__rest
     // phase 2: per digit, offsets of the warps inside the tile and of the digit inside the tile
     u32 run = 0;
 #pragma unroll
-    for (u32 w = 0; w < kRsThreads / 32; w++) { u32 c = wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = run; run += c; }
+    for (u32 w = 0; w < kRsThreads / 32; w++) { u32 c = wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = (u16)run; run += c; }
     u32 tot;
     lbase[threadIdx.x] = block_exscan_256(run, s_w, &tot);
     __syncthreads();
@@ -140,10 +142,11 @@ rs_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__rest
     for (u32 r = 0; r < kRsPerThread; r++) {
         const u32 i = wbeg + r * 32 + lane;
         if (i < t.count) {
-            const u32 dg = (u32)(k[r] >> shift) & mask;
+            const u64 kk = kt[i];
+            const u32 dg = (u32)(kk >> shift) & mask;
             const u32 p = lbase[dg] + wcnt[warp][dg] + rk[r];
-            skey[p] = k[r];
-            sval[p] = v[r];
+            skey[p] = kk;
+            sval[p] = vt[i];
         }
     }
     __syncthreads();

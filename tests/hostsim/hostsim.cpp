@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
+#include <stdio.h>
 
 #include "../../csc_b200/csrc/host_common.h"
 #include "../../csc_b200/csrc/plan.h"
@@ -56,6 +58,45 @@ void build_mf_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, u32 bits, u3
                     while (l < avail && lz[x + l] == lz[e + l]) l++;
                     L6[(size_t)x * K + k] = (u16)l;
                     e = P6[(size_t)e * K];
+                }
+            }
+        }
+        a += seg[s];
+    }
+}
+
+
+// -m5 bounded search rows (csc_defs.h: kBt*): nearest earlier positions by 6-byte hash, 8- and 12-byte context
+// hash, merged by distance, duplicates removed -- what k_mf_hash / k_mf_rows / k_mf_merge compute on the device.
+void build_mf5_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, std::vector<u32> &P6, std::vector<u16> &L6) {
+    const u32 bits = kBtHashBits, K = kBtRowK;
+    std::vector<u32> lastA((size_t)1 << bits, kNone), lastB((size_t)1 << bits, kNone), lastC((size_t)1 << bits, kNone);
+    std::vector<u32> prevA(n, kNone), prevB(n, kNone), prevC(n, kNone);
+    P6.assign((size_t)n * K, kNone);
+    L6.assign((size_t)n * K, 0);
+    u32 a = 0;
+    for (u32 s = 0; s < seg.size(); s++) {
+        for (u32 off = 0; off < seg[s]; off += kBlock) {
+            u32 sb = seg[s] - off < kBlock ? seg[s] - off : kBlock;
+            u32 sb_end = a + off + sb;
+            for (u32 x = a + off; x < sb_end; x++) {
+                u32 avail = sb_end - x;
+                u32 hA = hash6_padded(lz + x, avail, bits), hB = hash_ctx_padded(lz + x, avail, kBtCtxB, bits),
+                    hC = hash_ctx_padded(lz + x, avail, kBtCtxC, bits);
+                prevA[x] = lastA[hA]; lastA[hA] = x;
+                prevB[x] = lastB[hB]; lastB[hB] = x;
+                prevC[x] = lastC[hC]; lastC[hC] = x;
+                std::vector<u32> c;
+                u32 q = prevA[x]; for (u32 k = 0; k < kBtKA && q != kNone; k++) { c.push_back(q); q = prevA[q]; }
+                q = prevB[x]; for (u32 k = 0; k < kBtKB && q != kNone; k++) { c.push_back(q); q = prevB[q]; }
+                q = prevC[x]; for (u32 k = 0; k < kBtKC && q != kNone; k++) { c.push_back(q); q = prevC[q]; }
+                std::sort(c.begin(), c.end(), [](u32 u, u32 v) { return u > v; });
+                c.erase(std::unique(c.begin(), c.end()), c.end());
+                for (u32 k = 0; k < K && k < c.size(); k++) {
+                    P6[(size_t)x * K + k] = c[k];
+                    u32 l = 0;
+                    while (l < avail && lz[x + l] == lz[c[k] + l]) l++;
+                    L6[(size_t)x * K + k] = (u16)l;
                 }
             }
         }
@@ -164,6 +205,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         std::vector<u16> L6;
         u32 K = cfg.ht_width;
         build_mf_cpu(lz.data(), n, seg, cfg.ht_bits, K, P6, L6, Z2, Z6);
+        if (cfg.bounded) build_mf5_cpu(lz.data(), n, seg, P6, L6);
         std::vector<u32> P3, P2;
         std::vector<u16> L3, L2;
         build_chain23_cpu(lz.data(), n, seg, seg_blk0, nolz, 3, P3, L3);

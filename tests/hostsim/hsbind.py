@@ -113,7 +113,7 @@ class Stages:
 def encode_stages(data, dict_size, level):
     """hostsim encode + its intermediate arrays."""
     a = _u8(data)
-    K = props(dict_size, level)["hash_width"]
+    K = 16 if level == 5 else props(dict_size, level)["hash_width"]   # -m5: bounded-search rows (csc_defs.h kBtRowK)
     st = Stages(a.size, max(K, 1))
     l = lib()
     l.hs_debug_dump.argtypes = [C.c_void_p] * 9

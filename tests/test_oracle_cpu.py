@@ -132,6 +132,17 @@ def test_hostsim_stream_identical_to_reference(ref, hs, name, level):
     assert same(hs.encode(d, dict_size, level), ref.encode(d, dict_size, level))
 
 
+def test_hostsim_m5_bounded_search_ratio_and_reference_decode(ref, hs):
+    """-m5 is ratio-gated (BASELINE north_star): the bounded multi-context search must decode bit-exact with
+    the reference decoder and stay within 0.5 % of libcsc -m5's size."""
+    for name, d in {"text": synth.text(400000, 11), "mixed": EC["mixed_small"][:600000],
+                    "redundant": synth.redundant(700000, base=250000, seed=12)}.items():
+        ours, theirs = hs.encode(d, d.size, 5), ref.encode(d, d.size, 5)
+        assert same(ref.decode(ours, d.size), d), name
+        assert same(hs.decode(ours, d.size), d), name
+        assert ours.size <= theirs.size * 1.005, (name, ours.size, theirs.size)
+
+
 @pytest.mark.parametrize("read_size", [8192, 100000, 300007])
 def test_hostsim_read_granularity_is_part_of_the_stream(ref, hs, read_size):
     d = synth.mixed(700000, 8)
