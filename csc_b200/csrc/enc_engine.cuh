@@ -138,7 +138,7 @@ struct Encoder {
     CSC_HDF void enc_bit_g(u32 gidx, u32 bit) { q_push(kSlotGlobal | gidx, bit); }   // p_lit / p_delta entry
     CSC_HDN void rc_block_full() { event(1); }   // cold: a 64 KiB RC block completed (csc_coder.cpp:97-104)
     CSC_HDN void flush_bits() {
-        const u32 n = bq_n;
+        const u32 n = w_uni_u32(bq_n);
         if (!n) return;
         const u32 bits = bq_bits;
         u32 v = 0;   // probability of decision `lane` (device) / scratch (host)
@@ -173,17 +173,21 @@ struct Encoder {
             const u32 bound = (rg >> 12) * p;
             if ((bits >> k) & 1) rg = bound;
             else { lo += bound; rg -= bound; }
-            if (rg < (1u << 24)) {   // RC_ShiftLow, csc_coder.cpp:89-112
+            if (w_uni(rg < (1u << 24))) {   // RC_ShiftLow, csc_coder.cpp:89-112
                 rg <<= 8;
-                if ((u32)lo < 0xFF000000u || (u32)(lo >> 32) != 0) {
+                if (w_uni((u32)lo < 0xFF000000u || (u32)(lo >> 32) != 0)) {
                     u32 t = ca;
                     const u32 carry = (u32)(lo >> 32);
                     do {
                         if (on < cap) out[on] = (u8)(t + carry); else err = kErrOverflow;
                         on++;
-                        if (++ob == bsz) { rc_n = on; rc_block_full(); ob = 0; }
+                        if (w_uni(++ob == bsz)) {   // a 64 KiB RC block completed (csc_coder.cpp:97-104)
+                            if (ev_n < S.ev_cap) S.events[ev_n] = 1; else err = kErrOverflow;
+                            ev_n++;
+                            ob = 0;
+                        }
                         t = 0xFF;
-                    } while (--cs != 0);
+                    } while (w_uni(--cs != 0));
                     ca = ((u32)lo >> 24) & 0xFF;
                 }
                 cs++;
@@ -250,7 +254,7 @@ struct Encoder {
 #if defined(__CUDA_ARCH__)
         // device fast path: the 9 decisions (flag + 8 tree nodes) are known up front, lane k owns decision k;
         // probabilities are fetched/adapted in parallel and the range recurrence is unrolled over shuffles
-        const u32 cc = c | 0x100;
+        const u32 cc = w_uni_u32(c) | 0x100;   // (the reduction also tells the compiler the warp is converged here)
         const u32 lane = CSC_LANE;
         u32 v = 0;
         if (lane < 9) {
@@ -270,7 +274,7 @@ struct Encoder {
             const bool bit = k == 0 ? false : ((cc >> (8 - k)) & 1u) != 0;
             if (bit) rg = bound;
             else { lo += bound; rg -= bound; }
-            if (rg < (1u << 24)) { rg <<= 8; low = lo; shift_low(); lo = low; }
+            if (w_uni(rg < (1u << 24))) { rg <<= 8; low = lo; shift_low(); lo = low; }
         }
         low = lo; range = rg;
         __syncwarp();
@@ -284,6 +288,7 @@ struct Encoder {
 #endif
     }
     CSC_HDN void encode_matchlen_1(u32 len) {   // csc_model.cpp:113-145
+        len = w_uni_u32(len);
         if (len < 16) {
             u16 *p;
             if (len < 8) {
@@ -296,12 +301,12 @@ struct Encoder {
                 p = M.p_matchlen_extra2;
             }
             u32 c = len | 8;
-            do { enc_bit(p[c >> 3], (c >> 2) & 1); c <<= 1; } while (c < 0x40);
+            do { enc_bit(p[c >> 3], (c >> 2) & 1); c <<= 1; } while (w_uni(c < 0x40));
         } else {
             enc_bit(M.p_matchlen_slot[0], 1);
             enc_bit(M.p_matchlen_slot[1], 1);
             u32 c = (len - 16) | 0x80;
-            do { enc_bit(M.p_matchlen_extra3[c >> 7], (c >> 6) & 1); c <<= 1; } while (c < 0x4000);
+            do { enc_bit(M.p_matchlen_extra3[c >> 7], (c >> 6) & 1); c <<= 1; } while (w_uni(c < 0x4000));
         }
     }
     CSC_HDN void encode_matchlen_2(u32 len) {   // csc_model.cpp:147-159
@@ -338,6 +343,8 @@ struct Encoder {
     }
     CSC_HDN void encode_match(u32 dist, u32 lencode) {   // csc_model.cpp:301-366
         trace(1, lencode, dist);
+        dist = w_uni_u32(dist);
+        lencode = w_uni_u32(lencode);
         enc_bit(M.p_state[state * 3 + 0], 1);
         enc_bit(M.p_state[state * 3 + 1], 1);
         encode_matchlen_2(lencode);
@@ -349,14 +356,14 @@ struct Encoder {
         u32 slot = dist_slot(dist);
         u16 *p = M.p_dist + base;
         u32 c = slot | (1u << sbits);
-        do { enc_bit(p[c >> sbits], (c >> (sbits - 1)) & 1); c <<= 1; } while (c < (1u << (sbits * 2)));
-        if (slot > 2) {
+        do { enc_bit(p[c >> sbits], (c >> (sbits - 1)) & 1); c <<= 1; } while (w_uni(c < (1u << (sbits * 2))));
+        if (w_uni(slot > 2)) {
             u32 ebits = slot - 2;
             u32 elen = dist - (1u << ebits) - 1;
-            if (ebits > 4) direct(elen >> 4, ebits - 4);
+            if (w_uni(ebits > 4)) direct(elen >> 4, ebits - 4);
             c = rev4(elen & 0x0F) | 0x10;
             p = M.p_matchdist_extra + (ebits - 1) * 16;
-            do { enc_bit(p[c >> 4], (c >> 3) & 1); c <<= 1; } while (c < 0x100);
+            do { enc_bit(p[c >> 4], (c >> 3) & 1); c <<= 1; } while (w_uni(c < 0x100));
         }
         state = (state * 4 + 1) & 0x3F;
         flush_bits();

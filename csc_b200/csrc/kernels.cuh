@@ -615,6 +615,29 @@ k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const 
     }
 }
 
+// ------------------------------------------------------------------ result packing
+// The RC / BC sub-streams of all streams of a wave are gathered into one dense buffer each, so that the
+// download is two large copies instead of two small ones per stream.  Offsets and sizes are 16-byte aligned.
+struct PackDesc { u32 rc_src, rc_dst, rc_n, bc_src, bc_dst, bc_n, pad0, pad1; };
+__global__ void __launch_bounds__(256)
+k_pack_results(const u8 *__restrict__ rc, const u8 *__restrict__ bc, u8 *__restrict__ rc_out, u8 *__restrict__ bc_out,
+               const PackDesc *__restrict__ desc) {
+    const PackDesc d = desc[blockIdx.x];
+    const u32 part = blockIdx.y, parts = gridDim.y;
+    {
+        const uint4 *s = reinterpret_cast<const uint4 *>(rc + d.rc_src);
+        uint4 *o = reinterpret_cast<uint4 *>(rc_out + d.rc_dst);
+        const u32 nv = (d.rc_n + 15) / 16;
+        for (u32 i = part * 256 + threadIdx.x; i < nv; i += parts * 256) o[i] = s[i];
+    }
+    {
+        const uint4 *s = reinterpret_cast<const uint4 *>(bc + d.bc_src);
+        uint4 *o = reinterpret_cast<uint4 *>(bc_out + d.bc_dst);
+        const u32 nv = (d.bc_n + 15) / 16;
+        for (u32 i = part * 256 + threadIdx.x; i < nv; i += parts * 256) o[i] = s[i];
+    }
+}
+
 // ------------------------------------------------------------------ fill helper
 __global__ void k_fill_u16(u16 *p, u64 n, u16 v) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -624,7 +647,10 @@ __global__ void k_fill_u16(u16 *p, u64 n, u16 v) {
 
 // ------------------------------------------------------------------ serial engines
 static const int kEncWarps = 4;
-__global__ void __launch_bounds__(kEncWarps * 32)
+#ifndef CSC_ENC_MIN_CTAS
+#define CSC_ENC_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(kEncWarps * 32, CSC_ENC_MIN_CTAS)
 k_encode(const EncStream *__restrict__ streams, u32 ns, u32 *queue, const u32 *__restrict__ p2bits) {
     __shared__ ModelSmall sm[kEncWarps];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -14,6 +14,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <thread>
+#include <atomic>
 
 #include "../../include/csc_enc.h"
 #include "../../include/csc_dec.h"
@@ -83,7 +85,7 @@ struct Ctx {
     AnalyzerTables *d_AT = nullptr;
     DictTables *d_DT = nullptr;
     u32 *d_p2bits = nullptr;
-    DevBuf lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
+    DevBuf packdesc, lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
         cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB;
     PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta;
@@ -443,15 +445,29 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         hrc += align_up(rcn[s], 16); hbc += align_up(bcn[s], 16);
     }
     if (C.h_rc.ensure(hrc + 16) || C.h_bc.ensure(hbc + 16)) return kErrCuda;
+    bool any_payload = false;
+    std::vector<PackDesc> pd(ns);
     for (u32 s = 0; s < ns; s++) {
+        PackDesc &d = pd[s];
+        memset(&d, 0, sizeof(d));
         if (jobs[s]->status < 0) continue;
         jobs[s]->ev = C.h_ev.as<u8>() + evoff[s];
         if (jobs[s]->no_payload) continue;
-        if (rcn[s]) CK(cudaMemcpyAsync(C.h_rc.as<u8>() + hrcoff[s], C.rc.as<u8>() + rcoff[s], rcn[s], cudaMemcpyDeviceToHost, st));
-        if (bcn[s]) CK(cudaMemcpyAsync(C.h_bc.as<u8>() + hbcoff[s], C.bc.as<u8>() + bcoff[s], bcn[s], cudaMemcpyDeviceToHost, st));
+        any_payload = true;
+        d.rc_src = rcoff[s]; d.rc_dst = hrcoff[s]; d.rc_n = rcn[s];
+        d.bc_src = bcoff[s]; d.bc_dst = hbcoff[s]; d.bc_n = bcn[s];
         jobs[s]->rc = C.h_rc.as<u8>() + hrcoff[s];
         jobs[s]->bc = C.h_bc.as<u8>() + hbcoff[s];
-        jobs[s]->ev = C.h_ev.as<u8>() + evoff[s];
+    }
+    if (any_payload) {   // gather on the device, then two dense downloads
+        // the sort buffers are free again: 8 bytes per position each, the sub-streams need < 1.2
+        if (hrc + 16 > C.keys0.cap || hbc + 16 > C.keys1.cap) { if (C.keys0.ensure(hrc + 16) || C.keys1.ensure(hbc + 16)) return kErrCuda; }
+        if (C.packdesc.ensure((size_t)ns * sizeof(PackDesc))) return kErrCuda;
+        CK(cudaMemcpyAsync(C.packdesc.p, pd.data(), (size_t)ns * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
+        k_pack_results<<<dim3(ns, 4), 256, 0, st>>>(C.rc.as<u8>(), C.bc.as<u8>(), C.keys0.as<u8>(), C.keys1.as<u8>(), C.packdesc.as<PackDesc>());
+        if (hrc) CK(cudaMemcpyAsync(C.h_rc.p, C.keys0.p, hrc, cudaMemcpyDeviceToHost, st));
+        if (hbc) CK(cudaMemcpyAsync(C.h_bc.p, C.keys1.p, hbc, cudaMemcpyDeviceToHost, st));
+        launches += 1;
     }
     T.mark(st);                                                                   // 10
     CK(cudaStreamSynchronize(st));
@@ -653,7 +669,7 @@ static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_
     }
     // waves: as many streams as fit the memory budget (largest first inside a wave for balance)
     const size_t budget = mem_budget();
-    const u32 K = jobs[0].props.hash_width;
+    const u32 K = cfg_from_props(&jobs[0].props).ht_width;   // (-m5: width of the bounded-search rows)
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
     int ret = 0;
@@ -673,18 +689,36 @@ static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_
         int r = encode_wave(C, wave);
         if (r < 0) { ret = r; break; }
         auto t0 = std::chrono::steady_clock::now();
-        for (EncJob *J : wave) {
-            size_t i = J - jobs.data();
-            if (device) { out_size[i] = framed_size(*J, with_props != 0); C.stats.bytes_out += out_size[i]; continue; }
-            MemSink sink{out[i], out_cap[i], 0, false};
-            if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&J->props, hdr); sink(hdr, CSC_PROP_SIZE); }
-            Framer fr(J->props.csc_blocksize);
-            frame_job(*J, fr, sink);
-            fr.eof(sink);
-            out_size[i] = sink.off;
-            if (sink.overflow) ret = kErrOverflow;
-            C.stats.bytes_out += sink.off;
+        // host framing (MemIO replay) of the wave's streams: independent per stream, so spread over host threads
+        std::atomic<size_t> next{0}, bytes_out{0};
+        std::atomic<int> overflow{0};
+        auto work = [&]() {
+            for (;;) {
+                const size_t w = next.fetch_add(1);
+                if (w >= wave.size()) break;
+                EncJob *J = wave[w];
+                size_t i = J - jobs.data();
+                if (device) { out_size[i] = framed_size(*J, with_props != 0); bytes_out += out_size[i]; continue; }
+                MemSink sink{out[i], out_cap[i], 0, false};
+                if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&J->props, hdr); sink(hdr, CSC_PROP_SIZE); }
+                Framer fr(J->props.csc_blocksize);
+                frame_job(*J, fr, sink);
+                fr.eof(sink);
+                out_size[i] = sink.off;
+                if (sink.overflow) overflow = 1;
+                bytes_out += sink.off;
+            }
+        };
+        {
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            const unsigned nt = (unsigned)std::min<size_t>(std::min(hw, 16u), (wave.size() + 7) / 8);
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+            work();
+            for (auto &th : pool) th.join();
         }
+        if (overflow) ret = kErrOverflow;
+        C.stats.bytes_out += bytes_out;
         C.stats.ms_frame += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     if (ret < 0) return ret;

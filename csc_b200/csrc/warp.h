@@ -17,6 +17,11 @@ namespace cscb {
 #define CSC_NLANES 32u
 CSC_HDF void w_sync() { __syncwarp(); }
 CSC_HDF bool w_any(bool p) { return __any_sync(0xFFFFFFFFu, p); }
+// A warp-uniform condition routed through a vote: the compiler then knows the branch cannot diverge and
+// drops the convergence-barrier bookkeeping (BSSY/BSYNC/BMOV) it would otherwise emit around it.
+CSC_HDF bool w_uni(bool p) { return __any_sync(0xFFFFFFFFu, p); }
+// same for a warp-uniform value: the result of a warp reduction lives in a uniform register
+CSC_HDF u32 w_uni_u32(u32 v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
 CSC_HDF u32 w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 CSC_HDF u32 w_min(u32 v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
 CSC_HDF u32 w_add(u32 v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -31,6 +36,8 @@ CSC_HDF void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l
 #define CSC_NLANES 1u
 CSC_HDF void w_sync() {}
 CSC_HDF bool w_any(bool p) { return p; }
+CSC_HDF bool w_uni(bool p) { return p; }
+CSC_HDF u32 w_uni_u32(u32 v) { return v; }
 CSC_HDF u32 w_ballot(bool p) { return p ? 1u : 0u; }
 CSC_HDF u32 w_min(u32 v) { return v; }
 CSC_HDF u32 w_add(u32 v) { return v; }
