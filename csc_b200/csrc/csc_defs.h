@@ -104,6 +104,7 @@ struct ModelSmall {
     u32 row_l[8];
     u32 cl[kMaxCand];     // scratch: candidate list of the current find_match (len, dist code)
     u32 cd[kMaxCand];
+    u32 dsum[64];         // coarse summary of the liveness bitmaps D6/D23: bit g set = some position of granule g may be dead
     u32 bq[32];           // pending range-coder decisions of the current packet: probability slot ids
     u16 bq_p[32];         //   ... and the probabilities fetched for them (lane-parallel)
 };

@@ -39,11 +39,19 @@ CSC_HD u32 dist_slot(u32 d) { return d < 3 ? d : 2u + ilog2(d - 1); }
 CSC_HD u32 rev4(u32 v) { return ((v & 1) << 3) | ((v & 2) << 1) | ((v & 4) >> 1) | ((v & 8) >> 3); }
 
 // read-mostly context of the match-finder hot loop; a local copy lives in registers inside the parser
+// parser control flow: routing these branches through votes (w_uni) was measured slower than leaving them to
+// the compiler (r01: -m2 text 705 vs 669 ms), unlike the coder loops where it removes the BMOV traffic
+#ifdef CSC_PARSER_UNI
+#define p_uni(x) w_uni(x)
+#else
+#define p_uni(x) (x)
+#endif
 struct MfCtx {
     const u8 *lz;
     const u32 *P6; const u16 *L6; const u32 *P3; const u16 *L3; const u32 *P2; const u16 *L2;
     const u32 *Z6;
     u32 *D6, *D23, *ht2, *ht3, *cl, *cd;
+    u32 *dsum; u32 gs;     // liveness summary (ModelSmall::dsum) and its granule shift
     u32 vld, W, K, good;
     bool tmode;
 };
@@ -59,6 +67,7 @@ struct Encoder {
     u32 bq_n, bq_bits;
     // model (csc_model.h)
     u32 state, ctx, lp_rebuild;
+    u32 gs;   // granule shift of the liveness summary
     // LZ (csc_lz.h:22)
     u32 rep[4];
     i32 err;
@@ -76,6 +85,7 @@ struct Encoder {
         MfCtx h;
         h.lz = S.lz; h.P6 = S.P6; h.L6 = S.L6; h.P3 = S.P3; h.L3 = S.L3; h.P2 = S.P2; h.L2 = S.L2; h.Z6 = S.Z6;
         h.D6 = S.D6; h.D23 = S.D23; h.ht2 = S.ht2; h.ht3 = S.ht3; h.cl = M.cl; h.cd = M.cd;
+        h.dsum = M.dsum; h.gs = gs;
         h.vld = vld; h.W = W; h.K = K; h.good = good; h.tmode = tmode;
         return h;
     }
@@ -419,8 +429,20 @@ struct Encoder {
     }
     CSC_HDF static u32 h2_of(u32 w) { return ((w & 0xFFFF) * 65521u) & 0x3FFF; }
     CSC_HDF static u32 h3_of(u32 w) { return ((w & 0xFF) << 8) ^ (((w >> 8) & 0xFF) << 5) ^ ((w >> 16) & 0xFF); }
-    CSC_HDF static bool dead6(const MfCtx &h, u32 e) { return bit_get(h.D6, e); }
-    CSC_HDF static void kill6(const MfCtx &h, u32 e) { g_or(&h.D6[e >> 5], 1u << (e & 31)); }
+    // Liveness bitmaps live in global memory (one L2 round trip per look-up, behind the row load it depends
+    // on).  Dead positions are rare, so a 2048-bit summary in shared memory answers most look-ups: a clear
+    // summary bit means no position of that granule was ever marked in D6 or D23.
+    CSC_HDF static bool maybe_dead(const MfCtx &h, u32 e) { const u32 g = e >> h.gs; return (h.dsum[g >> 5] >> (g & 31)) & 1u; }
+    CSC_HDF static void sum_mark(const MfCtx &h, u32 e) { const u32 g = e >> h.gs; s_or(&h.dsum[g >> 5], 1u << (g & 31)); }
+    CSC_HDF static void sum_mark_range(const MfCtx &h, u32 a, u32 b) {   // [a, b), warp-uniform call
+        if (a >= b) return;
+        const u32 g0 = a >> h.gs, g1 = (b - 1) >> h.gs;
+        for (u32 g = g0 + CSC_LANE; g <= g1; g += CSC_NLANES) s_or(&h.dsum[g >> 5], 1u << (g & 31));
+        w_sync();
+    }
+    CSC_HDF static bool dead6(const MfCtx &h, u32 e) { return maybe_dead(h, e) && bit_get(h.D6, e); }
+    CSC_HDF static bool dead23(const MfCtx &h, u32 e) { return maybe_dead(h, e) && bit_get(h.D23, e); }
+    CSC_HDF static void kill6(const MfCtx &h, u32 e) { sum_mark(h, e); g_or(&h.D6[e >> 5], 1u << (e & 31)); }
 
     // newest position < bound on the 6-byte chain of x that is still in the table
     // (= slot 0 of the reference bucket at the time the window ended at `bound`)
@@ -438,13 +460,13 @@ struct Encoder {
     // warm the lines the next find_match(y) will need while the coder is busy with a packet
     CSC_HDF static void prefetch_core(const MfCtx &h, u32 y, u32 sb_end) {
         if (y >= sb_end) return;
-        if (h.W) { pf_l2(h.P6 + (size_t)y * h.K); pf_l2(h.L6 + (size_t)y * h.K); }
+        if (h.W) { pf_l1(h.P6 + (size_t)y * h.K); pf_l1(h.L6 + (size_t)y * h.K); }
         if (h.tmode) {
             u32 w = word_at(h, y, sb_end);
             pf_l2(h.ht2 + h2_of(w));
             pf_l2(h.ht3 + h3_of(w));
         } else {
-            pf_l2(h.P3 + y); pf_l2(h.P2 + y);
+            pf_l1(h.P3 + y); pf_l1(h.P2 + y);
         }
     }
     CSC_HDN void prefetch_fm(u32 y, u32 sb_end) { const MfCtx h = mfctx(); prefetch_core(h, y, sb_end); }
@@ -463,7 +485,7 @@ struct Encoder {
     }
     // first entry at or behind e on a 2-/3-byte chain that the reference really inserted
     CSC_HDN static u32 alive23(const MfCtx &h, const u32 *chain, u32 e) {
-        while (e != kNone && bit_get(h.D23, e)) e = chain[e];
+        while (e != kNone && dead23(h, e)) e = chain[e];
         return e;
     }
 
@@ -498,9 +520,10 @@ struct Encoder {
         while (l < lim && a[l] == m[l]) l++;
         return l;
     }
-    static __device__ __forceinline__ u32 scan_max_excl(u32 v, u32 lane) {
+    static __device__ __forceinline__ u32 scan_max_excl(u32 v, u32 lane, bool wide) {   // wide: lanes >= 16 in use
 #pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, v, sft); if (lane >= (u32)sft) v = max(v, t); }
+        for (int sft = 1; sft < 16; sft <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, v, sft); if (lane >= (u32)sft) v = max(v, t); }
+        if (wide) { u32 t = __shfl_up_sync(0xFFFFFFFFu, v, 16); if (lane >= 16u) v = max(v, t); }
         u32 e = __shfl_up_sync(0xFFFFFFFFu, v, 1);
         return lane ? e : 0;
     }
@@ -521,7 +544,7 @@ struct Encoder {
                 const u32 *P = three ? h.P3 : h.P2;
                 u32 e = P[x];
                 L = three ? h.L3[x] : h.L2[x];
-                if (e != kNone && bit_get(h.D23, e)) { e = alive23(h, P, e); need_cmp = true; }
+                if (e != kNone && dead23(h, e)) { e = alive23(h, P, e); need_cmp = true; }
                 d = (e == kNone) ? pos : x - e;
             } else {
                 const u32 w = word_at(h, x, x + limit);
@@ -546,7 +569,10 @@ struct Encoder {
         const bool cons = is_row && cand && (u32)__popc(alivem & lt) < h.W;
         // distance filter: running maximum over the table candidates that are looked at
         const u32 dm = (is_tab || cons) ? d : 0;
-        const bool entered = dm > scan_max_excl(dm, lane);
+        // rows are ordered nearest first, so among the row lanes the running maximum is always the previous
+        // looked-at entry (smaller); only the 2-/3-byte candidates in front of them can be larger
+        const u32 d2v = __shfl_sync(FULL, d, 4), d3v = __shfl_sync(FULL, d, 5);
+        const bool entered = dm > (lane == 4 ? 0u : lane == 5 ? d2v : max(d2v, d3v));
         bool usable;
         if (is_rep) usable = cand;
         else if (lane == 4) usable = entered && d < h.vld && x > d;      // `wpos > dist` (csc_mf.cpp:306)
@@ -568,7 +594,7 @@ struct Encoder {
         }
         // length filter: running maximum of the usable lengths (starts at 1)
         const u32 lu = usable ? L : 0;
-        const u32 run = max(1u, scan_max_excl(lu, lane));
+        const u32 run = max(1u, scan_max_excl(lu, lane, h.K > 8));
         bool acc = usable && L > run && !(!is_rep && L <= 6 && d >= mf_bound(L));
         const u32 stopm = __ballot_sync(FULL, acc && L >= h.good);
         if (stopm && lane > (u32)__ffs((int)stopm) - 1) acc = false;
@@ -633,7 +659,7 @@ struct Encoder {
             bool cdead = false;
             if (CSC_LANE == 8) { ce = h.P3[x]; cl = h.L3[x]; }
             if (CSC_LANE == 9) { ce = h.P2[x]; cl = h.L2[x]; }
-            if (ce != kNone) cdead = bit_get(h.D23, ce);
+            if (ce != kNone) cdead = dead23(h, ce);
             const u32 x3 = __shfl_sync(0xFFFFFFFFu, ce, 8), x2 = __shfl_sync(0xFFFFFFFFu, ce, 9);
             l3 = __shfl_sync(0xFFFFFFFFu, cl, 8); l2 = __shfl_sync(0xFFFFFFFFu, cl, 9);
             const u32 deadm = __ballot_sync(0xFFFFFFFFu, cdead);
@@ -649,8 +675,8 @@ struct Encoder {
             u32 x3 = h.P3[x], x2 = h.P2[x];
             l3 = h.L3[x]; l2 = h.L2[x];
             known3 = known2 = true;
-            if (x3 != kNone && bit_get(h.D23, x3)) { x3 = alive23(h, h.P3, x3); known3 = false; }
-            if (x2 != kNone && bit_get(h.D23, x2)) { x2 = alive23(h, h.P2, x2); known2 = false; }
+            if (x3 != kNone && dead23(h, x3)) { x3 = alive23(h, h.P3, x3); known3 = false; }
+            if (x2 != kNone && dead23(h, x2)) { x2 = alive23(h, h.P2, x2); known2 = false; }
             e3 = (x3 == kNone) ? 0 : h.vld + x3;
             e2 = (x2 == kNone) ? 0 : h.vld + x2;
         }
@@ -816,10 +842,10 @@ struct Encoder {
 
     // SlidePos (csc_mf.cpp:134-206): positions s+1 .. s+len-1 are passed over by a match.
     CSC_HDF static void slide_core(const MfCtx &h, u32 s, u32 len, u32 sb_end) {
-        if (len <= 1) return;
+        if (p_uni(len <= 1)) return;
         u32 i0 = 1;
-        while (i0 + 128 < len) i0 += 4;
-        if (h.tmode) {
+        while (p_uni(i0 + 128 < len)) i0 += 4;
+        if (p_uni(h.tmode)) {
 #pragma unroll 1
             for (u32 i = 1 + CSC_LANE; i < len; i += CSC_NLANES) {
                 if (i < i0 && ((i - 1) & 3)) continue;   // inside the skip zone only every 4th position (:140-145)
@@ -828,17 +854,18 @@ struct Encoder {
                 g_max(&h.ht2[h2_of(w)], h.vld + q);
                 g_max(&h.ht3[h3_of(w)], h.vld + q);
             }
-        } else if (i0 > 1) {
+        } else if (p_uni(i0 > 1)) {
             // chain mode: everything is "inserted" by default; only the 3 of 4 skipped zone positions are not
+            sum_mark_range(h, s + 1, s + i0);
 #pragma unroll 1
             for (u32 i = 1 + CSC_LANE; i < i0; i += CSC_NLANES)
                 if ((i - 1) & 3) g_or(&h.D23[(s + i) >> 5], 1u << ((s + i) & 31));
         }
         w_sync();
-        if (h.W) {
-            bits_set_range(h.D6, s + 1, s + i0);          // never inserted (:145)
+        if (p_uni(h.W != 0)) {
+            if (p_uni(i0 > 1)) { sum_mark_range(h, s + 1, s + i0); bits_set_range(h.D6, s + 1, s + i0); }   // never inserted (:145)
             u32 first = s + i0;
-            if (i0 < len && bit_get_ro(h.Z6, first)) {    // h6 == lasth6 (== 0): slot 0 overwritten (:147-156)
+            if (p_uni(i0 < len && bit_get_ro(h.Z6, first))) {    // h6 == lasth6 (== 0): slot 0 overwritten (:147-156)
                 u32 e = newest_alive6(h, first, first);
                 if (e != kNone) kill6(h, e);
             }
@@ -942,13 +969,13 @@ struct Encoder {
         Cand u1;
         u1.len = 1; u1.dist = 0;
         bool have = false;
-        while (x < end) {
-            if (!have || !(u1.len == 1 || u1.len >= h.good)) {
+        while (p_uni(x < end)) {
+            if (p_uni(!have || !(u1.len == 1 || u1.len >= h.good))) {
                 // the one probe site: u1 at x, or the lazy look-ahead u2 at x + 1
                 const u32 px = have ? x + 1 : x;
                 Cand c = best_of(h, fm_core(h, px, end - px, rep[0], rep[1], rep[2], rep[3]));
-                if (!have) { u1 = c; have = true; continue; }
-                if (second_better(u1, c)) {
+                if (p_uni(!have)) { u1 = c; have = true; continue; }
+                if (p_uni(second_better(u1, c))) {
                     emit(OP_LIT, h.lz[x], 0, 0);
                     x++;
                     u1 = c;
@@ -961,7 +988,7 @@ struct Encoder {
                 }
                 continue;
             }
-            if (u1.dist == 0) emit(OP_LIT, h.lz[x], 0, 0);
+            if (p_uni(u1.dist == 0)) emit(OP_LIT, h.lz[x], 0, 0);
             else { prefetch_core(h, x + u1.len, end); encode_nonlit(u1, h.lz[x + u1.len - 1]); }
             slide_core(h, x, u1.len, end);
             x += u1.len;
@@ -1069,10 +1096,10 @@ struct Encoder {
         Cand t0;
         t0.len = 1; t0.dist = 0;
         LV_FOR(j) { wp.v[LV_AT(j)] = 0; wd.v[LV_AT(j)] = 0; wb.v[LV_AT(j)] = 0; td.v[LV_AT(j)] = 0; tp.v[LV_AT(j)] = 0; }
-        while (in_round || i < size) {
+        while (p_uni(in_round || i < size)) {
             const u32 lit = h.lz[x];
             u32 ns = state, r0 = rep[0], r1 = rep[1], r2 = rep[2], r3 = rep[3];
-            if (in_round) {   // apcur >= 1
+            if (p_uni(in_round)) {   // apcur >= 1
                 const u32 d = lv_get(wd, 0), l = lv_get(wb, 0);
                 const ApUnit pl = ap[l];
                 r0 = pl.rep[0]; r1 = pl.rep[1]; r2 = pl.rep[2]; r3 = pl.rep[3];
@@ -1099,13 +1126,13 @@ struct Encoder {
                 ap[apcur] = u;
                 w_sync();
             }
-            if (!in_round || apcur < aplimit) {
+            if (p_uni(!in_round || apcur < aplimit)) {
                 prefetch_core(h, x + 1, end);
                 const u32 n = fm_core(h, x, end - x, r0, r1, r2, r3);
                 price_table(n, ns, t0, td, tp, t1d, t1p);
             }
-            if (!in_round) {
-                if (t0.dist == 0) {
+            if (p_uni(!in_round)) {
+                if (p_uni(t0.dist == 0)) {
                     emit(OP_LIT, lit, 0, 0);
                     i++; x++;
                     continue;
@@ -1119,13 +1146,13 @@ struct Encoder {
                 u.dist = 0; u.back_pos = 0; u.next_pos = 0; u.state = (u8)ns; u.lit = (u8)lit; u.pad = 0; u.pad2 = 0;
                 ap[0] = u;
                 w_sync();
-            } else if (apcur == aplimit) {
+            } else if (p_uni(apcur == aplimit)) {
                 ap_backward(apcur);
                 i += apcur;
                 in_round = false;
                 continue;
             }
-            if (t0.len == 1 && apcur + 1 == apend) {
+            if (p_uni(t0.len == 1 && apcur + 1 == apend)) {
                 ap_backward(apcur);
                 emit(OP_LIT, lit, 0, 0);
                 i += apcur + 1;
@@ -1134,7 +1161,7 @@ struct Encoder {
                 continue;
             }
             if (apcur + 1 >= apend) apend++;   // (the window already holds 0xFFFFFFFF there)
-            if (t0.len >= good || (t0.len > 1 && t0.len + apcur >= aplimit)) {
+            if (p_uni(t0.len >= good || (t0.len > 1 && t0.len + apcur >= aplimit))) {
                 ap_backward(apcur);
                 encode_nonlit(t0, h.lz[x + t0.len - 1]);
                 slide_core(h, x, t0.len, end);
@@ -1179,6 +1206,7 @@ struct Encoder {
         emit(OP_MATCH, 64, 0, 0x100);   // end marker (:95-98), literal context untouched
     }
     CSC_HDN void skip_run(u32 a, u32 size) {   // mode 5: SlidePosFast (csc_mf.cpp:208-241)
+        { const MfCtx h = mfctx(); sum_mark_range(h, a, a + size); }
         if (W) bits_or_not_range(S.D6, S.Z2, a, a + size);
         bits_set_range(S.D23, a, a + size);   // never enters the 2-/3-byte tables
     }
@@ -1384,6 +1412,11 @@ struct Encoder {
         vld = S.cfg.vld_rge; W = S.cfg.ht_width; K = S.K; good = S.cfg.good_len;
         err = 0; tr_n = 0;
         tmode = false; want_tables = false;
+        gs = 5;
+        while (((S.n + 63) >> gs) > 2048) gs++;   // 2048 summary bits cover the stream
+        w_sync();
+        for (u32 i = CSC_LANE; i < 64; i += CSC_NLANES) M.dsum[i] = 0;
+        w_sync();
         rc_n = bc_n = ev_n = 0;
         seg_rc0 = seg_bc0 = seg_ev0 = 0;
         head = tail = 0;

@@ -31,6 +31,8 @@ CSC_HDF u32 g_ld(const u32 *p) { return __ldcg(p); }   // L2-coherent read of la
 CSC_HDF u32 ffs32(u32 m) { return (u32)__ffs((int)m); }
 CSC_HDF u32 popc32(u32 m) { return (u32)__popc(m); }
 CSC_HDF void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+CSC_HDF void pf_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }   // read-only arrays only
+CSC_HDF void s_or(u32 *p, u32 m) { atomicOr(p, m); }   // shared-memory word, lanes may collide
 #else
 #define CSC_LANE 0u
 #define CSC_NLANES 1u
@@ -47,6 +49,8 @@ CSC_HDF u32 g_ld(const u32 *p) { return *p; }
 CSC_HDF u32 ffs32(u32 m) { return (u32)__builtin_ffs((int)m); }
 CSC_HDF u32 popc32(u32 m) { return (u32)__builtin_popcount(m); }
 CSC_HDF void pf_l2(const void *) {}
+CSC_HDF void pf_l1(const void *) {}
+CSC_HDF void s_or(u32 *p, u32 m) { *p |= m; }
 #endif
 
 #if defined(__CUDA_ARCH__)
