@@ -4,8 +4,9 @@
 Metric (BASELINE.json): compress MB/s (10^6 uncompressed bytes per second).
 Workload at N=1 (BASELINE.json configs[1]): libcsc -m2 (lazy parser, 6-byte table width 8),
 -d64m, 1 GiB of synthetic English-like text on one B200, split csarc -p style into
-independent 512 KiB chunks (one libcsc stream per chunk, dict = min(64 MiB, chunk); the chunk
-size is part of the parity key and is the same for the reference arm).  At N>1
+independent 368 KiB chunks (one libcsc stream per chunk, dict = min(64 MiB, chunk); the chunk
+size is part of the parity key and is the same for the reference arm; 368 KiB makes 2850 streams
+per GiB, just under the 2960 warps the encoder kernel keeps resident on 148 SMs).  At N>1
 every rank compresses its own 1 GiB (weak scaling, contiguous chunk ranges, no collective).
 
 A "step" is one pass of the whole hot path (analyzer -> filters -> match finder -> parser ->
@@ -37,9 +38,9 @@ import numpy as np  # noqa: E402
 
 LEVEL = 2
 DICT = 64 << 20
-CHUNK = 512 << 10
+CHUNK = 368 << 10
 TOTAL = 1 << 30
-WORKLOAD = "libcsc -m2 -d64m, 1 GiB synthetic English-like text, 2048 independent 512 KiB chunks per GPU"
+WORKLOAD = "libcsc -m2 -d64m, 1 GiB synthetic English-like text, 2850 independent 368 KiB chunks per GPU"
 
 
 def gen_text(total: int, rank: int) -> np.ndarray:
