@@ -460,6 +460,29 @@ __global__ void k_mf_rows(const u64 *__restrict__ keys, const u32 *__restrict__ 
     if (!K) return;
     // row_stride != 0: write K entries at column col0 of a wider row (-m5 merges several such lists)
     u32 *row = P6 + (stream_goff[s] + vals[i]) * (row_stride ? row_stride : K) + col0;
+    if (kforce != 1 && K <= 8) {
+        // 6-byte rows (no flagged entries): the K predecessors in the sorted array are read with independent
+        // loads, the row is the prefix of them that still has this element's (stream, hash) key
+        u64 kk[8];
+        u32 vv[8];
+#pragma unroll
+        for (u32 c = 0; c < 8; c++) {
+            const bool in = c < K && i > c;
+            kk[c] = in ? keys[i - 1 - c] : ~k;
+            vv[c] = in ? vals[i - 1 - c] : kNone;
+        }
+        bool ok = true;
+#pragma unroll
+        for (u32 c = 0; c < 8; c++) { ok = ok && kk[c] == k; vv[c] = ok ? vv[c] : kNone; }
+        if (K == 8 && !row_stride) {
+            reinterpret_cast<uint4 *>(row)[0] = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+            reinterpret_cast<uint4 *>(row)[1] = make_uint4(vv[4], vv[5], vv[6], vv[7]);
+        } else {
+#pragma unroll
+            for (u32 c = 0; c < 8; c++) if (c < K) row[c] = vv[c];
+        }
+        return;
+    }
     bool live = true;
     u32 j = i;
     for (u32 c = 0; c < K; c++) {
@@ -572,7 +595,7 @@ template <> struct RowIO<8> {
 };
 
 template <int K>
-__global__ void __launch_bounds__(kMfThreads)
+__global__ void __launch_bounds__(kMfThreads, K == 8 ? 4 : 1)
 k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u64 *__restrict__ stream_goff,
             const u32 *__restrict__ P6, u16 *__restrict__ L6) {
     const BlockDesc bd = blk[blockIdx.x];
@@ -604,7 +627,8 @@ k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const 
                 else {
 #pragma unroll
                     for (int j = 0; j < K; j++)
-                        if ((K <= 8 || (j >= k - 2 && j <= k + 2)) && !got && pe[j] == e[k] - 1 && pl[j] >= 1) { l[k] = pl[j] - 1; got = true; }
+                        // a new or a dropped candidate shifts the ranks by one or two: look only there
+                        if (j != k && j >= k - 2 && j <= k + 2 && !got && pe[j] == e[k] - 1 && pl[j] >= 1) { l[k] = pl[j] - 1; got = true; }
                 }
             }
             if (!got) l[k] = lcp_words(base + x, base + e[k], limit);
