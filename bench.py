@@ -259,6 +259,15 @@ def main():
     algo = {"ms_analyze": 1.0, "ms_filters": 2.0, "ms_mf_hash": 1.0 + 12.0, "ms_mf_sort": 3 * 2 * 12.0, "ms_mf_rows": 12.0 + 4.0 * W,
             "ms_mf_extend": 1.0 + 4.0 * W + 2.0 * W, "ms_mf_chains": 2 * (1.0 + 12.0 + 2 * 2 * 12.0 + 12.0 + 4.0 + 1.0 + 4.0 + 2.0),
             "ms_encode": 1.0 + ratio + 6.0 * (W + 2)}
+    # DRAM bytes of one k_encode launch from the committed ncu capture of this very configuration (else null)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_encode_traffic.json")))
+        w = tj["workload"]
+        if (w["level"], w["chunk"], w["bytes_per_gpu"]) == (LEVEL, CHUNK, total):
+            traffic, traffic_src = int(tj["dram_bytes_per_launch"]), "profiles/r01_k_encode_traffic.json (ncu, one launch)"
+    except Exception:
+        pass
     for k, bpb in algo.items():
         ms = kern.get(k, 0.0) / args.steps
         if ms > 0:
@@ -279,7 +288,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_encode (parser + range coder, one stream per warp; latency-bound)",
                      "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 6),
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": int(total * (1.0 + ratio + 6.0 * (W + 2))), "peak_source": peak_src,
                      "algorithmic_bytes": "(1 + ratio + 6*(W+2)) B per input byte: window byte, coded bytes, W+2 candidates of 6 B (SURVEY 8d)"},
         "kernels": per_kernel,
         "clocks": sampler.summary(),
