@@ -9,7 +9,7 @@
 // (csc_model.cpp) and the range / raw-bit coder (csc_coder.{h,cpp}).
 //
 // It is NOT a translation of the reference's data structures: the 6-byte hash
-// table does not exist here.  The parallel kernels (mf_kernels.cu) produce, for
+// table does not exist here.  The parallel kernels (kernels.cuh: k_mf_*) produce, for
 // every position p, the K nearest earlier positions with the same 6-byte hash
 // (row P6[p]) and their forward match lengths (L6[p]).  The reference bucket
 // at any moment equals "the first W entries along that chain that are still
@@ -17,7 +17,8 @@
 // match rule (csc_mf.cpp:145), sampled out by SlidePosFast (csc_mf.cpp:215),
 // or overwritten by the run de-duplication rule (csc_mf.cpp:147-157).  The
 // engine keeps one bit per position (D6) for that and walks rows.
-// The tiny 2-/3-byte single-slot tables are emulated directly (320 KiB).
+// The 2-/3-byte single-slot tables are depth-1 chains (P3/L3, P2/L2) with their own liveness bitmap (D23);
+// a stream whose statically excluded blocks get LZ-parsed after all falls back to the real tables (tmode).
 #pragma once
 #include "csc_defs.h"
 #include "warp.h"

@@ -27,7 +27,7 @@ struct Sink {
     void operator()(const u8 *p, u32 n) { v->insert(v->end(), p, p + n); }
 };
 
-// Brute-force "last-K prior occurrences per position" (what mf_kernels.cu computes with a
+// Brute-force "last-K prior occurrences per position" (what kernels.cuh: k_mf_hash / k_mf_rows / k_mf_extend compute with a
 // sort + segmented scan) through an actual last-occurrence table.
 void build_mf_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, u32 bits, u32 K, std::vector<u32> &P6,
                   std::vector<u16> &L6, std::vector<u32> &Z2, std::vector<u32> &Z6) {
