@@ -117,7 +117,7 @@ def run_reference_arm(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built and /root/reference absent"}))
         return 0
     cores = os.cpu_count() or 1
-    sample = min(TOTAL, max(8, cores) * 4 * CHUNK)   # bounded sample of the same workload
+    sample = min(TOTAL, max(8, cores) * 32 * CHUNK)   # bounded sample of the same workload: 32 chunks per host thread
     data = gen_text(sample, 0)
     chunks = [data[o:o + CHUNK] for o in range(0, sample, CHUNK)]
     for _ in range(args.warmup):
@@ -298,8 +298,9 @@ def main():
         from oracle import refbind
         if refbind.available():
             cores = os.cpu_count() or 1
-            sample = min(total, max(8, cores) * 2 * CHUNK)
+            sample = min(total, max(8, cores) * 32 * CHUNK)   # 32 chunks per host thread, after one warm-up pass
             chunks = [data[o:o + CHUNK] for o in range(0, sample, CHUNK)]
+            cpu_reference_run(chunks[:cores], cores)
             dt, _ = cpu_reference_run(chunks, cores)
             line["cpu_baseline"] = {"value": round(sample / dt / 1e6, 2), "unit": "MB/s", "cores": cores, "kind": "reference",
                                     "sample": f"first {sample >> 20} MiB of the workload ({len(chunks)} chunks), unmodified libcsc "
