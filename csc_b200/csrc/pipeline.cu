@@ -817,6 +817,7 @@ int CSCEnc_Encode(CSCEncHandle p, ISeqInStream *is, ICompressProgress *progress)
     EncHandle *h = (EncHandle *)p;
     Ctx &C = g_ctx;
     if (ctx_init(C)) return kErrCuda;
+    if (!h || !is) return kErrCuda;   // callers such as libcsc/csc.cpp do not check CSCEnc_Create's result
     // pull the whole input, one Read() of raw_blocksize per flush segment (csc_enc.cpp:169-176)
     std::vector<u8> data;
     EncJob J;
@@ -853,6 +854,7 @@ int CSCEnc_Encode(CSCEncHandle p, ISeqInStream *is, ICompressProgress *progress)
 
 int CSCEnc_Encode_Flush(CSCEncHandle p) {
     EncHandle *h = (EncHandle *)p;
+    if (!h) return kErrCuda;
     CbSink sink{h->os, false, 0};
     h->fr->eof(sink);
     return sink.fail ? WRITE_ERROR : 0;

@@ -23,6 +23,22 @@ def build(verbose: bool = False) -> None:
         raise RuntimeError("oracle/_ref build failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stdout)
+    # the reference's own command-line tool, once on the reference library and once relinked against the
+    # product (needs csc_b200/csrc/libcsc_b200.so; skipped quietly when the product is not built yet)
+    if os.path.exists(os.path.join(_HERE, "..", "csc_b200", "csrc", "libcsc_b200.so")):
+        r = subprocess.run(["make", "-C", _HERE, "cli"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle/_ref cli build failed:\n" + r.stdout + r.stderr)
+
+
+def cli(which: str) -> str:
+    """Path of oracle/_ref/csc_cli_ref or csc_cli_b200 (libcsc/csc.cpp, unmodified), built on demand."""
+    path = os.path.join(_REF_DIR, "csc_cli_" + which)
+    if not os.path.exists(path):
+        build()
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    return path
 
 
 def _load(name: str):

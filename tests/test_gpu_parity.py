@@ -185,3 +185,25 @@ def test_empty_and_tiny_inputs(gpu_lib, ref):
         for level in (1, 3):
             assert same(gpu_lib.encode_chunks([d], 1 << 30, level)[0], ref.encode(d, d.size, level))
             assert same(gpu_lib.encode_stream(d, max(d.size, 1), level), ref.encode(d, max(d.size, 1), level))
+
+
+def test_reference_cli_relinked_against_the_product(gpu_lib, ref, tmp_path):
+    """The reference's own tool (libcsc/csc.cpp, unmodified source) linked with libcsc_b200.so instead of
+    libcsc.a: its archives are byte-identical to the reference tool's, and each tool unpacks the other's."""
+    import subprocess
+    try:
+        exe, exe_ref = ref.cli("b200"), ref.cli("ref")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/csc_cli_* not built")
+    d = synth.mixed(700000, 23)
+    src = tmp_path / "in.bin"
+    d.tofile(src)
+    for level in (1, 3):
+        a, b = tmp_path / f"gpu{level}.csc", tmp_path / f"ref{level}.csc"
+        assert subprocess.run([exe, "c", f"-m{level}", str(src), str(a)], capture_output=True).returncode == 0
+        assert subprocess.run([exe_ref, "c", f"-m{level}", str(src), str(b)], capture_output=True).returncode == 0
+        assert same(np.fromfile(a, dtype=np.uint8), np.fromfile(b, dtype=np.uint8)), level
+        back_gpu, back_ref = tmp_path / f"back_gpu{level}.bin", tmp_path / f"back_ref{level}.bin"
+        assert subprocess.run([exe, "d", str(b), str(back_gpu)], capture_output=True).returncode == 0
+        assert subprocess.run([exe_ref, "d", str(a), str(back_ref)], capture_output=True).returncode == 0
+        assert same(np.fromfile(back_gpu, dtype=np.uint8), d) and same(np.fromfile(back_ref, dtype=np.uint8), d)

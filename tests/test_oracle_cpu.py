@@ -228,3 +228,29 @@ def test_restatement_matches_golden():
         d = EC[rec["name"]]
         out = restate.encode(d, max(d.size, 32768), rec["level"])
         assert out.size == rec["size"] and hashlib.sha256(out.tobytes()).hexdigest() == rec["sha256"], rec
+
+
+# ---------------------------------------------------------------- drop-in boundary
+def test_reference_cli_builds_against_product_headers_and_library(ref, tmp_path):
+    """the reference's own tool (libcsc/csc.cpp, unmodified) compiles against
+    include/ and links with libcsc_b200.so.  Without a CUDA device the relinked tool must fail loudly and
+    produce nothing but the caller-written 10-byte header: there is no CPU fallback."""
+    import subprocess
+    try:
+        exe, exe_ref = ref.cli("b200"), ref.cli("ref")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/csc_cli_* not built and /root/reference absent")
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libcsc_b200.so" in ldd and "not found" not in ldd
+    d = synth.mixed(300000, 21)
+    src, out, out_ref = tmp_path / "in.bin", tmp_path / "out.csc", tmp_path / "ref.csc"
+    d.tofile(src)
+    r = subprocess.run([exe_ref, "c", "-m1", str(src), str(out_ref)], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert same(np.fromfile(out_ref, dtype=np.uint8), ref.encode(d, d.size, 1))   # the tool == the library oracle
+    import csc_b200
+    csc_b200.lib()
+    if not csc_b200.available():
+        r = subprocess.run([exe, "c", "-m1", str(src), str(out)], capture_output=True, text=True)
+        assert "no CPU fallback" in r.stderr
+        assert os.path.getsize(out) == 10
