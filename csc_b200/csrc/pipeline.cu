@@ -816,8 +816,16 @@ struct CbSink {
 int CSCEnc_Encode(CSCEncHandle p, ISeqInStream *is, ICompressProgress *progress) {
     EncHandle *h = (EncHandle *)p;
     Ctx &C = g_ctx;
-    if (ctx_init(C)) return kErrCuda;
-    if (!h || !is) return kErrCuda;   // callers such as libcsc/csc.cpp do not check CSCEnc_Create's result
+    if (ctx_init(C) || !h) {
+        // Callers such as libcsc/csc.cpp do not check CSCEnc_Create's result, and csarc feeds the stream from
+        // a producer thread that blocks until its queue is read: consume the input before failing.
+        if (is) {
+            std::vector<u8> sink(1 << 20);
+            for (;;) { size_t got = sink.size(); if (is->Read(is, sink.data(), &got) < 0 || !got) break; }
+        }
+        return kErrCuda;
+    }
+    if (!is) return kErrCuda;
     // pull the whole input, one Read() of raw_blocksize per flush segment (csc_enc.cpp:169-176)
     std::vector<u8> data;
     EncJob J;

@@ -33,7 +33,7 @@ def build(verbose: bool = False) -> None:
 
 def cli(which: str) -> str:
     """Path of oracle/_ref/csc_cli_ref or csc_cli_b200 (libcsc/csc.cpp, unmodified), built on demand."""
-    path = os.path.join(_REF_DIR, "csc_cli_" + which)
+    path = os.path.join(_REF_DIR, which if which.startswith("csarc") else "csc_cli_" + which)
     if not os.path.exists(path):
         build()
     if not os.path.exists(path):

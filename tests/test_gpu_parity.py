@@ -207,3 +207,4 @@ def test_reference_cli_relinked_against_the_product(gpu_lib, ref, tmp_path):
         assert subprocess.run([exe, "d", str(b), str(back_gpu)], capture_output=True).returncode == 0
         assert subprocess.run([exe_ref, "d", str(a), str(back_ref)], capture_output=True).returncode == 0
         assert same(np.fromfile(back_gpu, dtype=np.uint8), d) and same(np.fromfile(back_ref, dtype=np.uint8), d)
+

@@ -254,3 +254,32 @@ def test_reference_cli_builds_against_product_headers_and_library(ref, tmp_path)
         r = subprocess.run([exe, "c", "-m1", str(src), str(out)], capture_output=True, text=True)
         assert "no CPU fallback" in r.stderr
         assert os.path.getsize(out) == 10
+
+
+def test_reference_archiver_links_against_the_product(ref, tmp_path):
+    """csarc (archiver/*.cpp, unmodified) builds against include/ + libcsc_b200.so.  The reference build of the
+    same sources round-trips here; without a CUDA device the relinked one reports the missing device and
+    terminates (its producer threads are drained) instead of hanging."""
+    import subprocess
+    try:
+        exe, exe_ref = ref.cli("csarc_b200"), ref.cli("csarc_ref")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/csarc_* not built and /root/reference absent")
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libcsc_b200.so" in ldd and "not found" not in ldd
+    files = {"a.txt": synth.text(200000, 31), "b.exe": synth.exe(150000, 32)}
+    for n, d in files.items():
+        d.tofile(tmp_path / n)
+    names = list(files)
+    r = subprocess.run([exe_ref, "a", "-m2", "-t2", "-f", "ref.csa"] + names, cwd=tmp_path, capture_output=True, timeout=120)
+    assert r.returncode == 0
+    os.mkdir(tmp_path / "out")
+    r = subprocess.run([exe_ref, "x", "-t2", "-o", "out/", "ref.csa"], cwd=tmp_path, capture_output=True, timeout=120)
+    assert r.returncode == 0
+    for n, d in files.items():
+        assert same(np.fromfile(tmp_path / "out" / n, dtype=np.uint8), d)
+    import csc_b200
+    csc_b200.lib()
+    if not csc_b200.available():
+        r = subprocess.run([exe, "a", "-m2", "-t2", "-f", "gpu.csa"] + names, cwd=tmp_path, capture_output=True, text=True, timeout=60)
+        assert "no CPU fallback" in r.stderr
