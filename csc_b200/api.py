@@ -35,7 +35,7 @@ class Stats(C.Structure):
                                           "ms_mf_extend", "ms_encode", "ms_d2h", "ms_frame", "ms_decode", "ms_unfilter",
                                           "ms_total_gpu", "ms_mf_chains")] + \
                [(k, C.c_uint64) for k in ("bytes_in", "bytes_out", "mf_positions")] + \
-               [(k, C.c_uint32) for k in ("kernel_launches", "streams", "waves")]
+               [(k, C.c_uint32) for k in ("kernel_launches", "streams", "waves", "replans")]
 
 
 READ_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t))
@@ -187,6 +187,24 @@ def decode_chunks(streams, raw_sizes):
     sizes = decode_chunks_raw([c.ctypes.data for c in ins], [c.size for c in ins], [o.ctypes.data for o in outs],
                               [int(s) for s in raw_sizes])
     return [o[:s] for o, s in zip(outs, sizes)]
+
+
+def encode_traced(data, dict_size: int, level: int):
+    """Debug (tests): one chunk through CSCB200_EncodeChunks plus the engine's trace as (kind, a, b) triples --
+    packets 0..3 and, per find_match call, (4, position, n) followed by n x (5, len, dist code)."""
+    a = _u8(data)
+    l = lib()
+    l.CSCB200_DebugTrace.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    tr = np.zeros(((a.size + 1024) * 12, 3), dtype=np.uint32)
+    n = C.c_size_t(0)
+    l.CSCB200_DebugTrace(tr.ctypes.data, tr.shape[0], C.byref(n))
+    try:
+        out = encode_chunks([a], dict_size, level)[0]
+    finally:
+        l.CSCB200_DebugTrace(None, 0, None)
+    if n.value > tr.shape[0]:
+        raise RuntimeError("trace buffer too small")
+    return out, tr[: n.value]
 
 
 def encode_stream(data, dict_size: int, level: int, read_size: int = 0, flt_mask: int = 7, with_props: bool = True):

@@ -144,6 +144,8 @@ struct EncStream {
     const u32 *P2; const u16 *L2;
     u32 *D23;
     const u8 *blk_nolz;    // [nblk] block left out of the 2-/3-byte chains (statically typed BAD/ENTROPY/DLT)
+    const u8 *flip;        // [nblk] outcome of the duplicate-block test the static plan assumed (plan.h); may be null
+    u32 *replan;           // [2] out: block and observed outcome when the assumption failed (status kErrReplan)
     u32 *ht2;              // [16 Ki] 2-byte table, emulated directly (csc_mf.h:17-18)
     u32 *ht3;              // [64 Ki] 3-byte table
     // model in global memory
@@ -177,5 +179,6 @@ struct DecStream {
 };
 
 static const i32 kErrDecode = -96, kErrWrite = -97, kErrRead = -98, kErrOverflow = -90, kErrUnsupported = -91;
+static const i32 kErrReplan = -93;   // internal: the static plan of a wrapped stream has to be redone (never leaves the library)
 
 }  // namespace cscb

@@ -22,6 +22,7 @@
 #pragma once
 #include "csc_defs.h"
 #include "warp.h"
+#include "plan.h"
 
 namespace cscb {
 
@@ -54,6 +55,7 @@ struct MfCtx {
     u32 *D6, *D23, *ht2, *ht3, *cl, *cd;
     u32 *dsum; u32 gs;     // liveness summary (ModelSmall::dsum) and its granule shift
     u32 vld, W, K, good;
+    u32 wnd;               // window size when the stream wraps, else 0 (no ring arithmetic on the hot path)
     bool tmode;
 };
 
@@ -75,6 +77,7 @@ struct Encoder {
     u32 tr_n;
     u32 vld, W, K, good;
     bool tmode, want_tables;   // 2-/3-byte tables: false = chains + liveness bits, true = real tables (after a flip)
+    bool wrap;                 // the stream is longer than its window: ring semantics apply (csc_lz.cpp:91-92)
     // parser -> coder command ring (two-warp pipeline of the lazy modes); null = execute in place
     uint4 *ring;
     volatile u32 *vhead, *vtail;
@@ -88,6 +91,7 @@ struct Encoder {
         h.D6 = S.D6; h.D23 = S.D23; h.ht2 = S.ht2; h.ht3 = S.ht3; h.cl = M.cl; h.cd = M.cd;
         h.dsum = M.dsum; h.gs = gs;
         h.vld = vld; h.W = W; h.K = K; h.good = good; h.tmode = tmode;
+        h.wnd = wrap ? S.cfg.wnd_size : 0;
         return h;
     }
 
@@ -111,6 +115,13 @@ struct Encoder {
             if (tr_n < S.trace_cap) { S.trace[tr_n * 3] = k; S.trace[tr_n * 3 + 1] = a; S.trace[tr_n * 3 + 2] = b; }
             tr_n++;
         }
+    }
+
+    // debug: the candidate list of one find_match call as (4, position, n) + n x (5, len, dist code) records,
+    // the same records oracle/ref_mftrace.cpp takes from the reference MatchFinder
+    CSC_HDN void trace_cands(u32 x, u32 n) {
+        trace(4, x, n);
+        for (u32 i = 0; i < n; i++) trace(5, M.cl[i], M.cd[i]);
     }
 
     // ------------------------------------------------------------- range coder
@@ -490,6 +501,13 @@ struct Encoder {
         return e;
     }
 
+    // compare limit of a candidate at distance d: the sub-block end on our side, the window end on its side
+    CSC_HDF static u32 climit_of(const MfCtx &h, u32 x, u32 d, u32 limit) {
+        if (!h.wnd) return limit;
+        const u32 c = h.wnd - (x - d) % h.wnd;
+        return c < limit ? c : limit;
+    }
+
     // one table / rep probe once the candidate is known to be in range: reference semantics of
     // "pre-check byte at minlen, full compare, update minlen, bound filter, record, good_len stop"
     // returns true when every further probe is disabled (dist poisoned)
@@ -566,6 +584,7 @@ struct Encoder {
         const u32 validrow = __ballot_sync(FULL, is_row && d != 0) >> 8;
         const u32 alivem = __ballot_sync(FULL, is_row && cand);
         if (limit <= 1) return 0;
+        const u32 wpos = h.wnd ? x % h.wnd : x;   // window offset of x (csc_mf.cpp: wpos)
         const u32 lt = (1u << lane) - 1;
         const bool cons = is_row && cand && (u32)__popc(alivem & lt) < h.W;
         // distance filter: running maximum over the table candidates that are looked at
@@ -576,21 +595,24 @@ struct Encoder {
         const bool entered = dm > (lane == 4 ? 0u : lane == 5 ? d2v : max(d2v, d3v));
         bool usable;
         if (is_rep) usable = cand;
-        else if (lane == 4) usable = entered && d < h.vld && x > d;      // `wpos > dist` (csc_mf.cpp:306)
+        else if (lane == 4) usable = entered && d < h.vld && wpos != d && x >= d;   // `wpos > dist` (csc_mf.cpp:306): offset 0 of the lap is lost
         else if (lane == 5) usable = entered && d < h.vld && x >= d;
         else usable = cons && entered && d < h.vld;
+        // a compare never runs past the window end on the candidate's side (climit, csc_mf.cpp:268,307,338,460)
+        u32 lim = limit;
+        if (h.wnd && usable) { lim = min(limit, h.wnd - (x - d) % h.wnd); L = min(L, lim); }
         // lengths that are not precomputed: rep distances, table-mode / re-walked table candidates
         if (need_cmp && usable) {
             const u8 *m = cur - d;
             L = 0;
-            if (m[1] == cur[1]) L = lane_lcp(cur, m, limit < 64 ? limit : 64);
+            if (m[1] == cur[1]) L = lane_lcp(cur, m, lim < 64 ? lim : 64);
         }
-        u32 more = __ballot_sync(FULL, need_cmp && usable && L == 64 && limit > 64);
+        u32 more = __ballot_sync(FULL, need_cmp && usable && L == 64 && lim > 64);
         while (more) {   // long matches are finished by the whole warp
             const u32 src = (u32)__ffs((int)more) - 1;
             more &= more - 1;
-            const u32 dd = __shfl_sync(FULL, d, src);
-            const u32 ext = 64 + lcp_bytes(cur + 64, cur - dd + 64, limit - 64);
+            const u32 dd = __shfl_sync(FULL, d, src), ll = __shfl_sync(FULL, lim, src);
+            const u32 ext = 64 + lcp_bytes(cur + 64, cur - dd + 64, ll - 64);
             if (lane == src) L = ext;
         }
         // length filter: running maximum of the usable lengths (starts at 1)
@@ -624,54 +646,29 @@ struct Encoder {
                 u32 dd = x - e;
                 if (dd <= dist) continue;
                 dist = dd;
-                if (dist >= h.vld || minlen >= limit) continue;
-                if (probe(h, cur, dd, limit, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
+                if (dist >= h.vld) continue;
+                const u32 cl = climit_of(h, x, dd, limit);
+                if (minlen >= cl) continue;
+                if (probe(h, cur, dd, cl, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
             }
         }
         return cnt;
     }
 #endif
 
-    // find_match (csc_mf.cpp:243-495): candidate list (M.cl / M.cd) in reference probe order.
+    // find_match (csc_mf.cpp:243-495): candidate list (M.cl / M.cd) in reference probe order.  On the device
+    // this is fm_lanes; the scalar statement below is what the host simulation runs against the oracle.
     CSC_HDF static u32 fm_core(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
 #if defined(__CUDA_ARCH__)
         return fm_lanes(h, x, limit, r0, r1, r2, r3);
-#endif
+#else
         const u8 *cur = h.lz + x;
         const u32 pos = h.vld + x;
         const u32 sb_end = x + limit;
+        const u32 wpos = h.wnd ? x % h.wnd : x;
         u32 cnt = 0, minlen = 1, dist = 0;
-        // ---- issue every independent load first: candidate row, 2-/3-byte candidates, first probe bytes
-        // candidate row: entry k, its length and its liveness bit are fetched by lane k; in chain mode
-        // lanes 8 / 9 fetch the 3-byte / 2-byte chain candidates the same way
-        u32 re = kNone, rl = 0;
-        bool rdead = false;
         u32 e2 = 0, e3 = 0, l2 = 0, l3 = 0, h2 = 0, h3 = 0;   // table entries as reference pos_ values (0 = empty)
         bool known2 = false, known3 = false;                    // match length already known (chain mode)
-#if defined(__CUDA_ARCH__)
-        if (CSC_LANE < h.K) {
-            const size_t at = (size_t)x * h.K + CSC_LANE;
-            re = h.P6[at];
-            rl = h.L6[at];
-            if (re != kNone) rdead = dead6(h, re);
-        }
-        if (!h.tmode) {
-            u32 ce = kNone, cl = 0;
-            bool cdead = false;
-            if (CSC_LANE == 8) { ce = h.P3[x]; cl = h.L3[x]; }
-            if (CSC_LANE == 9) { ce = h.P2[x]; cl = h.L2[x]; }
-            if (ce != kNone) cdead = dead23(h, ce);
-            const u32 x3 = __shfl_sync(0xFFFFFFFFu, ce, 8), x2 = __shfl_sync(0xFFFFFFFFu, ce, 9);
-            l3 = __shfl_sync(0xFFFFFFFFu, cl, 8); l2 = __shfl_sync(0xFFFFFFFFu, cl, 9);
-            const u32 deadm = __ballot_sync(0xFFFFFFFFu, cdead);
-            known3 = known2 = true;
-            e3 = x3; e2 = x2;
-            if (deadm & 0x100) { e3 = alive23(h, h.P3, x3); known3 = false; }
-            if (deadm & 0x200) { e2 = alive23(h, h.P2, x2); known2 = false; }
-            e3 = (e3 == kNone) ? 0 : h.vld + e3;
-            e2 = (e2 == kNone) ? 0 : h.vld + e2;
-        }
-#else
         if (!h.tmode) {
             u32 x3 = h.P3[x], x2 = h.P2[x];
             l3 = h.L3[x]; l2 = h.L2[x];
@@ -680,110 +677,51 @@ struct Encoder {
             if (x2 != kNone && dead23(h, x2)) { x2 = alive23(h, h.P2, x2); known2 = false; }
             e3 = (x3 == kNone) ? 0 : h.vld + x3;
             e2 = (x2 == kNone) ? 0 : h.vld + x2;
-        }
-#endif
-        const bool deep = limit > 1;
-        u32 c1;
-        if (h.tmode) {
+        } else {
             const u32 w0 = word_at(h, x, sb_end);
             h2 = h2_of(w0); h3 = h3_of(w0);
             e2 = g_ld(&h.ht2[h2]); e3 = g_ld(&h.ht3[h3]);
-            c1 = (w0 >> 8) & 0xFF;
-        } else {
-            c1 = deep ? cur[1] : 0;
-        }
-        const bool v0 = deep && r0 < h.vld, v1 = deep && r1 < h.vld, v2 = deep && r2 < h.vld, v3 = deep && r3 < h.vld;
-        const u32 b0 = v0 ? (cur - r0)[1] : 0x100, b1 = v1 ? (cur - r1)[1] : 0x100;
-        const u32 b2 = v2 ? (cur - r2)[1] : 0x100, b3 = v3 ? (cur - r3)[1] : 0x100;
-        const u32 d2 = pos - e2, d3 = pos - e3;
-        const bool q2 = deep && d2 < h.vld && x > d2, q3 = deep && d3 < h.vld && x >= d3;
-        u32 t2 = 0x100, t3 = 0x100;
-        if (h.tmode) {
-            t2 = q2 ? (cur - d2)[1] : 0x100; t3 = q3 ? (cur - d3)[1] : 0x100;
             h.ht2[h2] = pos;
             h.ht3[h3] = pos;
         }
+        const u32 c1 = limit > 1 ? cur[1] : 0;
         bool stop = false;
-        // rep-distance probes (:266-299); rep0 also yields the 1-byte match when it matches >= 2
-        if (v0 && b0 == c1) {
-            u32 ml = lcp_bytes(cur, cur - r0, limit);
-            if (ml) push_cand(h, cnt, 1, 1);
-            if (ml > minlen) { minlen = ml; push_cand(h, cnt, ml, 1); stop = ml >= h.good; }
+        // rep-distance probes (:266-299); rep0 also yields the 1-byte match when it matches at all
+        const u32 rr[4] = {r0, r1, r2, r3};
+        for (u32 i = 0; i < 4 && !stop; i++) {
+            if (rr[i] >= h.vld) continue;
+            const u32 cl = climit_of(h, x, rr[i], limit);
+            if (minlen >= cl || (cur - rr[i])[minlen] != cur[minlen]) continue;
+            const u32 ml = lcp_bytes(cur, cur - rr[i], cl);
+            if (ml && i == 0) push_cand(h, cnt, 1, 1);
+            if (ml > minlen) { minlen = ml; push_cand(h, cnt, ml, 1 + i); stop = ml >= h.good; }
         }
-        if (!stop && v1 && minlen < limit) stop = probe(h, cur, r1, limit, b1, c1, 2, false, minlen, cnt);
-        if (!stop && v2 && minlen < limit) stop = probe(h, cur, r2, limit, b2, c1, 3, false, minlen, cnt);
-        if (!stop && v3 && minlen < limit) stop = probe(h, cur, r3, limit, b3, c1, 4, false, minlen, cnt);
         if (stop) dist = 0xFFFFFFFFu;
-        // 2-byte and 3-byte single-slot tables (:303-366).  `wpos > dist` (:306): a 2-byte candidate
-        // at window offset 0 is dropped but still poisons dist.
+        // 2-byte and 3-byte single-slot tables (:303-366).  `wpos > dist` (:306): a 2-byte candidate at window
+        // offset 0 of the lap is dropped but still poisons dist.
+        const u32 d2 = pos - e2, d3 = pos - e3;
         if (d2 > dist) {
             dist = d2;
-            if (q2 && minlen < limit) {
-                if (known2) { if (take(h, l2, d2, minlen, cnt)) dist = 0xFFFFFFFFu; }
-                else if (probe(h, cur, d2, limit, h.tmode ? t2 : (u32)(cur - d2)[1], c1, 4 + d2, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+            if (d2 < h.vld && wpos != d2 && x >= d2) {
+                const u32 cl = climit_of(h, x, d2, limit);
+                if (minlen < cl) {
+                    if (known2) { if (take(h, l2 < cl ? l2 : cl, d2, minlen, cnt)) dist = 0xFFFFFFFFu; }
+                    else if (probe(h, cur, d2, cl, (u32)(cur - d2)[1], c1, 4 + d2, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+                }
             }
         }
         if (d3 > dist) {
             dist = d3;
-            if (q3 && minlen < limit) {
-                if (known3) { if (take(h, l3, d3, minlen, cnt)) dist = 0xFFFFFFFFu; }
-                else if (probe(h, cur, d3, limit, h.tmode ? t3 : (u32)(cur - d3)[1], c1, 4 + d3, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+            if (d3 < h.vld && x >= d3) {
+                const u32 cl = climit_of(h, x, d3, limit);
+                if (minlen < cl) {
+                    if (known3) { if (take(h, l3 < cl ? l3 : cl, d3, minlen, cnt)) dist = 0xFFFFFFFFu; }
+                    else if (probe(h, cur, d3, cl, (u32)(cur - d3)[1], c1, 4 + d3, true, minlen, cnt)) dist = 0xFFFFFFFFu;
+                }
             }
         }
         // 6-byte table of width h.W (:453-485): the first h.W live entries of the chain
         if (h.W && dist != 0xFFFFFFFFu) {
-#if defined(__CUDA_ARCH__)
-            // lanes 0..K-1 evaluate their entry; the running minlen is a prefix maximum and the
-            // strictly increasing distances make the `<= dist` filter a compare with the entry value
-            const u32 validm = __ballot_sync(0xFFFFFFFFu, re != kNone);
-            const u32 alivem = __ballot_sync(0xFFFFFFFFu, re != kNone && !rdead);
-            const u32 lt = (1u << CSC_LANE) - 1;
-            const u32 d = x - re;
-            const bool cons = ((alivem >> CSC_LANE) & 1) && (u32)__popc(alivem & lt) < h.W;
-            const bool passd = cons && d > dist && d < h.vld && minlen < limit;
-            u32 pm = passd ? rl : 0;
-#pragma unroll
-            for (int sft = 1; sft < 8; sft <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, pm, sft); if (CSC_LANE >= (u32)sft) pm = max(pm, t); }
-            u32 excl = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
-            if (CSC_LANE == 0) excl = 0;
-            const u32 run = max(minlen, excl);
-            bool acc = passd && rl > run && !(rl <= 6 && d >= mf_bound(rl));
-            const u32 stopm = __ballot_sync(0xFFFFFFFFu, acc && rl >= h.good);
-            if (stopm && CSC_LANE > (u32)__ffs((int)stopm) - 1) acc = false;
-            const u32 accm = __ballot_sync(0xFFFFFFFFu, acc);
-            if (acc) { u32 idx = cnt + (u32)__popc(accm & lt); h.cl[idx] = rl; h.cd[idx] = 4 + d; }
-            cnt += (u32)__popc(accm);
-            __syncwarp();
-            // a dead entry inside a full row leaves the bucket short: keep walking behind the row (rare)
-            const u32 full = (h.K >= 32) ? 0xFFFFFFFFu : ((1u << h.K) - 1);
-            if (!stopm && validm == full && (u32)__popc(alivem) < h.W) {
-                u32 found = (u32)__popc(alivem);
-                u32 last_d = 0, last_l = 0;   // state after the row: dist / minlen
-                {
-                    const u32 pdm = __ballot_sync(0xFFFFFFFFu, cons);
-                    u32 md = cons ? d : 0;
-                    u32 ml2 = (passd && rl > run) ? rl : 0;
-#pragma unroll
-                    for (int sft = 16; sft; sft >>= 1) { md = max(md, __shfl_xor_sync(0xFFFFFFFFu, md, sft)); ml2 = max(ml2, __shfl_xor_sync(0xFFFFFFFFu, ml2, sft)); }
-                    last_d = pdm ? md : 0; last_l = ml2;
-                }
-                if (last_d > dist) dist = last_d;
-                if (last_l > minlen) minlen = last_l;
-                u32 src = __shfl_sync(0xFFFFFFFFu, re, h.K - 1), kk = 0;
-                while (found < h.W) {
-                    u32 e = h.P6[(size_t)src * h.K + kk];
-                    if (e == kNone) break;
-                    if (++kk == h.K) { src = e; kk = 0; }
-                    if (dead6(h, e)) continue;
-                    found++;
-                    u32 dd = x - e;
-                    if (dd <= dist) continue;
-                    dist = dd;
-                    if (dist >= h.vld || minlen >= limit) continue;
-                    if (probe(h, cur, dd, limit, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
-                }
-            }
-#else
             u32 found = 0, src = x, k = 0;
             while (found < h.W) {
                 size_t at = (size_t)src * h.K + k;
@@ -797,14 +735,16 @@ struct Encoder {
                 if (d <= dist) continue;
                 dist = d;
                 if (dist >= h.vld) continue;
-                if (minlen >= limit) continue;
+                const u32 cl = climit_of(h, x, d, limit);
+                if (minlen >= cl) continue;
                 u32 ml;
                 if (inrow) {
                     ml = h.L6[at];
+                    if (ml > cl) ml = cl;
                 } else {
                     const u8 *m = cur - dist;
                     if (m[minlen] != cur[minlen]) continue;
-                    ml = lcp_bytes(cur, m, limit);
+                    ml = lcp_bytes(cur, m, cl);
                 }
                 if (ml > minlen) {
                     minlen = ml;
@@ -813,10 +753,10 @@ struct Encoder {
                     if (ml >= h.good) break;
                 }
             }
-#endif
         }
         // x itself is now the newest entry everywhere (alive by default)
         return cnt;
+#endif
     }
 
     CSC_HDF static bool second_better(Cand u1, Cand u2) {   // csc_mf.cpp:570-582 (== fold of :497-524)
@@ -974,7 +914,9 @@ struct Encoder {
             if (p_uni(!have || !(u1.len == 1 || u1.len >= h.good))) {
                 // the one probe site: u1 at x, or the lazy look-ahead u2 at x + 1
                 const u32 px = have ? x + 1 : x;
-                Cand c = best_of(h, fm_core(h, px, end - px, rep[0], rep[1], rep[2], rep[3]));
+                const u32 nc = fm_core(h, px, end - px, rep[0], rep[1], rep[2], rep[3]);
+                if (S.trace) trace_cands(px, nc);
+                Cand c = best_of(h, nc);
                 if (p_uni(!have)) { u1 = c; have = true; continue; }
                 if (p_uni(second_better(u1, c))) {
                     emit(OP_LIT, h.lz[x], 0, 0);
@@ -1130,6 +1072,7 @@ struct Encoder {
             if (p_uni(!in_round || apcur < aplimit)) {
                 prefetch_core(h, x + 1, end);
                 const u32 n = fm_core(h, x, end - x, r0, r1, r2, r3);
+                if (S.trace) trace_cands(x, n);
                 price_table(n, ns, t0, td, tp, t1d, t1p);
             }
             if (p_uni(!in_round)) {
@@ -1172,7 +1115,8 @@ struct Encoder {
                 continue;
             }
             const u32 base = lv_get(wp, 0);
-            const u32 cprice = literal_price_w(ns, x ? h.lz[x - 1] : 0, lit);
+            // lit_ctx = wnd_curpos_ ? wnd_[wnd_curpos_ - 1] : 0 (csc_lz.cpp:297): offset 0 of every lap has no context
+            const u32 cprice = literal_price_w(ns, (h.wnd ? x % h.wnd : x) ? h.lz[x - 1] : 0, lit);
             const u32 len = t0.len;
             if (apcur + len >= apend) apend = apcur + len + 1;
             LV_FOR(j) {
@@ -1199,6 +1143,10 @@ struct Encoder {
         for (u32 off = 0; off < size;) {
             u32 sb = size - off;
             if (sb > kBlock) sb = kBlock;
+            if (wrap) {   // a sub-block never straddles the window end (csc_lz.cpp:65-66)
+                const u32 to_wrap = S.cfg.wnd_size - (a + off) % S.cfg.wnd_size;
+                if (to_wrap < sb) sb = to_wrap;
+            }
             if (S.cfg.lz_mode == 3) parse_optimal(a + off, sb);
             else parse_lazy(a + off, sb);
             off += sb;
@@ -1214,6 +1162,7 @@ struct Encoder {
     // A statically excluded block is LZ-parsed after all (duplicate-block flip): the chains do not know its
     // positions, so rebuild the real 2-/3-byte tables from the history [0, upto) and use them from here on.
     CSC_HDN void enter_table_mode(u32 upto) {
+        if (wrap) { err = kErrUnsupported; return; }   // cannot happen: a wrapped stream re-plans instead (compress_segment)
         u32 a = 0;
         for (u32 sg = 0; sg < S.nseg && a < upto; sg++) {
             u32 sz = S.seg_size[sg];
@@ -1310,9 +1259,11 @@ struct Encoder {
                     if (e != kNone && run_start - e < vld) {
                         u32 limit = bsize - off, k = 0;
                         const u8 *a = S.lz + p, *m = S.lz + e;
-                        u32 valid = run_start - e;   // bytes beyond are unwritten (zero) window
+                        const u32 valid = run_start - e;   // bytes beyond are not written yet: zero on the first lap,
+                        const u32 wsz = S.cfg.wnd_size;     // the previous lap's bytes afterwards; compares stop at the window end
+                        if (wrap) { const u32 c = wsz - e % wsz; if (c < limit) limit = c; }
                         while (k < limit) {
-                            u8 mv = k < valid ? m[k] : (u8)0;
+                            u8 mv = k < valid ? m[k] : (e + k >= wsz ? S.lz[e + k - wsz] : (u8)0);
                             if (a[k] != mv) break;
                             k++;
                             if (k > 18) break;
@@ -1356,33 +1307,24 @@ struct Encoder {
 
     // one Compress() call (csc_encoder_main.cpp:85-146)
     CSC_HDN void compress_segment(u32 seg, u32 a, u32 size) {
-        const bool use_filters = (S.cfg.flt_dlt + S.cfg.flt_txt + S.cfg.flt_exe) != 0;
         u32 last_type = DT_NORMAL, last_begin = 0, last_size = 0;
         u32 bpb = 0;
         u32 blk = S.seg_blk0[seg];
         u32 last_blk = blk;
         for (u32 i = 0; i < size; blk++) {
             u32 cur = size - i < kBlock ? size - i : kBlock;
-            u32 t = DT_NORMAL;
-            bool inherited = false;
-            if (use_filters) {
-                t = S.binfo[blk] & 0xFF;
-                if (t != DT_SKIP) bpb = S.bbpb[blk];
-            }
-            if (t == DT_SKIP) { t = last_type; inherited = true; }
-            if (t != DT_NORMAL) {
-                if (t == DT_EXE && !S.cfg.flt_exe) t = DT_NORMAL;
-                else if (t == DT_ENGTXT && !S.cfg.flt_txt) t = DT_NORMAL;
-                else if (t >= DT_DLT && !S.cfg.flt_dlt) t = DT_NORMAL;
-            }
-            if (t >= DT_DLT) {   // GetDltBpb(...) >= bpb * 0.95 (csc_encoder_main.cpp:118-121)
-                bool fail;
-                if (inherited) fail = (double)S.tail_dlt[seg * 5 + (t - DT_DLT)] >= (double)bpb * 0.95;
-                else fail = ((S.binfo[blk] >> 8) & 1) != 0;
-                if (fail) t = DT_NORMAL;
-            }
+            u32 t = static_type(S.binfo, S.bbpb, S.tail_dlt + seg * 5, blk, last_type, bpb, S.cfg.flt_dlt, S.cfg.flt_txt, S.cfg.flt_exe);
             if (t >= DT_NO_LZ) {
-                if (dup_block(a + i, cur, a + last_begin)) t = DT_NORMAL;
+                const bool dup = dup_block(a + i, cur, a + last_begin);
+                // The static plan (plan.h) assumed an outcome for this test.  Once the window wraps, run ends
+                // move the sub-block grid the match-finder kernels hashed over, so a wrong guess is fatal
+                // there: report the block and let the host plan again with the observed outcome.
+                if (wrap && dup != (S.flip && S.flip[blk] != 0)) {
+                    if (S.replan) { S.replan[0] = blk; S.replan[1] = dup ? 1u : 0u; }
+                    err = kErrReplan;
+                    return;
+                }
+                if (dup) t = DT_NORMAL;
             }
             if (t < DT_NO_LZ && S.blk_nolz[blk] && !want_tables) {
                 // the pending run (if it continues into this block) must already be parsed with tables
@@ -1413,6 +1355,7 @@ struct Encoder {
         vld = S.cfg.vld_rge; W = S.cfg.ht_width; K = S.K; good = S.cfg.good_len;
         err = 0; tr_n = 0;
         tmode = false; want_tables = false;
+        wrap = S.n > S.cfg.wnd_size;
         gs = 5;
         while (((S.n + 63) >> gs) > 2048) gs++;   // 2048 summary bits cover the stream
         w_sync();

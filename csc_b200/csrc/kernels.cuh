@@ -26,14 +26,16 @@
 
 namespace cscb {
 
+// Two grids use this descriptor: the analyzer's 8 KiB blocks (built on the host) and the sub-blocks of the
+// window copy (built by k_plan from plan.h: identical to the block grid unless the window wraps inside a run).
 struct BlockDesc {
     u64 goff;      // byte offset of the block in the batch LZ buffer
     u32 x;         // byte offset of the block in its stream
-    u32 size;      // <= 8192
+    u32 size;      // <= 8192 (0: unused slot)
     u32 stream;
     u32 seg;       // batch-global segment index
     u32 cpos;      // compact position index of the block's first byte (sort arrays)
-    u32 pad;
+    u32 flags;     // sub-block grid: bit 0 = left out of the 2-/3-byte chains (plan.h)
 };
 struct SegDesc {
     u64 goff;      // byte offset of the segment in the batch LZ buffer
@@ -42,7 +44,11 @@ struct SegDesc {
     u32 stream;
     u32 blk0;      // batch-global index of the segment's first block
     u32 flt;       // bit0 DLT, bit1 TXT, bit2 EXE
-    u32 pad;
+    u32 wnd;       // LZ window size of the stream
+    u32 sub0;      // first slot of this segment in the sub-block grid
+    u32 nslots;    // its slots there: blocks + window ends inside the segment
+    u32 cpos;      // compact position index of the segment's first byte
+    u32 seg;       // batch-global segment index
 };
 struct GRun { u64 goff; u32 size; u32 kind; u32 gblk; u32 pad; };
 
@@ -158,18 +164,29 @@ k_analyze(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, u32 nblk
 }
 
 // -------------------------------------------------------------- plan + filters
-__global__ void k_plan(const SegDesc *__restrict__ segs, u32 nseg, const u32 *__restrict__ binfo, FilterRun *scratch,
-                       GRun *runs, u32 *nruns, u8 *nolz) {
+__global__ void k_plan(const SegDesc *__restrict__ segs, u32 nseg, const u32 *__restrict__ binfo, const u32 *__restrict__ bbpb,
+                       const u32 *__restrict__ tail_dlt, const u8 *__restrict__ flip, FilterRun *scratch, SubBlock *subscratch,
+                       GRun *runs, u32 *nruns, u8 *nolz, BlockDesc *subdesc) {
     u32 s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseg) return;
     const SegDesc sd = segs[s];
     FilterRun *mine = scratch + sd.blk0;
-    u32 nr = plan_segment(binfo, sd.blk0, 0, sd.size, sd.flt & 1, (sd.flt >> 1) & 1, (sd.flt >> 2) & 1, mine, nolz);
+    SubBlock *subs = subscratch + sd.sub0;
+    u32 nsub = 0;
+    u32 nr = plan_segment(binfo, bbpb, tail_dlt + (size_t)sd.seg * 5, flip, sd.blk0, sd.x, sd.size, sd.wnd, sd.flt & 1, (sd.flt >> 1) & 1,
+                          (sd.flt >> 2) & 1, mine, nolz, subs, &nsub);
+    for (u32 i = 0; i < sd.nslots; i++) {   // the sub-block grid the match-finder kernels run over
+        BlockDesc bd;
+        const u32 rel = i < nsub ? subs[i].x - sd.x : 0;   // relative to the segment
+        bd.goff = sd.goff + rel; bd.x = sd.x + rel; bd.size = i < nsub ? subs[i].size : 0; bd.stream = sd.stream; bd.seg = sd.seg;
+        bd.cpos = sd.cpos + rel; bd.flags = i < nsub ? subs[i].flags : 0;
+        subdesc[sd.sub0 + i] = bd;
+    }
     if (!nr) return;
     u32 at = atomicAdd(nruns, nr);
     for (u32 i = 0; i < nr; i++) {
         GRun r;
-        r.goff = sd.goff + mine[i].off; r.size = mine[i].size; r.kind = mine[i].kind; r.gblk = mine[i].first_blk; r.pad = 0;
+        r.goff = sd.goff - sd.x + mine[i].off; r.size = mine[i].size; r.kind = mine[i].kind; r.gblk = mine[i].first_blk; r.pad = 0;
         runs[at + i] = r;
     }
 }
@@ -372,10 +389,11 @@ static const int kMfThreads = 256;
 // 32 positions with shuffles (one atomic per non-empty word instead of one per set bit).
 __global__ void __launch_bounds__(kMfThreads)
 k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u32 *__restrict__ stream_bits,
-          const u64 *__restrict__ stream_goff, u32 key_shift, u64 *__restrict__ keys, u32 *__restrict__ vals,
-          u32 *Z2, u32 *Z6, u32 which, const u8 *__restrict__ nolz) {
+          const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_wnd, u32 key_shift, u64 *__restrict__ keys,
+          u32 *__restrict__ vals, u32 *Z2, u32 *Z6, u32 which) {
     __shared__ __align__(16) u32 sw[kBlock / 4 + 8];
     const BlockDesc bd = blk[blockIdx.x];
+    if (!bd.size) return;
     {   // stage the block, zero padding behind its end (H2); blocks start 4-byte aligned in the batch buffer
         // only when the stream offset is, so go through bytes when it is not
         const u8 *src = lz + bd.goff;
@@ -395,10 +413,18 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
         }
     }
     __syncthreads();
+    {   // once the window has wrapped, the bytes behind the sub-block end are the previous lap's, not zeros (plan.h: window_byte)
+        const u32 wnd = stream_wnd[bd.stream], sb_end = bd.x + bd.size;
+        if (sb_end > wnd) {
+            if (threadIdx.x < 16)
+                reinterpret_cast<u8 *>(sw)[bd.size + threadIdx.x] = (u8)window_byte(lz + stream_goff[bd.stream], sb_end + threadIdx.x, sb_end, wnd);
+            __syncthreads();
+        }
+    }
     const u32 bits = stream_bits[bd.stream];
     const u64 bitbase = (stream_goff[bd.stream]) + bd.x;   // bitmaps are indexed by batch byte offset
     const u64 skey = (u64)bd.stream << key_shift;
-    const bool excluded = which < 6 && nolz[blockIdx.x];
+    const bool excluded = which < 6 && (bd.flags & 1);
     const bool vec = (bd.cpos & 3) == 0;
     const u32 lane = threadIdx.x & 31;
     for (u32 i0 = threadIdx.x * 4; i0 < ((bd.size + 127) & ~127u); i0 += kMfThreads * 4) {
@@ -547,7 +573,7 @@ __device__ __forceinline__ void sort16_desc(u32 *v) {
 }
 __global__ void __launch_bounds__(256)
 k_mf_merge(const BlockDesc *__restrict__ blk, const u64 *__restrict__ stream_goff, u32 *__restrict__ P6) {
-    const BlockDesc bd = blk[blockIdx.x];
+    const BlockDesc bd = blk[blockIdx.x];   // (an unused slot has size 0)
     const u64 sg = stream_goff[bd.stream];
     for (u32 i = threadIdx.x; i < bd.size; i += 256) {
         uint4 *row = reinterpret_cast<uint4 *>(P6 + (sg + bd.x + i) * 16);

@@ -87,8 +87,9 @@ struct Ctx {
     u32 *d_p2bits = nullptr;
     DevBuf packdesc, lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
-        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB;
-    PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta;
+        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
+        flip, replan, subdesc, subscratch, swnd;
+    PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta, h_replan;
     Timer tm;
     CSCB200_Stats stats;
 };
@@ -99,6 +100,10 @@ int g_device = -1;
 // debug: copy the intermediate arrays of a single-stream wave back to the host (tests only)
 struct DebugDump { u32 *binfo, *bbpb; u8 *lz; u32 *P6; u16 *L6; u32 *Z2, *Z6; u8 *dict_ok; u32 *tail_dlt; bool on; };
 thread_local DebugDump g_dump = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false};
+
+// debug: packet + match-candidate trace of the next single-stream encode (tests only; see Encoder::trace)
+struct DebugTrace { u32 *buf; size_t cap; size_t *n_out; bool on; };
+thread_local DebugTrace g_trace = {nullptr, 0, nullptr, false};
 
 int ctx_init(Ctx &C) {
     if (C.init) return 0;
@@ -147,6 +152,7 @@ struct EncJob {
     bool no_payload = false;   // leave RC/BC sub-streams in HBM, only fetch the per-segment records
     CSCProps props;
     std::vector<u32> segs;     // Read() sizes
+    std::vector<u8> flip;      // per block: assumed outcome of the duplicate-block test (plan.h); refined on kErrReplan
     int status;
     // results (host, pinned staging): filled by encode_wave
     std::vector<SegOut> so;
@@ -162,34 +168,39 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     cudaStream_t st = C.st;
     // ---- layout
     std::vector<u64> goff(ns);
-    std::vector<u32> seg0(ns), sbits(ns), sK(ns), rcoff(ns), bcoff(ns), rccap(ns), evcap(ns), evoff(ns);
+    std::vector<u32> seg0(ns), sbits(ns), sK(ns), swnd(ns), sblk0(ns), rcoff(ns), bcoff(ns), rccap(ns), evcap(ns), evoff(ns);
     std::vector<BlockDesc> blks;
     std::vector<SegDesc> segs;
     std::vector<u32> segsize, segblk0;
     u64 total = 0, rctot = 0, evtot = 0;
-    u32 cpos = 0, K = 0, key_shift = 0;
+    u32 cpos = 0, K = 0, key_shift = 0, nsub = 0;
     bool bounded = false;   // -m5: bounded multi-context search rows
     for (u32 s = 0; s < ns; s++) {
         EncJob &J = *jobs[s];
         EncCfg cfg = cfg_from_props(&J.props);
-        if (J.n > cfg.wnd_size || cfg.bt_bits || !cfg.ht_width) { J.status = kErrUnsupported; return kErrUnsupported; }
+        // (a stream longer than its window wraps: plan.h re-grids the sub-blocks; MatchFinder::normalize, csc_mf.cpp:108-114,
+        // which only triggers beyond ~4 GiB per stream, is not modelled)
+        if ((u64)J.n + cfg.vld_rge >= 0xFFFFFFF0ull || cfg.bt_bits || !cfg.ht_width) { J.status = kErrUnsupported; return kErrUnsupported; }
         if (s == 0) { K = cfg.ht_width; bounded = cfg.bounded != 0; }
         if (cfg.ht_width != K || (cfg.bounded != 0) != bounded) return kErrUnsupported;   // one level per wave
         goff[s] = total;
         seg0[s] = (u32)segs.size();
-        sbits[s] = cfg.ht_bits; sK[s] = cfg.ht_width;
+        sbits[s] = cfg.ht_bits; sK[s] = cfg.ht_width; swnd[s] = cfg.wnd_size; sblk0[s] = (u32)blks.size();
         key_shift = std::max(key_shift, cfg.ht_bits);
         u32 x = 0;
         u32 flt = (J.props.DLTFilter ? 1 : 0) | (J.props.TXTFilter ? 2 : 0) | (J.props.EXEFilter ? 4 : 0);
         for (u32 sz : J.segs) {
             SegDesc sd;
-            sd.goff = total + x; sd.x = x; sd.size = sz; sd.stream = s; sd.blk0 = (u32)blks.size(); sd.flt = flt; sd.pad = 0;
+            sd.goff = total + x; sd.x = x; sd.size = sz; sd.stream = s; sd.blk0 = (u32)blks.size(); sd.flt = flt;
+            sd.wnd = cfg.wnd_size; sd.sub0 = nsub; sd.nslots = (sz + kBlock - 1) / kBlock + wraps_inside(x, sz, cfg.wnd_size);
+            sd.cpos = cpos; sd.seg = (u32)segs.size();
+            nsub += sd.nslots;
             segsize.push_back(sz);
             segblk0.push_back(sd.blk0);
             for (u32 off = 0; off < sz; off += kBlock) {
                 BlockDesc bd;
                 bd.goff = total + x + off; bd.x = x + off; bd.size = std::min(kBlock, sz - off); bd.stream = s;
-                bd.seg = (u32)segs.size(); bd.cpos = cpos; bd.pad = 0;
+                bd.seg = (u32)segs.size(); bd.cpos = cpos; bd.flags = 0;
                 cpos += bd.size;
                 blks.push_back(bd);
             }
@@ -232,7 +243,9 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     const size_t bmbytes = total / 8 + 64;
     r |= C.Z2.ensure(bmbytes); r |= C.Z6.ensure(bmbytes); r |= C.D6.ensure(bmbytes); r |= C.D23.ensure(bmbytes);
     r |= C.P3.ensure(total * 4); r |= C.P2.ensure(total * 4); r |= C.L3.ensure(total * 2); r |= C.L2.ensure(total * 2);
-    r |= C.nolz.ensure(nblk + 16);
+    r |= C.nolz.ensure(nblk + 16); r |= C.flip.ensure(nblk + 16); r |= C.replan.ensure((size_t)ns * 8);
+    r |= C.subdesc.ensure((size_t)nsub * sizeof(BlockDesc)); r |= C.subscratch.ensure((size_t)nsub * sizeof(SubBlock));
+    r |= C.swnd.ensure((size_t)ns * 4);
     r |= C.ht.ensure((size_t)ns * 81920 * 4);
     r |= C.plit.ensure((size_t)ns * 131072 * 2);
     r |= C.ap.ensure((size_t)ns * (kApLimit + 2) * sizeof(ApUnit));
@@ -300,6 +313,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         S.P3 = C.P3.as<u32>() + goff[s]; S.L3 = C.L3.as<u16>() + goff[s];
         S.P2 = C.P2.as<u32>() + goff[s]; S.L2 = C.L2.as<u16>() + goff[s];
         S.D23 = C.D23.as<u32>() + goff[s] / 32; S.blk_nolz = C.nolz.as<u8>();
+        S.flip = C.flip.as<u8>(); S.replan = C.replan.as<u32>() + 2 * (size_t)s;
         S.ht2 = C.ht.as<u32>() + (size_t)s * 81920; S.ht3 = S.ht2 + 16384;
         S.p_lit = C.plit.as<u16>() + (size_t)s * 131072; S.p_delta = S.p_lit + 65536;
         S.ap = C.ap.as<ApUnit>() + (size_t)s * (kApLimit + 2);
@@ -308,6 +322,11 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         S.events = C.ev.as<u8>() + evoff[s]; S.ev_cap = evcap[s];
         S.segout = C.segout.as<SegOut>() + seg0[s];
         S.status = C.status.as<i32>() + s;
+    }
+    const bool tracing = g_trace.on && ns == 1;
+    if (tracing) {
+        if (C.trace.ensure(g_trace.cap * 12 + 16)) return kErrCuda;
+        es[0].trace = C.trace.as<u32>(); es[0].trace_cap = (u32)g_trace.cap; es[0].trace_n = C.counters.as<u32>() + 2;
     }
     Timer &T = C.tm;
     T.n = 0;
@@ -325,6 +344,11 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     CK(cudaMemcpyAsync(C.sbits.p, sbits.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.sgoff.p, goff.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.sK.p, sK.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(C.swnd.p, swnd.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(C.flip.p, 0, nblk, st));
+    for (u32 s = 0; s < ns; s++)
+        if (!jobs[s]->flip.empty())
+            CK(cudaMemcpyAsync(C.flip.as<u8>() + sblk0[s], jobs[s]->flip.data(), jobs[s]->flip.size(), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.streams.p, es.data(), (size_t)ns * sizeof(EncStream), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(C.Z2.p, 0, bmbytes, st));
     CK(cudaMemsetAsync(C.Z6.p, 0, bmbytes, st));
@@ -346,15 +370,16 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     T.mark(st);                                                                   // 2
     u32 *d_nruns = C.counters.as<u32>();
     u32 *d_queue = C.counters.as<u32>() + 1;
-    k_plan<<<(nseg + 127) / 128, 128, 0, st>>>(C.segdesc.as<SegDesc>(), nseg, C.binfo.as<u32>(), C.planscratch.as<FilterRun>(),
-                                               C.runs.as<GRun>(), d_nruns, C.nolz.as<u8>());
+    k_plan<<<(nseg + 127) / 128, 128, 0, st>>>(C.segdesc.as<SegDesc>(), nseg, C.binfo.as<u32>(), C.bbpb.as<u32>(), C.taildlt.as<u32>(),
+                                               C.flip.as<u8>(), C.planscratch.as<FilterRun>(), C.subscratch.as<SubBlock>(),
+                                               C.runs.as<GRun>(), d_nruns, C.nolz.as<u8>(), C.subdesc.as<BlockDesc>());
     k_filter_runs<<<std::min<u32>(nblk, 148 * 8), kFltThreads, 0, st>>>(C.lz.as<u8>(), C.tmp.as<u8>(), C.runs.as<GRun>(), d_nruns, C.d_DT, C.dictok.as<u8>());
     T.mark(st);                                                                   // 3
     launches += 3;
     // ---- match finder precomputation: 6-byte rows, then the 3-byte and 2-byte chains
     const u32 *pos_stream = nullptr;
-    k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), key_shift,
-                                           C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), 6, C.nolz.as<u8>());
+    k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), key_shift,
+                                           C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), 6);
     T.mark(st);                                                                   // 4
     u64 *ksorted = nullptr;
     u32 *vsorted = nullptr;
@@ -364,31 +389,31 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
                                                   C.P6.as<u32>(), pos_stream, bounded ? kBtKA : 0, bounded ? kBtRowK : 0, 0);
     if (bounded) {   // two more candidate lists by 8- and 12-byte context, then one distance-ordered row
         for (u32 which = kBtCtxB; which <= kBtCtxC; which += kBtCtxC - kBtCtxB) {
-            k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), key_shift,
-                                                   C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which, C.nolz.as<u8>());
+            k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), key_shift,
+                                                   C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
             sort_pairs(key_shift, end_bit, ksorted, vsorted);
             k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
                                                           pos_stream, which == kBtCtxB ? kBtKB : kBtKC, kBtRowK, which == kBtCtxB ? kBtKA : kBtKA + kBtKB);
         }
-        k_mf_merge<<<nblk, 256, 0, st>>>(C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>());
+        k_mf_merge<<<nsub, 256, 0, st>>>(C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>());
         launches += 5;
     }
     T.mark(st);                                                                   // 6
-    if (K == 1) k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
-    else if (K == 2) k_mf_extend<2><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
-    else if (K == 8) k_mf_extend<8><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
-    else if (K == 16) k_mf_extend<16><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
+    if (K == 1) k_mf_extend<1><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
+    else if (K == 2) k_mf_extend<2><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
+    else if (K == 8) k_mf_extend<8><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
+    else if (K == 16) k_mf_extend<16><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>(), C.L6.as<u16>());
     else return kErrUnsupported;
     T.mark(st);                                                                   // 7
     for (u32 which = 3; which >= 2; which--) {
         const u32 shift = which == 3 ? 16 : 14;
         u32 *P = which == 3 ? C.P3.as<u32>() : C.P2.as<u32>();
         u16 *L = which == 3 ? C.L3.as<u16>() : C.L2.as<u16>();
-        k_mf_hash<<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), shift,
-                                               C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which, C.nolz.as<u8>());
+        k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), shift,
+                                               C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
         sort_pairs(shift, (int)(shift + stream_bits), ksorted, vsorted);
         k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P, pos_stream, 1, 0, 0);
-        k_mf_extend<1><<<nblk, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
+        k_mf_extend<1><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
     }
     T.mark(st);                                                                   // 8
     launches += 3 + 1 + 2 * 3;
@@ -407,6 +432,17 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     }
     // ---- serial engines, one stream per warp
     int nsm = 148;
+    struct TraceFetch {   // copies the debug trace back once the encoder has run (scope exit on every path)
+        Ctx &C; bool on; cudaStream_t st;
+        ~TraceFetch() {
+            if (!on) return;
+            u32 n = 0;
+            cudaStreamSynchronize(st);
+            cudaMemcpy(&n, C.counters.as<u32>() + 2, 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(g_trace.buf, C.trace.p, std::min<size_t>(n, g_trace.cap) * 12, cudaMemcpyDeviceToHost);
+            if (g_trace.n_out) *g_trace.n_out = n;
+        }
+    } trace_fetch{C, tracing, st};
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, C.dev);
     const bool pair_mode = es[0].cfg.lz_mode == 2 && getenv("CSC_B200_PAIR");   // experimental: measured slower in round 1
     if (pair_mode) {
@@ -421,9 +457,12 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     launches += 1;
     CK(cudaGetLastError());
     // ---- results
-    if (C.h_segout.ensure((size_t)nseg * sizeof(SegOut)) || C.h_status.ensure((size_t)ns * 4) || C.h_ev.ensure(evtot + 16)) return kErrCuda;
+    if (C.h_segout.ensure((size_t)nseg * sizeof(SegOut)) || C.h_status.ensure((size_t)ns * 4) || C.h_ev.ensure(evtot + 16) ||
+        C.h_replan.ensure((size_t)ns * 8))
+        return kErrCuda;
     CK(cudaMemcpyAsync(C.h_segout.p, C.segout.p, (size_t)nseg * sizeof(SegOut), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(C.h_status.p, C.status.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(C.h_replan.p, C.replan.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(C.h_ev.p, C.ev.p, evtot, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const SegOut *hso = C.h_segout.as<SegOut>();
@@ -434,6 +473,16 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     for (u32 s = 0; s < ns; s++) {
         EncJob &J = *jobs[s];
         J.status = hst[s];
+        if (J.status == kErrReplan) {
+            // the engine saw a duplicate-block outcome the static plan had not assumed (wrapped stream): record it;
+            // the caller submits the stream again (prefix-stable, so every round fixes the earliest wrong guess)
+            const u32 *rp = C.h_replan.as<u32>() + 2 * (size_t)s;
+            if (J.flip.empty()) J.flip.assign((s + 1 < ns ? sblk0[s + 1] : nblk) - sblk0[s], 0);
+            if (rp[0] >= sblk0[s] && rp[0] - sblk0[s] < J.flip.size()) J.flip[rp[0] - sblk0[s]] = (u8)rp[1];
+            else { J.status = kErrUnsupported; ret = kErrUnsupported; }
+            C.stats.replans += 1;
+            continue;
+        }
         if (J.status < 0) { ret = J.status; continue; }
         u32 nsg = (u32)J.segs.size();
         J.so.assign(hso + seg0[s], hso + seg0[s] + nsg);
@@ -636,6 +685,11 @@ void CSCB200_DebugDump(uint32_t *binfo, uint32_t *bbpb, uint8_t *lz, uint32_t *P
     g_dump.dict_ok = dict_ok; g_dump.tail_dlt = tail_dlt; g_dump.on = binfo != nullptr;
 }
 
+// tests only: record the packet / match-candidate trace of the next single-stream encode as (kind, a, b) triples
+void CSCB200_DebugTrace(uint32_t *buf, size_t cap_triples, size_t *n_out) {
+    g_trace.buf = buf; g_trace.cap = cap_triples; g_trace.n_out = n_out; g_trace.on = buf != nullptr;
+}
+
 int CSCB200_Available(void) {
     int n = 0;
     return (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
@@ -674,10 +728,13 @@ static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_
     for (int i = 0; i < n; i++) order[i] = i;
     int ret = 0;
     size_t at = 0;
-    while (at < order.size()) {
+    std::vector<EncJob *> again;   // streams whose static plan has to be redone (kErrReplan)
+    while (at < order.size() || !again.empty()) {
         std::vector<EncJob *> wave;
+        if (!again.empty()) wave.swap(again);
+        const bool fresh = wave.empty();
         size_t bytes = 0, pos = 0;
-        while (at < order.size()) {
+        while (fresh && at < order.size()) {
             EncJob &J = jobs[order[at]];
             size_t need = per_stream_bytes() + (size_t)J.n * per_pos_bytes(K) + 4096;
             if (!wave.empty() && (bytes + need > budget || pos + J.n > 0x70000000ull)) break;
@@ -698,6 +755,7 @@ static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_
                 if (w >= wave.size()) break;
                 EncJob *J = wave[w];
                 size_t i = J - jobs.data();
+                if (J->status == kErrReplan) continue;   // goes round again below
                 if (device) { out_size[i] = framed_size(*J, with_props != 0); bytes_out += out_size[i]; continue; }
                 MemSink sink{out[i], out_cap[i], 0, false};
                 if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&J->props, hdr); sink(hdr, CSC_PROP_SIZE); }
@@ -718,6 +776,7 @@ static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_
             for (auto &th : pool) th.join();
         }
         if (overflow) ret = kErrOverflow;
+        for (EncJob *J : wave) if (J->status == kErrReplan) again.push_back(J);
         C.stats.bytes_out += bytes_out;
         C.stats.ms_frame += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
@@ -851,7 +910,8 @@ int CSCEnc_Encode(CSCEncHandle p, ISeqInStream *is, ICompressProgress *progress)
     J.in = data.data(); J.n = (u32)data.size();
     memset(&C.stats, 0, sizeof(C.stats));
     std::vector<EncJob *> wave{&J};
-    int r = encode_wave(C, wave);
+    int r;
+    do { r = encode_wave(C, wave); } while (r >= 0 && J.status == kErrReplan);   // wrapped window: plan again (plan.h)
     if (r < 0) return r;
     CbSink sink{h->os, false, 0};
     frame_job(J, *h->fr, sink);

@@ -48,6 +48,7 @@ typedef struct {
         ms_frame, ms_decode, ms_unfilter, ms_total_gpu, ms_mf_chains;   /* mf_hash..extend: 6-byte rows; mf_chains: 3-/2-byte chains */
     uint64_t bytes_in, bytes_out, mf_positions;
     uint32_t kernel_launches, streams, waves;
+    uint32_t replans;   /* streams encoded again because a duplicate-block outcome moved the sub-block grid of a wrapped window */
 } CSCB200_Stats;
 void CSCB200_GetStats(CSCB200_Stats *out);
 

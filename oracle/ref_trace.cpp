@@ -13,6 +13,8 @@
 static uint32_t *g_trace = 0;   // triples (kind, a, b)
 static size_t g_cap = 0, g_n = 0;
 
+static bool g_cands = false;   // also record the match-finder candidate lists (ref_mftrace.cpp)
+
 static inline void put(uint32_t k, uint32_t a, uint32_t b) {
     if (g_trace && g_n < g_cap) {
         g_trace[g_n * 3 + 0] = k;
@@ -30,7 +32,12 @@ void PEncode1BMatch() { put(2, 0, 0); }
 void PEncodeRepMatch(uint32_t len, uint32_t idx) { put(3, len, idx); }
 void PWriteLog() {}
 
+void ref_trace_put(uint32_t k, uint32_t a, uint32_t b) { put(k, a, b); }
+bool ref_trace_cands_on() { return g_trace && g_cands; }
+
 extern "C" {
-void ref_trace_begin(uint32_t *buf, size_t cap_triples) { g_trace = buf; g_cap = cap_triples; g_n = 0; }
-size_t ref_trace_end() { g_trace = 0; return g_n; }
+void ref_trace_begin(uint32_t *buf, size_t cap_triples) { g_trace = buf; g_cap = cap_triples; g_n = 0; g_cands = false; }
+// same, plus (4, position, n) / (5, len, dist) records for every MatchFinder::FindMatch / FindMatchWithPrice call
+void ref_trace_begin_cands(uint32_t *buf, size_t cap_triples) { g_trace = buf; g_cap = cap_triples; g_n = 0; g_cands = true; }
+size_t ref_trace_end() { g_trace = 0; g_cands = false; return g_n; }
 }

@@ -72,6 +72,7 @@ def tlib():
         _tlib = _load("libcsc_ref_trace.so")
         _sig(_tlib)
         _tlib.ref_trace_begin.argtypes = [C.c_void_p, C.c_size_t]
+        _tlib.ref_trace_begin_cands.argtypes = [C.c_void_p, C.c_size_t]
         _tlib.ref_trace_end.restype = C.c_size_t
     return _tlib
 
@@ -100,16 +101,19 @@ def out_bound(n: int) -> int:
 
 
 def encode(data, dict_size: int, level: int, read_size: int = 0, flt_mask: int = 7,
-           with_props: bool = True, trace: bool = False):
-    """Reference stream for one handle; dict_size is the argument of CSCEncProps_Init."""
+           with_props: bool = True, trace: bool = False, cands: bool = False):
+    """Reference stream for one handle; dict_size is the argument of CSCEncProps_Init.
+    trace: also return the packet trace; cands: the trace additionally carries the candidate list of every
+    MatchFinder::FindMatch / FindMatchWithPrice call (oracle/ref_mftrace.cpp)."""
+    trace = trace or cands
     a = _u8(data)
     l = tlib() if trace else lib()
     out = np.empty(out_bound(a.size), dtype=np.uint8)
     n = C.c_size_t(0)
     tr = None
     if trace:
-        tr = np.zeros((max(16, a.size + 1024), 3), dtype=np.uint32)
-        l.ref_trace_begin(tr.ctypes.data, tr.shape[0])
+        tr = np.zeros((max(16, a.size + 1024) * (12 if cands else 1), 3), dtype=np.uint32)
+        (l.ref_trace_begin_cands if cands else l.ref_trace_begin)(tr.ctypes.data, tr.shape[0])
     r = l.ref_encode(a.ctypes.data, a.size, dict_size, level, read_size, flt_mask, int(with_props),
                      out.ctypes.data, out.size, C.byref(n))
     if trace:

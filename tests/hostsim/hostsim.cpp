@@ -28,8 +28,8 @@ struct Sink {
 };
 
 // Brute-force "last-K prior occurrences per position" (what kernels.cuh: k_mf_hash / k_mf_rows / k_mf_extend compute with a
-// sort + segmented scan) through an actual last-occurrence table.
-void build_mf_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, u32 bits, u32 K, std::vector<u32> &P6,
+// sort + segmented scan) through an actual last-occurrence table, over the sub-block grid of plan.h.
+void build_mf_cpu(const u8 *lz, u32 n, const std::vector<SubBlock> &subs, u32 wnd, u32 bits, u32 K, std::vector<u32> &P6,
                   std::vector<u16> &L6, std::vector<u32> &Z2, std::vector<u32> &Z6) {
     u32 words = (n + 31) / 32 + 1;
     Z2.assign(words, 0);
@@ -38,103 +38,88 @@ void build_mf_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, u32 bits, u3
     L6.assign((size_t)n * (K ? K : 1), 0);
     std::vector<u32> last;
     if (K) last.assign((size_t)1 << bits, kNone);
-    u32 a = 0;
-    for (u32 s = 0; s < seg.size(); s++) {
-        for (u32 off = 0; off < seg[s]; off += kBlock) {
-            u32 sb = seg[s] - off < kBlock ? seg[s] - off : kBlock;
-            u32 sb_end = a + off + sb;
-            for (u32 x = a + off; x < sb_end; x++) {
-                u32 avail = sb_end - x;
-                if (hash2_padded(lz + x, avail) % 16 == 0) Z2[x >> 5] |= 1u << (x & 31);
-                if (!K) continue;
-                u32 h = hash6_padded(lz + x, avail, bits);
-                if (h == 0) Z6[x >> 5] |= 1u << (x & 31);
-                u32 prev = last[h];
-                last[h] = x;
-                u32 e = prev;
-                for (u32 k = 0; k < K && e != kNone; k++) {
-                    P6[(size_t)x * K + k] = e;
-                    u32 l = 0;
-                    while (l < avail && lz[x + l] == lz[e + l]) l++;
-                    L6[(size_t)x * K + k] = (u16)l;
-                    e = P6[(size_t)e * K];
-                }
+    for (const SubBlock &sb : subs) {
+        u32 sb_end = sb.x + sb.size;
+        for (u32 x = sb.x; x < sb_end; x++) {
+            u32 avail = sb_end - x;
+            if (hash2_at(lz, x, sb_end, wnd) % 16 == 0) Z2[x >> 5] |= 1u << (x & 31);
+            if (!K) continue;
+            u32 h = hash6_at(lz, x, sb_end, wnd, bits);
+            if (h == 0) Z6[x >> 5] |= 1u << (x & 31);
+            u32 prev = last[h];
+            last[h] = x;
+            u32 e = prev;
+            for (u32 k = 0; k < K && e != kNone; k++) {
+                P6[(size_t)x * K + k] = e;
+                u32 l = 0;
+                while (l < avail && lz[x + l] == lz[e + l]) l++;
+                L6[(size_t)x * K + k] = (u16)l;
+                e = P6[(size_t)e * K];
             }
         }
-        a += seg[s];
     }
 }
 
 
 // -m5 bounded search rows (csc_defs.h: kBt*): nearest earlier positions by 6-byte hash, 8- and 12-byte context
 // hash, merged by distance, duplicates removed -- what k_mf_hash / k_mf_rows / k_mf_merge compute on the device.
-void build_mf5_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, std::vector<u32> &P6, std::vector<u16> &L6) {
+void build_mf5_cpu(const u8 *lz, u32 n, const std::vector<SubBlock> &subs, u32 wnd, std::vector<u32> &P6, std::vector<u16> &L6) {
     const u32 bits = kBtHashBits, K = kBtRowK;
     std::vector<u32> lastA((size_t)1 << bits, kNone), lastB((size_t)1 << bits, kNone), lastC((size_t)1 << bits, kNone);
     std::vector<u32> prevA(n, kNone), prevB(n, kNone), prevC(n, kNone);
     P6.assign((size_t)n * K, kNone);
     L6.assign((size_t)n * K, 0);
-    u32 a = 0;
-    for (u32 s = 0; s < seg.size(); s++) {
-        for (u32 off = 0; off < seg[s]; off += kBlock) {
-            u32 sb = seg[s] - off < kBlock ? seg[s] - off : kBlock;
-            u32 sb_end = a + off + sb;
-            for (u32 x = a + off; x < sb_end; x++) {
-                u32 avail = sb_end - x;
-                u32 hA = hash6_padded(lz + x, avail, bits), hB = hash_ctx_padded(lz + x, avail, kBtCtxB, bits),
-                    hC = hash_ctx_padded(lz + x, avail, kBtCtxC, bits);
-                prevA[x] = lastA[hA]; lastA[hA] = x;
-                prevB[x] = lastB[hB]; lastB[hB] = x;
-                prevC[x] = lastC[hC]; lastC[hC] = x;
-                std::vector<u32> c;
-                u32 q = prevA[x]; for (u32 k = 0; k < kBtKA && q != kNone; k++) { c.push_back(q); q = prevA[q]; }
-                q = prevB[x]; for (u32 k = 0; k < kBtKB && q != kNone; k++) { c.push_back(q); q = prevB[q]; }
-                q = prevC[x]; for (u32 k = 0; k < kBtKC && q != kNone; k++) { c.push_back(q); q = prevC[q]; }
-                std::sort(c.begin(), c.end(), [](u32 u, u32 v) { return u > v; });
-                c.erase(std::unique(c.begin(), c.end()), c.end());
-                for (u32 k = 0; k < K && k < c.size(); k++) {
-                    P6[(size_t)x * K + k] = c[k];
-                    u32 l = 0;
-                    while (l < avail && lz[x + l] == lz[c[k] + l]) l++;
-                    L6[(size_t)x * K + k] = (u16)l;
-                }
+    for (const SubBlock &sb : subs) {
+        u32 sb_end = sb.x + sb.size;
+        for (u32 x = sb.x; x < sb_end; x++) {
+            u32 avail = sb_end - x;
+            u32 hA = hash6_at(lz, x, sb_end, wnd, bits), hB = hash_ctx_at(lz, x, sb_end, wnd, kBtCtxB, bits),
+                hC = hash_ctx_at(lz, x, sb_end, wnd, kBtCtxC, bits);
+            prevA[x] = lastA[hA]; lastA[hA] = x;
+            prevB[x] = lastB[hB]; lastB[hB] = x;
+            prevC[x] = lastC[hC]; lastC[hC] = x;
+            std::vector<u32> c;
+            u32 q = prevA[x]; for (u32 k = 0; k < kBtKA && q != kNone; k++) { c.push_back(q); q = prevA[q]; }
+            q = prevB[x]; for (u32 k = 0; k < kBtKB && q != kNone; k++) { c.push_back(q); q = prevB[q]; }
+            q = prevC[x]; for (u32 k = 0; k < kBtKC && q != kNone; k++) { c.push_back(q); q = prevC[q]; }
+            std::sort(c.begin(), c.end(), [](u32 u, u32 v) { return u > v; });
+            c.erase(std::unique(c.begin(), c.end()), c.end());
+            for (u32 k = 0; k < K && k < c.size(); k++) {
+                P6[(size_t)x * K + k] = c[k];
+                u32 l = 0;
+                while (l < avail && lz[x + l] == lz[c[k] + l]) l++;
+                L6[(size_t)x * K + k] = (u16)l;
             }
         }
-        a += seg[s];
     }
 }
 
-// nearest earlier position with equal (padded) HASH3 / HASH2 among the blocks not statically excluded
-void build_chain23_cpu(const u8 *lz, u32 n, const std::vector<u32> &seg, const std::vector<u32> &seg_blk0,
-                       const std::vector<u8> &nolz, int which, std::vector<u32> &P, std::vector<u16> &L) {
+// nearest earlier position with equal (padded) HASH3 / HASH2 among the sub-blocks not statically excluded
+void build_chain23_cpu(const u8 *lz, u32 n, const std::vector<SubBlock> &subs, u32 wnd, int which, std::vector<u32> &P,
+                       std::vector<u16> &L) {
     P.assign(n + 1, kNone);
     L.assign(n + 1, 0);
     std::vector<u32> last(which == 3 ? 65536 : 16384, kNone);
-    u32 a = 0;
-    for (u32 s = 0; s < seg.size(); s++) {
-        u32 b = seg_blk0[s];
-        for (u32 off = 0; off < seg[s]; off += kBlock, b++) {
-            u32 sb = seg[s] - off < kBlock ? seg[s] - off : kBlock;
-            u32 sb_end = a + off + sb;
-            if (nolz[b]) continue;
-            for (u32 x = a + off; x < sb_end; x++) {
-                u32 avail = sb_end - x;
-                u32 h = which == 3 ? hash3_padded(lz + x, avail) : hash2_padded(lz + x, avail);
-                u32 e = last[h];
-                last[h] = x;
-                if (e == kNone) continue;
-                P[x] = e;
-                u32 l = 0;
-                while (l < avail && lz[x + l] == lz[e + l]) l++;
-                L[x] = (u16)l;
-            }
+    for (const SubBlock &sb : subs) {
+        if (sb.flags & 1) continue;
+        u32 sb_end = sb.x + sb.size;
+        for (u32 x = sb.x; x < sb_end; x++) {
+            u32 avail = sb_end - x;
+            u32 h = which == 3 ? hash3_at(lz, x, sb_end, wnd) : hash2_at(lz, x, sb_end, wnd);
+            u32 e = last[h];
+            last[h] = x;
+            if (e == kNone) continue;
+            P[x] = e;
+            u32 l = 0;
+            while (l < avail && lz[x + l] == lz[e + l]) l++;
+            L[x] = (u16)l;
         }
-        a += seg[s];
     }
 }
 
 }  // namespace
 
+static int g_replans = 0;   // how often hs_encode had to plan again (tests look at it)
 struct StageDump { u32 *binfo, *bbpb; u8 *lz; u32 *P6; u16 *L6; u32 *Z2, *Z6; u8 *dict_ok; u32 *tail_dlt; bool on; };
 static StageDump g_dump = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false};
 
@@ -157,7 +142,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
     props_init(&p, dict_size, level);
     p.DLTFilter = flt_mask & 1; p.TXTFilter = (flt_mask >> 1) & 1; p.EXEFilter = (flt_mask >> 2) & 1;
     EncCfg cfg = cfg_from_props(&p);
-    if (n > cfg.wnd_size) return kErrUnsupported;
+    if ((u64)n + cfg.vld_rge >= 0xFFFFFFF0ull) return kErrUnsupported;   // MatchFinder::normalize (csc_mf.cpp:108-114) is not modelled
     std::vector<u8> res;
     Sink sink{&res};
     if (with_props) { u8 hdr[10]; write_props(&p, hdr); sink(hdr, 10); }
@@ -172,6 +157,11 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
             seg_blk0.push_back(nblk);
             nblk += (s + kBlock - 1) / kBlock;
         }
+        std::vector<u8> flip(nblk, 0);   // assumed outcomes of the duplicate-block test (plan.h); refined on kErrReplan
+        std::vector<u8> rc, bc, ev;
+        std::vector<SegOut> so;
+        u32 tn = 0;
+        for (;;) {
         std::vector<u8> lz(in, in + n);
         lz.resize(n + 64, 0);
         AnalyzerTables AT;
@@ -180,6 +170,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         build_dict_tables(DT);
         std::vector<u32> binfo(nblk), bbpb(nblk), tail_dlt(seg.size() * 5, 0);
         std::vector<u8> dict_ok(nblk, 0), nolz(nblk, 0);
+        std::vector<SubBlock> subs;
         u32 a = 0;
         bool use_filters = (cfg.flt_dlt + cfg.flt_txt + cfg.flt_exe) != 0;
         for (u32 s = 0; s < seg.size(); s++) {
@@ -189,8 +180,13 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
                 if (use_filters) analyze_block(lz.data() + a + off, sz, AT, &binfo[b], &bbpb[b], &tail_dlt[s * 5]);
                 else { binfo[b] = DT_NORMAL; bbpb[b] = 0; }
             }
-            std::vector<FilterRun> runs((seg[s] + kBlock - 1) / kBlock + 1);
-            u32 nr = plan_segment(binfo.data(), seg_blk0[s], a, seg[s], cfg.flt_dlt, cfg.flt_txt, cfg.flt_exe, runs.data(), nolz.data());
+            const u32 nb = (seg[s] + kBlock - 1) / kBlock;
+            std::vector<FilterRun> runs(nb + 1);
+            std::vector<SubBlock> sg(nb + wraps_inside(a, seg[s], cfg.wnd_size) + 1);
+            u32 nsg = 0;
+            u32 nr = plan_segment(binfo.data(), bbpb.data(), &tail_dlt[s * 5], flip.data(), seg_blk0[s], a, seg[s], cfg.wnd_size,
+                                  cfg.flt_dlt, cfg.flt_txt, cfg.flt_exe, runs.data(), nolz.data(), sg.data(), &nsg);
+            subs.insert(subs.end(), sg.begin(), sg.begin() + nsg);
             std::vector<u8> tmp;
             for (u32 r = 0; r < nr; r++) {
                 if (runs[r].kind == DT_EXE) e8e9_run(lz.data() + runs[r].off, runs[r].size, false);
@@ -204,12 +200,12 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         std::vector<u32> P6, Z2, Z6;
         std::vector<u16> L6;
         u32 K = cfg.ht_width;
-        build_mf_cpu(lz.data(), n, seg, cfg.ht_bits, K, P6, L6, Z2, Z6);
-        if (cfg.bounded) build_mf5_cpu(lz.data(), n, seg, P6, L6);
+        build_mf_cpu(lz.data(), n, subs, cfg.wnd_size, cfg.ht_bits, K, P6, L6, Z2, Z6);
+        if (cfg.bounded) build_mf5_cpu(lz.data(), n, subs, cfg.wnd_size, P6, L6);
         std::vector<u32> P3, P2;
         std::vector<u16> L3, L2;
-        build_chain23_cpu(lz.data(), n, seg, seg_blk0, nolz, 3, P3, L3);
-        build_chain23_cpu(lz.data(), n, seg, seg_blk0, nolz, 2, P2, L2);
+        build_chain23_cpu(lz.data(), n, subs, cfg.wnd_size, 3, P3, L3);
+        build_chain23_cpu(lz.data(), n, subs, cfg.wnd_size, 2, P2, L2);
         std::vector<u32> D23((n + 31) / 32 + 1, 0);
         if (g_dump.on) {
             memcpy(g_dump.binfo, binfo.data(), nblk * 4); memcpy(g_dump.bbpb, bbpb.data(), nblk * 4);
@@ -222,10 +218,11 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         std::vector<u16> p_lit(131072, 2048);
         std::vector<ApUnit> ap(kApLimit + 2);
         u32 rc_cap = n * 2 + 65536 * 2, bc_cap = n * 2 + 65536 * 2;
-        std::vector<u8> rc(rc_cap), bc(bc_cap), ev(rc_cap / 32768 + bc_cap / 32768 + 64);
-        std::vector<SegOut> so(seg.size());
+        rc.assign(rc_cap, 0); bc.assign(bc_cap, 0); ev.assign(rc_cap / 32768 + bc_cap / 32768 + 64, 0);
+        so.assign(seg.size(), SegOut());
         i32 status = 0;
-        u32 tn = 0;
+        u32 replan[2] = {0, 0};
+        tn = 0;
         EncStream S;
         memset(&S, 0, sizeof(S));
         std::vector<u8> tmpbuf(n + 64);
@@ -235,6 +232,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         S.tail_dlt = tail_dlt.data(); S.dict_ok = dict_ok.data();
         S.P6 = P6.data(); S.L6 = L6.data(); S.K = K ? K : 1; S.Z2 = Z2.data(); S.Z6 = Z6.data(); S.D6 = D6.data();
         S.P3 = P3.data(); S.L3 = L3.data(); S.P2 = P2.data(); S.L2 = L2.data(); S.D23 = D23.data(); S.blk_nolz = nolz.data();
+        S.flip = flip.data(); S.replan = replan;
         S.ht2 = ht2.data(); S.ht3 = ht3.data(); S.p_lit = p_lit.data(); S.p_delta = p_lit.data() + 65536; S.ap = ap.data();
         S.rc_out = rc.data(); S.rc_cap = rc_cap; S.bc_out = bc.data(); S.bc_cap = bc_cap;
         S.events = ev.data(); S.ev_cap = (u32)ev.size(); S.segout = so.data(); S.status = &status;
@@ -245,8 +243,11 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         E->run();
         delete E;
         delete M;
+        if (status == kErrReplan) { flip[replan[0]] = (u8)replan[1]; g_replans++; continue; }   // plan again with the observed outcome
         if (trace_n) *trace_n = tn;
         if (status < 0) return status;
+        break;
+        }
         for (u32 s = 0; s < seg.size(); s++)
             fr.segment(sink, rc.data() + so[s].rc_off, so[s].rc_len, bc.data() + so[s].bc_off, so[s].bc_len,
                        ev.data() + so[s].ev_off, so[s].ev_len);
@@ -257,6 +258,8 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
     memcpy(out, res.data(), res.size());
     return 0;
 }
+
+int hs_replans(void) { int r = g_replans; g_replans = 0; return r; }
 
 // Whole stream (with 10-byte props header) through the host-simulated decoder engine.
 int hs_decode(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_n) {

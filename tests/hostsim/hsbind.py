@@ -47,12 +47,13 @@ def _u8(a):
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
-def encode(data, dict_size, level, read_size=0, flt_mask=7, with_props=True, trace=False):
+def encode(data, dict_size, level, read_size=0, flt_mask=7, with_props=True, trace=False, cands=False):
     a = _u8(data)
+    trace = trace or cands   # the engine always records candidate lists when a trace buffer is given
     out = np.empty(a.size * 2 + (1 << 18), dtype=np.uint8)
     n = C.c_size_t(0)
     tn = C.c_size_t(0)
-    tr = np.zeros((a.size + 1024, 3), dtype=np.uint32) if trace else None
+    tr = np.zeros(((a.size + 1024) * (12 if cands else 1), 3), dtype=np.uint32) if trace else None
     r = lib().hs_encode(a.ctypes.data, a.size, dict_size, level, read_size, flt_mask, int(with_props),
                         out.ctypes.data, out.size, C.byref(n), tr.ctypes.data if trace else None,
                         tr.shape[0] if trace else 0, C.byref(tn))

@@ -117,6 +117,21 @@ def test_kernel_stages_match_host_simulation(gpu_lib, hs, level):
     assert (hst.tail_dlt[:5] == gst.tail_dlt[:5]).all()
 
 
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+def test_match_candidates_equal_reference_matchfinder(gpu_lib, ref, level):
+    """north_star part 1: the candidate list of EVERY find_match call of the device engine (lane-parallel
+    fm_lanes over the k_mf_* rows) equals the list the UNMODIFIED reference MatchFinder produces at the same
+    point of its parse (oracle/ref_mftrace.cpp intercepts FindMatch / FindMatchWithPrice at link time)."""
+    from csc_b200 import api
+    for name in ("mixed_small", "longmatch", "zero_runs", "dupblock", "exe_small", "text_small"):
+        d = EC[name]
+        rs, rt = ref.encode(d, d.size, level, cands=True)
+        gs, gt = api.encode_traced(d, d.size, level)
+        assert same(rs, gs), (name, level)
+        assert rt.shape == gt.shape and bool((rt == gt).all()), (name, level)
+        assert int((rt[:, 0] == 4).sum()) > 0
+
+
 def test_m5_bounded_search_is_ratio_gated(gpu_lib, ref, hs):
     """-m5 (binary tree in libcsc) runs as a bounded multi-context search: not stream-identical by design.
     Gates: the GPU stream equals the host simulation of the same search, decodes bit-exact with the
@@ -173,10 +188,95 @@ def test_malformed_streams_are_rejected(gpu_lib, ref):
         gpu_lib.decode_chunks([s], [d.size // 2])   # output capacity too small -> error, no overrun
 
 
+WRAP_CASES = [("mixed600k", lambda: synth.mixed(600000, 17), 40000, 0), ("mixed1M", lambda: EC["mixed_small"], 100000, 0),
+              ("text", lambda: synth.text(300000, 3), 33000, 0), ("dupblock", lambda: EC["dupblock"], 20000, 0),
+              ("dupdelta", lambda: EC["dupdelta"], 30000, 0), ("longmatch", lambda: EC["longmatch"], 50000, 0),
+              ("zero_runs", lambda: EC["zero_runs"], 40000, 0), ("exe_odd_reads", lambda: synth.exe(400000, 5), 70001, 30011)]
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+def test_window_wrap_streams_byte_identical(gpu_lib, ref, level):
+    """a stream longer than its dictionary (csc_lz.cpp:61-100: ring window, sub-blocks re-gridded at the window
+    end, stale-lap tail hashes): handle API and batched call, streams and candidate lists against the reference"""
+    from csc_b200 import api
+    for name, gen, dict_size, read_size in WRAP_CASES:
+        d = gen()
+        exp, rt = ref.encode(d, dict_size, level, read_size, cands=True)
+        got = gpu_lib.encode_stream(d, dict_size, level, read_size)
+        assert same(got, exp), (name, level)
+        assert same(gpu_lib.decode_stream(got), d), (name, level)
+        if not read_size:
+            g2, gt = api.encode_traced(d, dict_size, level)
+            assert same(g2, exp), (name, level)
+            assert rt.shape == gt.shape and bool((rt == gt).all()), (name, level)
+    assert gpu_lib.encode_chunks([EC["dupblock"]], 20000, 2)[0].size and gpu_lib.get_stats()["replans"] >= 1
+
+
+def test_config1_m1_d32m_64mib_single_chunk(gpu_lib, ref):
+    """BASELINE.json configs[0]: libcsc -m1 -d32m on a 64 MiB mixed buffer as ONE stream (the window wraps once):
+    byte-identical to the reference, and both decoders restore the input from either stream"""
+    d = synth.mixed(64 << 20, 12345)
+    exp = ref.encode(d, 32 << 20, 1)
+    got = gpu_lib.encode_chunks([d], 32 << 20, 1)[0]
+    assert same(got, exp)
+    assert same(gpu_lib.decode_chunks([exp], [d.size])[0], d)
+    assert same(ref.decode(got, d.size), d)
+
+
+def bench_text(total, rank=0):
+    tile = 32 << 20
+    return np.concatenate([synth.text(min(tile, total - off), 12345 + rank * 1000 + i) for i, off in enumerate(range(0, total, tile))])
+
+
+def test_config2_m2_text_bench_chunking_byte_identical(gpu_lib, ref):
+    """BASELINE.json configs[1] exactly as bench.py runs it: -m2 -d64m, English-like text, independent 368 KiB
+    chunks -- every stream of a 48 MiB slice byte-compared with the reference (bench.py re-checks a sample of
+    its own timed output as well)"""
+    chunk = 368 << 10
+    d = bench_text(48 << 20)
+    chunks = gpu_lib.split_chunks(d, chunk)
+    outs = gpu_lib.encode_chunks(chunks, 64 << 20, 2)
+    exp = ref.run_chunks(chunks, 64 << 20, 2, os.cpu_count() or 1)
+    assert all(same(o, e) for o, e in zip(outs, exp))
+
+
+@pytest.mark.parametrize("chunk", [368 << 10, 1 << 20])
+def test_config3_m3_mixed_chunked_byte_identical(gpu_lib, ref, chunk):
+    """BASELINE.json configs[2]: -m3 -d256m on the mixed corpus, chunked as the bench chunks it"""
+    d = synth.tiled("mixed", 24 << 20, tile=8 << 20)
+    chunks = gpu_lib.split_chunks(d, chunk)
+    outs = gpu_lib.encode_chunks(chunks, 256 << 20, 3)
+    exp = ref.run_chunks(chunks, 256 << 20, 3, os.cpu_count() or 1)
+    assert all(same(o, e) for o, e in zip(outs, exp))
+    back = gpu_lib.decode_chunks(outs, [c.size for c in chunks])
+    assert all(same(b, c) for b, c in zip(back, chunks))
+
+
 def test_unsupported_configurations_fail_loudly(gpu_lib):
+    """a binary tree AND a 6-byte table is a configuration CSCEncProps_Init never produces; the library refuses
+    it (-91) instead of guessing, and still drains the caller's input stream"""
+    from csc_b200 import api
+    l = api.lib()
+    p = gpu_lib.props_init(1 << 20, 5)
+    p.hash_width, p.hash_bits = 4, 20
     d = EC["mixed_small"]
-    with pytest.raises(RuntimeError):
-        gpu_lib.encode_stream(d, 65536, 1)   # stream longer than the window (wrap) is not supported yet
+    state = {"off": 0}
+
+    def rd(_p, buf, psize):
+        want = min(psize[0], d.size - state["off"])
+        if want:
+            C.memmove(buf, d.ctypes.data + state["off"], want)
+        state["off"] += want
+        psize[0] = want
+        return 0
+
+    ins = api._InStream(api.READ_FN(rd))
+    outs = api._OutStream(api.WRITE_FN(lambda _p, buf, size: size))
+    h = l.CSCEnc_Create(C.byref(p), C.byref(outs), None)
+    assert h
+    assert l.CSCEnc_Encode(h, C.byref(ins), None) == -91
+    assert state["off"] == d.size
+    l.CSCEnc_Destroy(h)
 
 
 def test_empty_and_tiny_inputs(gpu_lib, ref):

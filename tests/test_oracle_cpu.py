@@ -283,3 +283,61 @@ def test_reference_archiver_links_against_the_product(ref, tmp_path):
     if not csc_b200.available():
         r = subprocess.run([exe, "a", "-m2", "-t2", "-f", "gpu.csa"] + names, cwd=tmp_path, capture_output=True, text=True, timeout=60)
         assert "no CPU fallback" in r.stderr
+
+
+# ---------------------------------------------------------------- match finder, class level
+# north_star: "per-position match candidates bit-exact against the reference MatchFinder".  The reference
+# side is the UNMODIFIED MatchFinder with its two entry points intercepted at link time
+# (oracle/ref_mftrace.cpp); ours is the engine's candidate list of every find_match call.  The traces
+# interleave packets (0..3) with candidate records (4: position + count, 5: len + dist code), so equality
+# also pins WHERE along the parse each search happened.
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+@pytest.mark.parametrize("name", ["mixed_small", "text_small", "exe_small", "longmatch", "zero_runs", "dupblock"])
+def test_match_candidates_equal_reference_matchfinder(ref, hs, level, name):
+    d = EC[name]
+    rs, rt = ref.encode(d, d.size, level, cands=True)
+    hs_, ht = hs.encode(d, d.size, level, cands=True)
+    assert same(rs, hs_)
+    assert rt.shape == ht.shape and (rt == ht).all(), first_diff(rt, ht)
+    assert int((rt[:, 0] == 4).sum()) > 0
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    bad = np.nonzero((a[:n] != b[:n]).any(axis=1))[0]
+    i = int(bad[0]) if bad.size else n
+    return f"first differing trace record {i}: reference {a[i:i + 3].tolist()} vs ours {b[i:i + 3].tolist()}"
+
+
+# ---------------------------------------------------------------- window wrap (streams longer than their dictionary)
+# LZ::EncodeNormal re-grids the <= 8 KiB sub-blocks at the window end (csc_lz.cpp:65-66,91-92), tail hashes
+# read the previous lap's bytes, compares stop at the window end on the candidate's side
+# (csc_mf.cpp:268,307,338,460), and the optimal parser's literal context is dropped at window offset 0
+# (csc_lz.cpp:297).  Streams AND per-call candidate lists must equal the reference's.
+WRAP_CASES = [("mixed600k", lambda: synth.mixed(600000, 17), 40000, 0), ("mixed1M", lambda: EC["mixed_small"], 100000, 0),
+              ("text", lambda: synth.text(300000, 3), 33000, 0), ("dupblock", lambda: EC["dupblock"], 20000, 0),
+              ("dupdelta", lambda: EC["dupdelta"], 30000, 0), ("longmatch", lambda: EC["longmatch"], 50000, 0),
+              ("zero_runs", lambda: EC["zero_runs"], 40000, 0), ("exe_odd_reads", lambda: synth.exe(400000, 5), 70001, 30011)]
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+@pytest.mark.parametrize("case", WRAP_CASES, ids=[c[0] for c in WRAP_CASES])
+def test_window_wrap_matches_reference(ref, hs, case, level):
+    _, gen, dict_size, read_size = case
+    d = gen()
+    assert d.size > dict_size + 10240
+    rs, rt = ref.encode(d, dict_size, level, read_size, cands=True)
+    hs.lib().hs_replans()
+    hs_, ht = hs.encode(d, dict_size, level, read_size, cands=True)
+    assert same(rs, hs_)
+    assert rt.shape == ht.shape and (rt == ht).all(), first_diff(rt, ht)
+    assert same(hs.decode(hs_, d.size), d)
+
+
+def test_window_wrap_replans_on_duplicate_block_flips(ref, hs):
+    """the static sub-block grid assumes the outcome of IsDuplicateBlock; a wrong guess on a wrapped stream is
+    detected by the engine and planned again (plan.h / Encoder::compress_segment)"""
+    d = EC["dupblock"]
+    hs.lib().hs_replans()
+    assert same(hs.encode(d, 20000, 2), ref.encode(d, 20000, 2))
+    assert hs.lib().hs_replans() >= 1
