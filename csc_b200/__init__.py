@@ -7,7 +7,8 @@ that C ABI with ctypes for tests and bench.py.  There is no CPU fallback: if the
 library is missing or no CUDA device is usable, calls raise.
 """
 from .api import (CSCProps, available, decode_chunks, decode_stream, encode_bound, encode_chunks, encode_stream,
-                  get_stats, lib, props_init, set_device, split_chunks, EXPORTS)
+                  get_stats, lib, props_init, set_device, set_devices, device_count, split_chunks, EXPORTS)
 
 __all__ = ["CSCProps", "available", "decode_chunks", "decode_stream", "encode_bound", "encode_chunks",
-           "encode_stream", "get_stats", "lib", "props_init", "set_device", "split_chunks", "EXPORTS"]
+           "encode_stream", "get_stats", "lib", "props_init", "set_device", "set_devices", "device_count", "split_chunks",
+           "EXPORTS"]

@@ -20,7 +20,8 @@ _SO = os.environ.get("CSC_B200_LIB") or os.path.join(_HERE, "csrc", "libcsc_b200
 EXPORTS = ["CSCEncProps_Init", "CSCEnc_WriteProperties", "CSCEnc_EstMemUsage", "CSCEnc_Create", "CSCEnc_Destroy",
            "CSCEnc_Encode", "CSCEnc_Encode_Flush", "CSCDec_ReadProperties", "CSCDec_Create", "CSCDec_Destroy",
            "CSCDec_Decode", "CSCB200_EncodeBound", "CSCB200_EncodeChunks", "CSCB200_DecodeChunks",
-           "CSCB200_EncodeChunksDevice", "CSCB200_SetDevice", "CSCB200_GetStats", "CSCB200_Available"]
+           "CSCB200_EncodeChunksDevice", "CSCB200_SetDevice", "CSCB200_SetDevices", "CSCB200_DeviceCount", "CSCB200_Trim",
+           "CSCB200_GetStats", "CSCB200_Available"]
 
 
 class CSCProps(C.Structure):   # csc_common.h:19-63 (ABI)
@@ -96,6 +97,19 @@ def set_device(dev: int) -> None:
     r = lib().CSCB200_SetDevice(dev)
     if r < 0:
         raise RuntimeError(f"CSCB200_SetDevice({dev}) failed: {r}")
+
+
+def set_devices(devs) -> None:
+    """this thread's batched calls fan their chunks out over these GPUs (contiguous chunk ranges, no collective)"""
+    devs = list(devs)
+    arr = (C.c_int * max(len(devs), 1))(*devs)
+    r = lib().CSCB200_SetDevices(arr, len(devs))
+    if r < 0:
+        raise RuntimeError(f"CSCB200_SetDevices({devs}) failed: {r}")
+
+
+def device_count() -> int:
+    return int(lib().CSCB200_DeviceCount())
 
 
 def get_stats() -> dict:

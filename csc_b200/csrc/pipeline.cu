@@ -4,10 +4,10 @@
 //
 // There is NO CPU fallback: without a usable CUDA device every compute entry point fails.
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <stdio.h>
@@ -81,21 +81,33 @@ struct Timer {
 struct Ctx {
     bool init = false;
     int dev = -1;
+    bool busy = false;
     cudaStream_t st = nullptr;
     AnalyzerTables *d_AT = nullptr;
     DictTables *d_DT = nullptr;
     u32 *d_p2bits = nullptr;
     DevBuf packdesc, lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
-        cubtmp, dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
+        dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
         flip, replan, subdesc, subscratch, swnd;
     PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta, h_replan;
     Timer tm;
     CSCB200_Stats stats;
 };
 
-thread_local Ctx g_ctx;
-int g_device = -1;
+// Device contexts (stream, cached device / pinned buffers) are pooled per GPU and leased for the duration of one
+// API call: concurrent callers (csarc runs up to 8 worker threads, archiver/csarc.cpp:338-352) each get their own
+// context, sequential callers reuse one, and nothing is tied to the life of a thread.
+const int kMaxCtxPerDevice = 16;
+struct Pool {
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<Ctx *> all;
+} g_pool;
+thread_local int t_device = -1;                 // CSCB200_SetDevice: GPU of this thread's calls (-1: the current CUDA device)
+thread_local std::vector<int> t_devices;        // CSCB200_SetDevices: GPUs a batched call of this thread fans out over
+thread_local CSCB200_Stats t_stats;             // statistics of this thread's last call
+std::atomic<unsigned> g_rr{0};                  // round-robin of handles over the device list
 
 // debug: copy the intermediate arrays of a single-stream wave back to the host (tests only)
 struct DebugDump { u32 *binfo, *bbpb; u8 *lz; u32 *P6; u16 *L6; u32 *Z2, *Z6; u8 *dict_ok; u32 *tail_dlt; bool on; };
@@ -105,15 +117,16 @@ thread_local DebugDump g_dump = {nullptr, nullptr, nullptr, nullptr, nullptr, nu
 struct DebugTrace { u32 *buf; size_t cap; size_t *n_out; bool on; };
 thread_local DebugTrace g_trace = {nullptr, 0, nullptr, false};
 
-int ctx_init(Ctx &C) {
-    if (C.init) return 0;
+int device_count() {
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        fprintf(stderr, "csc_b200: no CUDA device available (this library has no CPU fallback)\n");
-        return kErrCuda;
-    }
-    if (g_device >= 0) CK(cudaSetDevice(g_device));
-    CK(cudaGetDevice(&C.dev));
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) return 0;
+    return ndev;
+}
+
+int ctx_init(Ctx &C, int dev) {
+    if (C.init) return 0;
+    CK(cudaSetDevice(dev));
+    C.dev = dev;
     CK(cudaStreamCreateWithFlags(&C.st, cudaStreamNonBlocking));
     AnalyzerTables AT;
     build_analyzer_tables(AT);
@@ -259,30 +272,17 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     r |= C.segsize.ensure((size_t)nseg * 4); r |= C.segblk0.ensure((size_t)nseg * 4);
     r |= C.sbits.ensure((size_t)ns * 4); r |= C.sgoff.ensure((size_t)ns * 8); r |= C.sK.ensure((size_t)ns * 4);
     if (r) return kErrCuda;
-    u32 stream_bits = 1;
-    while ((1u << stream_bits) < ns) stream_bits++;
-    const int end_bit = (int)(key_shift + stream_bits);
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, C.keys0.as<u64>(), C.keys1.as<u64>(), C.vals0.as<u32>(),
-                                    C.vals1.as<u32>(), (int)npos, 0, end_bit, st);
-    if (C.cubtmp.ensure(cub_bytes + 16)) return kErrCuda;
     if (C.rstiles.ensure((size_t)nrst * sizeof(RsTile)) || C.rsH.ensure((size_t)rsHn * 4 + 64) || C.rsB.ensure((size_t)rsNb * 4 + 64)) return kErrCuda;
     u32 launches = 1;
-    static const bool use_cub = getenv("CSC_B200_CUB_SORT") != nullptr;   // library sort only for A/B timing
     static bool smem_opt_in = false;
     if (!smem_opt_in) {
         CK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRsTile * 12)));
         smem_opt_in = true;
     }
     // sorts (keys0,vals0) by the low `hbits` key bits inside every stream; returns the buffers holding the result
-    auto sort_pairs = [&](u32 hbits, int cub_end_bit, u64 *&kres, u32 *&vres) -> int {
+    auto sort_pairs = [&](u32 hbits, u64 *&kres, u32 *&vres) -> int {
         u64 *ka = C.keys0.as<u64>(), *kb = C.keys1.as<u64>();
         u32 *va = C.vals0.as<u32>(), *vb = C.vals1.as<u32>();
-        if (use_cub) {
-            cub::DeviceRadixSort::SortPairs(C.cubtmp.p, cub_bytes, ka, kb, va, vb, (int)npos, 0, cub_end_bit, st);
-            kres = kb; vres = vb;
-            return 0;
-        }
         for (u32 shift = 0; shift < hbits; shift += 8) {
             const u32 bits = std::min<u32>(8, hbits - shift), mask = (1u << bits) - 1;
             rs_hist<<<nrst, kRsThreads, 0, st>>>(ka, C.rstiles.as<RsTile>(), shift, mask, C.rsH.as<u32>());
@@ -383,7 +383,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     T.mark(st);                                                                   // 4
     u64 *ksorted = nullptr;
     u32 *vsorted = nullptr;
-    sort_pairs(key_shift, end_bit, ksorted, vsorted);
+    sort_pairs(key_shift, ksorted, vsorted);
     T.mark(st);                                                                   // 5
     k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(),
                                                   C.P6.as<u32>(), pos_stream, bounded ? kBtKA : 0, bounded ? kBtRowK : 0, 0);
@@ -391,7 +391,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         for (u32 which = kBtCtxB; which <= kBtCtxC; which += kBtCtxC - kBtCtxB) {
             k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), key_shift,
                                                    C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
-            sort_pairs(key_shift, end_bit, ksorted, vsorted);
+            sort_pairs(key_shift, ksorted, vsorted);
             k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
                                                           pos_stream, which == kBtCtxB ? kBtKB : kBtKC, kBtRowK, which == kBtCtxB ? kBtKA : kBtKA + kBtKB);
         }
@@ -411,7 +411,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         u16 *L = which == 3 ? C.L3.as<u16>() : C.L2.as<u16>();
         k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), shift,
                                                C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
-        sort_pairs(shift, (int)(shift + stream_bits), ksorted, vsorted);
+        sort_pairs(shift, ksorted, vsorted);
         k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P, pos_stream, 1, 0, 0);
         k_mf_extend<1><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
     }
@@ -560,6 +560,7 @@ struct DecJob {
     int status;
     CSCProps props;
     DecInput di;
+    bool predeframed = false;      // di was filled block by block by the caller (handle API)
     std::vector<DecRun> runs;      // filled when want_runs
 };
 
@@ -574,11 +575,13 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
     for (u32 s = 0; s < ns; s++) {
         DecJob &J = *jobs[s];
         J.status = 0; J.out_size = 0;
-        if (J.n < CSC_PROP_SIZE) { J.status = -1; return -1; }
-        memset(&J.props, 0, sizeof(J.props));
-        read_props(&J.props, J.in);
+        if (!J.predeframed) {
+            if (J.n < CSC_PROP_SIZE) { J.status = -1; return -1; }
+            memset(&J.props, 0, sizeof(J.props));
+            read_props(&J.props, J.in);
+        }
         if (J.props.dict_size > 1024u * 1048576u || J.props.dict_size < 32 * 1024 || !J.props.csc_blocksize) { J.status = -1; return -1; }
-        if (deframe(J.in + CSC_PROP_SIZE, J.n - CSC_PROP_SIZE, J.props.csc_blocksize, J.di) < 0) { J.status = -1; return -1; }
+        if (!J.predeframed && deframe(J.in + CSC_PROP_SIZE, J.n - CSC_PROP_SIZE, J.props.csc_blocksize, J.di) < 0) { J.status = -1; return -1; }
         if (J.di.rc_off.size() < 2 || J.di.bc_off.size() < 2) { J.status = -1; return -1; }
         woff[s] = wtot; wtot = align_up(wtot + J.out_cap + 64, 256);
         rcoff[s] = rctot; rctot = align_up(rctot + J.di.rc.size(), 16);
@@ -649,7 +652,7 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
     for (u32 s = 0; s < ns; s++) {
         DecJob &J = *jobs[s];
         J.status = (i32)hm[s * 4 + 2];
-        if (J.status < 0) { ret = J.status; continue; }
+        if (J.status < 0) { ret = J.status; if (!want_runs) continue; }   // (the handle API still writes the runs decoded before the error)
         J.out_size = hm[s * 4 + 1];
         if (J.out_size) CK(cudaMemcpyAsync(J.out, C.dout.as<u8>() + woff[s], J.out_size, cudaMemcpyDeviceToHost, st));
         if (want_runs) {
@@ -667,47 +670,102 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
     return ret;
 }
 
-size_t mem_budget() {
+// ----------------------------------------------------------------------------- contexts
+// memory a wave may use on the leased context's device: what is free now plus what this context already holds
+size_t mem_budget(const Ctx &C) {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)8 << 30;
-    return tot - tot / 8;   // buffers are cached in the context, so budget against the whole device
+    size_t held = 0;
+    const DevBuf *b = &C.packdesc;
+    const DevBuf *e = &C.swnd + 1;   // the DevBuf members are declared contiguously
+    for (; b != e; b++) held += b->cap;
+    const size_t avail = fr + held;
+    return avail - avail / 8;
 }
 
-}  // namespace
-
-// =============================================================================== C ABI
-extern "C" {
-
-// tests only: capture the intermediate arrays of the next single-stream encode
-void CSCB200_DebugDump(uint32_t *binfo, uint32_t *bbpb, uint8_t *lz, uint32_t *P6, uint16_t *L6, uint32_t *Z2, uint32_t *Z6,
-                       uint8_t *dict_ok, uint32_t *tail_dlt) {
-    g_dump.binfo = binfo; g_dump.bbpb = bbpb; g_dump.lz = lz; g_dump.P6 = P6; g_dump.L6 = L6; g_dump.Z2 = Z2; g_dump.Z6 = Z6;
-    g_dump.dict_ok = dict_ok; g_dump.tail_dlt = tail_dlt; g_dump.on = binfo != nullptr;
+int pick_device() {   // device of this thread's next call, or a negative error
+    const int n = device_count();
+    if (n <= 0) {
+        fprintf(stderr, "csc_b200: no CUDA device available (this library has no CPU fallback)\n");
+        return kErrCuda;
+    }
+    int dev = t_device;
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return kErrCuda;
+    return dev < n ? dev : kErrCuda;
 }
 
-// tests only: record the packet / match-candidate trace of the next single-stream encode as (kind, a, b) triples
-void CSCB200_DebugTrace(uint32_t *buf, size_t cap_triples, size_t *n_out) {
-    g_trace.buf = buf; g_trace.cap = cap_triples; g_trace.n_out = n_out; g_trace.on = buf != nullptr;
+// devices a batched call of this thread fans out over: CSCB200_SetDevices, else the environment
+// (CSC_B200_DEVICES=all | 0,2,5 -- how an unmodified caller such as csarc is pointed at several GPUs), else one
+std::vector<int> device_list() {
+    std::vector<int> d = t_devices;
+    if (d.empty() && t_device < 0) {
+        const char *e = getenv("CSC_B200_DEVICES");
+        if (e && *e) {
+            const int n = device_count();
+            if (!strcmp(e, "all")) for (int i = 0; i < n; i++) d.push_back(i);
+            else for (const char *q = e; *q;) { char *end; long v = strtol(q, &end, 10); if (end == q) break; if (v >= 0 && v < n) d.push_back((int)v); q = *end ? end + 1 : end; }
+        }
+    }
+    if (d.empty()) { const int one = pick_device(); if (one >= 0) d.push_back(one); }
+    return d;
 }
 
-int CSCB200_Available(void) {
-    int n = 0;
-    return (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
-}
-int CSCB200_SetDevice(int device) {
-    g_device = device;
-    if (g_ctx.init && g_ctx.dev != device) return kErrUnsupported;   // context already bound on this thread
-    return 0;
-}
-void CSCB200_GetStats(CSCB200_Stats *out) { *out = g_ctx.stats; }
+struct Lease {
+    Ctx *c = nullptr;
+    int prev = -1;
+    explicit Lease(int dev) {
+        if (dev < 0) return;
+        cudaGetDevice(&prev);
+        std::unique_lock<std::mutex> lk(g_pool.m);
+        for (;;) {
+            int have = 0;
+            for (Ctx *x : g_pool.all) {
+                if (x->dev != dev) continue;
+                have++;
+                if (!x->busy) { c = x; break; }
+            }
+            if (c) break;
+            if (have < kMaxCtxPerDevice) { c = new Ctx; c->dev = dev; g_pool.all.push_back(c); break; }
+            g_pool.cv.wait(lk);
+        }
+        c->busy = true;
+        lk.unlock();
+        if (ctx_init(*c, dev) < 0) { release(); return; }
+        cudaSetDevice(dev);   // every entry point runs on its context's device, whatever the caller selected meanwhile
+        memset(&c->stats, 0, sizeof(c->stats));
+    }
+    void release() {
+        if (!c) return;
+        { std::lock_guard<std::mutex> lk(g_pool.m); c->busy = false; }
+        g_pool.cv.notify_one();
+        c = nullptr;
+    }
+    ~Lease() {
+        if (c) t_stats = c->stats;
+        release();
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    Lease(const Lease &) = delete;
+    Lease &operator=(const Lease &) = delete;
+};
 
-size_t CSCB200_EncodeBound(size_t n) { return n + n / 4 + (n / 65536 + 8) * 8 + 256; }
+void add_stats(CSCB200_Stats &a, const CSCB200_Stats &b) {   // devices work side by side: times are the slowest device's
+    double *x = &a.ms_h2d;
+    const double *y = &b.ms_h2d;
+    for (int i = 0; i < 14; i++) x[i] = std::max(x[i], y[i]);
+    a.bytes_in += b.bytes_in; a.bytes_out += b.bytes_out; a.mf_positions += b.mf_positions;
+    a.kernel_launches += b.kernel_launches; a.streams += b.streams; a.waves += b.waves; a.replans += b.replans;
+}
 
-static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
-                              int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size, bool device) {
-    Ctx &C = g_ctx;
-    if (ctx_init(C)) return kErrCuda;
-    memset(&C.stats, 0, sizeof(C.stats));
+// chunks [lo, hi) of n for device k of g: contiguous ranges, chunk c belongs to device c * g / n
+void chunk_range(int n, int k, int g, int &lo, int &hi) {
+    lo = (int)(((long long)n * k + g - 1) / g);
+    hi = (int)(((long long)n * (k + 1) + g - 1) / g);
+}
+
+// ----------------------------------------------------------------------------- batched encode on one device
+int encode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
+                     int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size, bool device) {
     if (n <= 0) return 0;
     std::vector<EncJob> jobs(n);
     for (int i = 0; i < n; i++) {
@@ -722,20 +780,18 @@ static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_
         C.stats.bytes_in += J.n;
     }
     // waves: as many streams as fit the memory budget (largest first inside a wave for balance)
-    const size_t budget = mem_budget();
+    const size_t budget = mem_budget(C);
     const u32 K = cfg_from_props(&jobs[0].props).ht_width;   // (-m5: width of the bounded-search rows)
-    std::vector<int> order(n);
-    for (int i = 0; i < n; i++) order[i] = i;
     int ret = 0;
     size_t at = 0;
     std::vector<EncJob *> again;   // streams whose static plan has to be redone (kErrReplan)
-    while (at < order.size() || !again.empty()) {
+    while (at < jobs.size() || !again.empty()) {
         std::vector<EncJob *> wave;
         if (!again.empty()) wave.swap(again);
         const bool fresh = wave.empty();
         size_t bytes = 0, pos = 0;
-        while (fresh && at < order.size()) {
-            EncJob &J = jobs[order[at]];
+        while (fresh && at < jobs.size()) {
+            EncJob &J = jobs[at];
             size_t need = per_stream_bytes() + (size_t)J.n * per_pos_bytes(K) + 4096;
             if (!wave.empty() && (bytes + need > budget || pos + J.n > 0x70000000ull)) break;
             bytes += need; pos += J.n;
@@ -794,28 +850,16 @@ static int encode_chunks_impl(int n, const uint8_t *const *in, const size_t *in_
     return ret;
 }
 
-int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
-                         int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size) {
-    return encode_chunks_impl(n, in, in_size, dict_size, level, flt_mask, with_props, out, out_cap, out_size, false);
-}
-
-int CSCB200_EncodeChunksDevice(int n, const uint8_t *const *d_in, const size_t *in_size, uint32_t dict_size, int level,
-                               int flt_mask, int with_props, size_t *out_size) {
-    return encode_chunks_impl(n, d_in, in_size, dict_size, level, flt_mask, with_props, nullptr, nullptr, out_size, true);
-}
-
-int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out, const size_t *out_cap,
-                         size_t *out_size) {
-    Ctx &C = g_ctx;
-    if (ctx_init(C)) return kErrCuda;
-    memset(&C.stats, 0, sizeof(C.stats));
+int decode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out, const size_t *out_cap,
+                     size_t *out_size) {
     if (n <= 0) return 0;
     std::vector<DecJob> jobs(n);
     for (int i = 0; i < n; i++) {
+        if (out_cap[i] >= 0xFFFF0000ull) return kErrUnsupported;
         jobs[i].in = in[i]; jobs[i].n = in_size[i]; jobs[i].out = out[i]; jobs[i].out_cap = out_cap[i];
         C.stats.bytes_in += in_size[i];
     }
-    const size_t budget = mem_budget();
+    const size_t budget = mem_budget(C);
     int ret = 0;
     size_t at = 0;
     while (at < jobs.size()) {
@@ -835,12 +879,122 @@ int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
     return ret;
 }
 
+// Runs fn(context, lo, hi) for the chunk range of every device of this thread's device list, side by side
+// (one host thread and one leased context per GPU; no data-path collective, results are already in chunk order).
+template <class Fn> int fan_out(int n, bool may_split, Fn fn) {
+    std::vector<int> devs = device_list();
+    if (devs.empty()) return kErrCuda;
+    if (!may_split || n < 2) devs.resize(1);
+    if ((int)devs.size() > n) devs.resize(std::max(n, 1));
+    const int g = (int)devs.size();
+    if (g == 1) {
+        Lease L(devs[0]);
+        if (!L.c) return kErrCuda;
+        return fn(*L.c, 0, n);
+    }
+    std::vector<int> rets(g, 0);
+    std::vector<CSCB200_Stats> st(g);
+    std::vector<std::thread> th;
+    for (int k = 0; k < g; k++)
+        th.emplace_back([&, k]() {
+            int lo, hi;
+            chunk_range(n, k, g, lo, hi);
+            Lease L(devs[k]);
+            if (!L.c) { rets[k] = kErrCuda; return; }
+            rets[k] = fn(*L.c, lo, hi);
+            st[k] = L.c->stats;
+        });
+    for (auto &t : th) t.join();
+    memset(&t_stats, 0, sizeof(t_stats));
+    int ret = 0;
+    for (int k = 0; k < g; k++) { add_stats(t_stats, st[k]); if (rets[k] < 0 && !ret) ret = rets[k]; }
+    return ret;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+// tests only: capture the intermediate arrays of the next single-stream encode
+void CSCB200_DebugDump(uint32_t *binfo, uint32_t *bbpb, uint8_t *lz, uint32_t *P6, uint16_t *L6, uint32_t *Z2, uint32_t *Z6,
+                       uint8_t *dict_ok, uint32_t *tail_dlt) {
+    g_dump.binfo = binfo; g_dump.bbpb = bbpb; g_dump.lz = lz; g_dump.P6 = P6; g_dump.L6 = L6; g_dump.Z2 = Z2; g_dump.Z6 = Z6;
+    g_dump.dict_ok = dict_ok; g_dump.tail_dlt = tail_dlt; g_dump.on = binfo != nullptr;
+}
+
+// tests only: record the packet / match-candidate trace of the next single-stream encode as (kind, a, b) triples
+void CSCB200_DebugTrace(uint32_t *buf, size_t cap_triples, size_t *n_out) {
+    g_trace.buf = buf; g_trace.cap = cap_triples; g_trace.n_out = n_out; g_trace.on = buf != nullptr;
+}
+
+int CSCB200_Available(void) { return device_count() > 0 ? 1 : 0; }
+int CSCB200_DeviceCount(void) { return device_count(); }
+
+int CSCB200_SetDevice(int device) {
+    if (device >= device_count()) return kErrUnsupported;   // (a failed call leaves the selection untouched)
+    t_device = device < 0 ? -1 : device;
+    t_devices.clear();
+    return 0;
+}
+int CSCB200_SetDevices(const int *devices, int n) {
+    const int have = device_count();
+    for (int i = 0; i < n; i++) if (devices[i] < 0 || devices[i] >= have) return kErrUnsupported;
+    t_devices.assign(devices, devices + std::max(n, 0));
+    return 0;
+}
+void CSCB200_GetStats(CSCB200_Stats *out) { *out = t_stats; }
+
+// release the cached device / pinned memory of every idle context (a long-lived host process calls this between jobs)
+void CSCB200_Trim(void) {
+    std::lock_guard<std::mutex> lk(g_pool.m);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (Ctx *c : g_pool.all) {
+        if (c->busy || !c->init) continue;
+        cudaSetDevice(c->dev);
+        for (DevBuf *b = &c->packdesc; b != &c->swnd + 1; b++) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+        for (PinBuf *b = &c->h_segout; b != &c->h_replan + 1; b++) { if (b->p) cudaFreeHost(b->p); b->p = nullptr; b->cap = 0; }
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+size_t CSCB200_EncodeBound(size_t n) { return n + n / 4 + (n / 65536 + 8) * 8 + 256; }
+
+int CSCB200_EncodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
+                         int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size) {
+    return fan_out(n, true, [&](Ctx &C, int lo, int hi) {
+        return encode_chunks_on(C, hi - lo, in + lo, in_size + lo, dict_size, level, flt_mask, with_props, out + lo, out_cap + lo, out_size + lo, false);
+    });
+}
+
+int CSCB200_EncodeChunksDevice(int n, const uint8_t *const *d_in, const size_t *in_size, uint32_t dict_size, int level,
+                               int flt_mask, int with_props, size_t *out_size) {
+    return fan_out(n, false, [&](Ctx &C, int lo, int hi) {   // the inputs live on one device: no fan-out
+        return encode_chunks_on(C, hi - lo, d_in + lo, in_size + lo, dict_size, level, flt_mask, with_props, nullptr, nullptr, out_size + lo, true);
+    });
+}
+
+int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out, const size_t *out_cap,
+                         size_t *out_size) {
+    return fan_out(n, true, [&](Ctx &C, int lo, int hi) {
+        return decode_chunks_on(C, hi - lo, in + lo, in_size + lo, out + lo, out_cap + lo, out_size + lo);
+    });
+}
+
 // ------------------------------------------------------------------- libcsc handle API
+// A handle owns no device state: every call leases a context.  One handle = one serially dependent stream
+// (SURVEY.md H1), so the stream's whole history is kept on the host and a further CSCEnc_Encode call codes the
+// stream again from its start and emits only the new segments (csa_worker.cpp / csc.cpp call it once).
 struct EncHandle {
     CSCProps props;
     ISeqOutStream *os;
     Framer *fr;
-    bool used;
+    int dev;
+    std::vector<u8> data;        // everything read so far
+    std::vector<u32> segs;       // one entry per Read() = per flush segment (csc_enc.cpp:169-176)
+    std::vector<u8> flip;        // duplicate-block outcomes learned so far (plan.h)
+    size_t segs_done;            // segments already framed and written
     uint64_t outsize;
 };
 
@@ -850,10 +1004,13 @@ uint64_t CSCEnc_EstMemUsage(const CSCProps *p) { return est_mem_usage(p); }
 
 CSCEncHandle CSCEnc_Create(const CSCProps *props, ISeqOutStream *outstream, ISzAlloc *alloc) {
     (void)alloc;   // device memory is managed by the library; host scratch uses the C++ heap
-    if (ctx_init(g_ctx)) return NULL;
+    if (!props) return NULL;
+    const std::vector<int> devs = device_list();
+    if (devs.empty()) return NULL;
     EncHandle *h = new (std::nothrow) EncHandle;
     if (!h) return NULL;
-    h->props = *props; h->os = outstream; h->used = false; h->outsize = 0;
+    h->props = *props; h->os = outstream; h->segs_done = 0; h->outsize = 0;
+    h->dev = devs[devs.size() > 1 ? g_rr.fetch_add(1) % devs.size() : 0];   // handles of one process spread over the device list
     h->fr = new Framer(props->csc_blocksize);
     return h;
 }
@@ -874,8 +1031,7 @@ struct CbSink {
 
 int CSCEnc_Encode(CSCEncHandle p, ISeqInStream *is, ICompressProgress *progress) {
     EncHandle *h = (EncHandle *)p;
-    Ctx &C = g_ctx;
-    if (ctx_init(C) || !h) {
+    if (!h || device_count() <= 0) {
         // Callers such as libcsc/csc.cpp do not check CSCEnc_Create's result, and csarc feeds the stream from
         // a producer thread that blocks until its queue is read: consume the input before failing.
         if (is) {
@@ -885,37 +1041,43 @@ int CSCEnc_Encode(CSCEncHandle p, ISeqInStream *is, ICompressProgress *progress)
         return kErrCuda;
     }
     if (!is) return kErrCuda;
-    // pull the whole input, one Read() of raw_blocksize per flush segment (csc_enc.cpp:169-176)
-    std::vector<u8> data;
-    EncJob J;
-    J.props = h->props; J.status = 0;
+    // pull the input, one Read() of raw_blocksize per flush segment (csc_enc.cpp:169-176)
+    std::vector<u8> &data = h->data;
     uint64_t insize = 0;
+    const size_t segs_before = h->segs.size();
     for (;;) {
         size_t want = h->props.raw_blocksize;
         size_t old = data.size();
         data.resize(old + want);
         size_t got = want;
         int rr = is->Read(is, data.data() + old, &got);
-        if (rr < 0) return READ_ERROR;
+        if (rr < 0) { data.resize(old); return READ_ERROR; }
         data.resize(old + got);
         if (!got) break;
-        J.segs.push_back((u32)got);
+        h->segs.push_back((u32)got);
         insize += got;
         if (progress) progress->Progress(progress, insize, h->outsize);
         if (data.size() >= 0xF0000000ull) return kErrUnsupported;
     }
-    if (data.empty()) return 0;
-    if (h->used) return kErrUnsupported;   // one data-carrying Encode per handle in this version
-    h->used = true;
+    if (h->segs.size() == segs_before) return 0;
+    EncJob J;
+    J.props = h->props; J.status = 0; J.segs = h->segs; J.flip = h->flip;
     J.in = data.data(); J.n = (u32)data.size();
-    memset(&C.stats, 0, sizeof(C.stats));
+    Lease L(h->dev);
+    if (!L.c) return kErrCuda;
+    Ctx &C = *L.c;
     std::vector<EncJob *> wave{&J};
     int r;
     do { r = encode_wave(C, wave); } while (r >= 0 && J.status == kErrReplan);   // wrapped window: plan again (plan.h)
     if (r < 0) return r;
+    h->flip = J.flip;
     CbSink sink{h->os, false, 0};
-    frame_job(J, *h->fr, sink);
-    for (const SegOut &o : J.so) h->outsize += o.rc_len + o.bc_len;
+    for (size_t sgi = h->segs_done; sgi < J.so.size(); sgi++) {
+        const SegOut &o = J.so[sgi];
+        h->fr->segment(sink, const_cast<u8 *>(J.rc) + o.rc_off, o.rc_len, J.bc + o.bc_off, o.bc_len, J.ev + o.ev_off, o.ev_len);
+        h->outsize += o.rc_len + o.bc_len;
+    }
+    h->segs_done = J.so.size();
     if (progress) progress->Progress(progress, insize, h->outsize);
     return sink.fail ? WRITE_ERROR : 0;
 }
@@ -931,61 +1093,110 @@ int CSCEnc_Encode_Flush(CSCEncHandle p) {
 struct DecHandle {
     CSCProps props;
     ISeqInStream *is;
+    int dev;
 };
 
 void CSCDec_ReadProperties(CSCProps *props, uint8_t *s) { read_props(props, s); }
 
 CSCDecHandle CSCDec_Create(const CSCProps *props, ISeqInStream *instream, ISzAlloc *alloc) {
     (void)alloc;
-    if (props->dict_size > 1024u * 1048576u || props->dict_size < 32 * 1024) return NULL;
-    if (ctx_init(g_ctx)) return NULL;
+    if (!props || props->dict_size > 1024u * 1048576u || props->dict_size < 32 * 1024) return NULL;
+    const std::vector<int> devs = device_list();
+    if (devs.empty()) return NULL;
     DecHandle *h = new (std::nothrow) DecHandle;
     if (!h) return NULL;
     h->props = *props; h->is = instream;
+    h->dev = devs[devs.size() > 1 ? g_rr.fetch_add(1) % devs.size() : 0];
     return h;
 }
 void CSCDec_Destroy(CSCDecHandle p) { delete (DecHandle *)p; }
 
+// exactly `n` bytes from the caller's stream (the reference asks for header, size and payload separately and
+// never for more than the framing announces: csc_memio.cpp:19-57); false on a short read
+static bool read_exact(ISeqInStream *is, u8 *dst, size_t n) {
+    size_t have = 0;
+    while (have < n) {
+        size_t got = n - have;
+        if (is->Read(is, dst + have, &got) < 0 || !got) return false;
+        have += got;
+    }
+    return true;
+}
+
+// Pulls framed blocks up to and including the next candidate for the stream's last segment: a 6-byte RC block
+// followed by the 3-byte BC block 19 00 00, which is what EncodeInt(SIG_EOF) + Flush leave behind
+// (csc_encoder_main.cpp:149-157).  Returns 1 at such a pair, 0 when the input ended first, -1 on bad framing.
+static int pull_until_eof_pair(ISeqInStream *is, u32 bsize, DecInput &d) {
+    u32 prev_rc6 = 0;
+    for (;;) {
+        u8 fb;
+        if (!read_exact(is, &fb, 1)) return 0;
+        u32 sz = bsize;
+        if (!((fb >> 6) & 1)) {
+            u8 sb[3];
+            if (!read_exact(is, sb, 3)) return -1;
+            sz = ((u32)sb[0] << 16) + ((u32)sb[1] << 8) + sb[2];
+        }
+        if (!sz || sz > bsize) return -1;   // "must be a abnormal stream" (csc_memio.cpp:43-46)
+        std::vector<u8> &v = (fb >> 7) ? d.rc : d.bc;
+        std::vector<u32> &off = (fb >> 7) ? d.rc_off : d.bc_off;
+        const size_t at = v.size();
+        off.push_back((u32)at);
+        v.resize(at + sz);
+        if (!read_exact(is, v.data() + at, sz)) return -1;
+        if (fb >> 7) { prev_rc6 = (sz == 6) ? 1 : 0; continue; }
+        if (prev_rc6 && sz == 3 && v[at] == 0x19 && v[at + 1] == 0 && v[at + 2] == 0) return 1;
+        prev_rc6 = 0;
+    }
+}
+
 int CSCDec_Decode(CSCDecHandle p, ISeqOutStream *os, ICompressProgress *progress) {
     DecHandle *h = (DecHandle *)p;
-    Ctx &C = g_ctx;
-    if (ctx_init(C)) return kErrCuda;
-    // the compressed stream is pulled to its end, then decoded on the device in one go
-    std::vector<u8> comp(CSC_PROP_SIZE);
-    write_props(&h->props, comp.data());
-    for (;;) {
-        size_t want = 1 << 20, old = comp.size();
-        comp.resize(old + want);
-        size_t got = want;
-        int rr = h->is->Read(h->is, comp.data() + old, &got);
-        comp.resize(old + (rr < 0 ? 0 : got));
-        if (rr < 0) return READ_ERROR;
-        if (!got) break;
-    }
-    memset(&C.stats, 0, sizeof(C.stats));
-    size_t cap = std::max<size_t>(comp.size() * 8, (size_t)16 << 20);
+    if (!h || !os || !h->is) return kErrCuda;
+    if (device_count() <= 0) return kErrCuda;
+    // The compressed stream is pulled block by block, never past its final segment (a caller's stream may block
+    // or carry other data behind it), then decoded on the device in one go.  The raw size is not part of the
+    // stream: the output capacity is a guess that grows until the decoder fits.
+    DecInput di;
+    size_t cap = 0;
     std::vector<u8> out;
     DecJob J;
+    Lease L(h->dev);
+    if (!L.c) return kErrCuda;
+    Ctx &C = *L.c;
     for (;;) {
-        out.resize(cap);
-        J = DecJob();
-        J.in = comp.data(); J.n = comp.size(); J.out = out.data(); J.out_cap = cap;
-        std::vector<DecJob *> wave{&J};
-        int r = decode_wave(C, wave, true);
-        if (r == kErrOverflow && cap < ((size_t)3 << 30)) { cap *= 4; continue; }   // raw size is not in the stream: grow and redo
-        if (r < 0) return r;
-        break;
+        const int pr = pull_until_eof_pair(h->is, h->props.csc_blocksize, di);
+        if (pr < 0) return -1;
+        if (di.rc_off.empty() || di.bc_off.empty()) return pr ? -1 : READ_ERROR;
+        const size_t comp = di.rc.size() + di.bc.size();
+        if (!cap) cap = std::min<size_t>(std::max<size_t>(comp * 12, (size_t)32 << 20), 0xFFFF0000ull - 64);
+        int r;
+        for (;;) {
+            out.resize(cap);
+            J = DecJob();
+            J.props = h->props; J.predeframed = true; J.in = nullptr; J.n = comp;
+            J.di.rc = di.rc; J.di.bc = di.bc; J.di.rc_off = di.rc_off; J.di.bc_off = di.bc_off;
+            J.di.rc_off.push_back((u32)J.di.rc.size()); J.di.bc_off.push_back((u32)J.di.bc.size());
+            J.di.rc.resize(J.di.rc.size() + 16, 0); J.di.bc.resize(J.di.bc.size() + 16, 0);
+            J.out = out.data(); J.out_cap = cap;
+            std::vector<DecJob *> wave{&J};
+            r = decode_wave(C, wave, true);
+            if (r == kErrOverflow && cap < 0xFFFF0000ull - 64) { cap = std::min<size_t>(cap * 6, 0xFFFF0000ull - 64); continue; }
+            break;
+        }
+        // ran out of blocks before SIG_EOF although the pair looked like the end (a 6 + 3 byte segment in mid-stream): pull on
+        if ((r == kErrRead || r == -1) && pr == 1) continue;
+        uint64_t done = 0;
+        for (const DecRun &rn : J.runs) {   // one Write per decoded run, as CSCDec_Decode does (csc_dec.cpp:767); also ahead of an error
+            if (!rn.size) continue;
+            done += rn.size;
+            if (progress) progress->Progress(progress, comp, done);
+            size_t w = os->Write(os, out.data() + rn.off, rn.size);
+            if (w == CSC_WRITE_ABORT) return 0;
+            if (w < rn.size) return WRITE_ERROR;
+        }
+        return r < 0 ? r : 0;
     }
-    uint64_t done = 0;
-    for (const DecRun &rn : J.runs) {   // one Write per decoded run, as CSCDec_Decode does (csc_dec.cpp:767)
-        if (!rn.size) continue;
-        done += rn.size;
-        if (progress) progress->Progress(progress, comp.size(), done);
-        size_t w = os->Write(os, out.data() + rn.off, rn.size);
-        if (w == CSC_WRITE_ABORT) break;
-        if (w < rn.size) return WRITE_ERROR;
-    }
-    return 0;
 }
 
 }  // extern "C"

@@ -8,7 +8,7 @@
  * per-handle API (csc_enc.h / csc_dec.h) produces -- they are additive, plain
  * C-ABI (pointers and sizes, no CUDA or torch types), and never touch CSCProps'
  * layout.  Host buffers may be pageable or pinned; device selection is by
- * CSCB200_SetDevice (default: current CUDA device).
+ * CSCB200_SetDevice / CSCB200_SetDevices (default: current CUDA device).
  */
 #ifndef _CSC_B200_H_
 #define _CSC_B200_H_
@@ -40,7 +40,19 @@ int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
 int CSCB200_EncodeChunksDevice(int n, const uint8_t *const *d_in, const size_t *in_size, uint32_t dict_size, int level,
                                int flt_mask, int with_props, size_t *out_size);
 
+/* GPU selection.  Every call runs on a device context leased from a per-GPU pool for the duration of the call, so
+ * handles and batched calls may be used from any number of threads (csarc: one handle per worker thread).
+ *   CSCB200_SetDevice(d)      this thread's calls run on GPU d (-1: the thread's current CUDA device, the default)
+ *   CSCB200_SetDevices(v, n)  this thread's batched calls split their chunks into n contiguous ranges, one per GPU
+ *                             of v, coded side by side (chunk c -> v[c * n / chunks]; no collective, results stay
+ *                             in chunk order); handles created by this thread are spread round-robin over v
+ * Without either call the environment variable CSC_B200_DEVICES ("all" or "0,1,5") plays the role of SetDevices:
+ * that is how an unmodified caller is given several GPUs. */
 int CSCB200_SetDevice(int device);
+int CSCB200_SetDevices(const int *devices, int n);
+int CSCB200_DeviceCount(void);
+/* Frees the device and pinned memory cached by idle contexts. */
+void CSCB200_Trim(void);
 
 /* Timing / launch statistics of the last Encode/Decode call on this thread's context. */
 typedef struct {
