@@ -34,7 +34,7 @@ class CSCProps(C.Structure):   # csc_common.h:19-63 (ABI)
 class Stats(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("ms_h2d", "ms_analyze", "ms_filters", "ms_mf_hash", "ms_mf_sort", "ms_mf_rows",
                                           "ms_mf_extend", "ms_encode", "ms_d2h", "ms_frame", "ms_decode", "ms_unfilter",
-                                          "ms_total_gpu", "ms_mf_chains")] + \
+                                          "ms_total_gpu", "ms_mf_chains", "ms_rc")] + \
                [(k, C.c_uint64) for k in ("bytes_in", "bytes_out", "mf_positions")] + \
                [(k, C.c_uint32) for k in ("kernel_launches", "streams", "waves", "replans")]
 

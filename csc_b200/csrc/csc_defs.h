@@ -110,12 +110,20 @@ struct ModelSmall {
 };
 static const u32 kSlotGlobal = 0x80000000u;   // slot id flag: index into p_lit/p_delta (global), else u16 index into ModelSmall
 
-// per-segment output record written by the encoder engine, read by host framing
+// Per-segment output record, read by host framing.  The parser / model engine (enc_engine.cuh) fills the
+// decision and raw-bit fields, the range-coder pass (rc_engine.cuh) the rc_* fields.  Block completions are
+// logged with a time stamp so that the host can replay their temporal order (H4): 2 * d for a BC block that
+// filled after d decisions of the segment, 2 * i + 1 for an RC block that filled while decision i was coded
+// (i = dec_len for the flush bytes).
 struct SegOut {
-    u32 rc_off, rc_len;   // bytes of the range-coder sub-stream of this segment
-    u32 bc_off, bc_len;   // bytes of the raw-bit sub-stream of this segment
-    u32 ev_off, ev_len;   // block-completion events ('R'=1, 'B'=0) in temporal order
+    u32 rc_off, rc_len;     // bytes of the range-coder sub-stream of this segment
+    u32 bc_off, bc_len;     // bytes of the raw-bit sub-stream of this segment
+    u32 dec_off, dec_len;   // binary decisions of this segment (DecEntry), dec_off 8-aligned
+    u32 rev_off, rev_len;   // RC block completions (time stamps)
+    u32 bev_off, bev_len;   // BC block completions (time stamps)
 };
+// one binary decision handed from the model to the range coder: probability (12 bits) | bit << 15
+typedef u16 DecEntry;
 
 // per-stream descriptor handed to the encoder engine (all device pointers)
 struct EncStream {
@@ -155,7 +163,8 @@ struct EncStream {
     // outputs
     u8 *rc_out; u32 rc_cap;
     u8 *bc_out; u32 bc_cap;
-    u8 *events; u32 ev_cap;
+    DecEntry *dec; u32 dec_cap;          // decisions of the whole stream, in coding order
+    u32 *rc_ev; u32 *bc_ev; u32 ev_cap;  // block-completion time stamps (each ev_cap entries)
     SegOut *segout;        // [nseg]
     i32 *status;           // 0 ok, <0 error
     u32 *trace; u32 trace_cap; u32 *trace_n;   // optional symbol trace (debug), may be null

@@ -62,11 +62,11 @@ struct MfCtx {
 struct Encoder {
     const EncStream &S;
     ModelSmall &M;
-    // range coder (csc_coder.h:44-50)
-    u64 low;
-    u32 range, cachesize, cache;
+    // The range-coder registers (csc_coder.h:44-50) do not live here: the engine hands every binary decision
+    // (probability + bit) to the range-coder pass of rc_engine.cuh, which runs after it.  Only the raw-bit
+    // coder stays, because its output is a pure function of the packet sequence.
     u32 bc_bits, bc_val;
-    u32 rc_n, rc_blk, bc_n, bc_blk, ev_n;
+    u32 dec_n, bc_n, bc_blk, bev_n;
     u32 bq_n, bq_bits;
     // model (csc_model.h)
     u32 state, ctx, lp_rebuild;
@@ -78,11 +78,7 @@ struct Encoder {
     u32 vld, W, K, good;
     bool tmode, want_tables;   // 2-/3-byte tables: false = chains + liveness bits, true = real tables (after a flip)
     bool wrap;                 // the stream is longer than its window: ring semantics apply (csc_lz.cpp:91-92)
-    // parser -> coder command ring (two-warp pipeline of the lazy modes); null = execute in place
-    uint4 *ring;
-    volatile u32 *vhead, *vtail;
-    u32 ring_cap, head, tail;
-    u32 seg_rc0, seg_bc0, seg_ev0;
+    u32 seg_dec0, seg_bc0, seg_bev0;
 
     CSC_HD Encoder(const EncStream &s, ModelSmall &m) : S(s), M(m) {}
     CSC_HDF MfCtx mfctx() const {
@@ -96,19 +92,14 @@ struct Encoder {
     }
 
     // ------------------------------------------------------------------ output
-    CSC_HD void event(u32 kind) {
-        if (ev_n < S.ev_cap) S.events[ev_n] = (u8)kind; else err = kErrOverflow;
-        ev_n++;
-    }
-    CSC_HD void put_rc(u32 b) {
-        if (rc_n < S.rc_cap) S.rc_out[rc_n] = (u8)b; else err = kErrOverflow;
-        rc_n++;
-        if (++rc_blk == S.cfg.csc_blocksize) { event(1); rc_blk = 0; }   // csc_coder.cpp:97-104
-    }
-    CSC_HD void put_bc(u32 b) {
+    CSC_HD void put_bc(u32 b, u32 stamp) {
         if (bc_n < S.bc_cap) S.bc_out[bc_n] = (u8)b; else err = kErrOverflow;
         bc_n++;
-        if (++bc_blk == S.cfg.csc_blocksize) { event(0); bc_blk = 0; }   // BCWCheckBound
+        if (++bc_blk == S.cfg.csc_blocksize) {   // BCWCheckBound: a 64 KiB BC block completed
+            if (bev_n < S.ev_cap) S.bc_ev[bev_n] = stamp; else err = kErrOverflow;
+            bev_n++;
+            bc_blk = 0;
+        }
     }
     CSC_HD void trace(u32 k, u32 a, u32 b) {
         if (S.trace) {
@@ -116,7 +107,6 @@ struct Encoder {
             tr_n++;
         }
     }
-
     // debug: the candidate list of one find_match call as (4, position, n) + n x (5, len, dist code) records,
     // the same records oracle/ref_mftrace.cpp takes from the reference MatchFinder
     CSC_HDN void trace_cands(u32 x, u32 n) {
@@ -124,29 +114,16 @@ struct Encoder {
         for (u32 i = 0; i < n; i++) trace(5, M.cl[i], M.cd[i]);
     }
 
-    // ------------------------------------------------------------- range coder
+    // ------------------------------------------------------------- binary decisions
     CSC_HD void coder_reset() {
-        low = 0; range = 0xFFFFFFFFu; cachesize = 1; cache = 0;
-        bc_bits = 0; bc_val = 0; rc_blk = 0; bc_blk = 0;
+        bc_bits = 0; bc_val = 0; bc_blk = 0;
         bq_n = 0; bq_bits = 0;
-    }
-    CSC_HDN void shift_low() {   // csc_coder.cpp:89-112
-        if ((u32)low < 0xFF000000u || (u32)(low >> 32) != 0) {
-            u32 t = cache;
-            u32 carry = (u32)(low >> 32);
-            do {
-                put_rc((t + carry) & 0xFF);
-                t = 0xFF;
-            } while (--cachesize != 0);
-            cache = ((u32)low >> 24) & 0xFF;
-        }
-        cachesize++;
-        low = (u64)((u32)low << 8);
     }
     // EncodeBit (csc_coder.h:67-81) is split in two.  The adaptive-probability half of a decision
     // (load p, adapt, store) does not depend on the coder registers, so a packet first QUEUES its
     // decisions (slot id + bit); flush_bits() then lets lane k fetch/adapt/store probability k (one
-    // memory round trip for the whole packet) and runs only the range/low recurrence serially.
+    // memory round trip for the whole packet) and appends (p, bit) to the stream's decision list.
+    // The range / low recurrence itself is the range-coder pass (rc_engine.cuh).
     // A queue never holds the same slot twice (callers flush in between), and it is flushed before
     // any raw-bit write so that RC/BC block events keep their temporal order (H4).
     CSC_HDF void q_push(u32 slot, u32 bit) {
@@ -158,65 +135,29 @@ struct Encoder {
         q_push((u32)(&pr - reinterpret_cast<u16 *>(&M)), bit);
     }
     CSC_HDF void enc_bit_g(u32 gidx, u32 bit) { q_push(kSlotGlobal | gidx, bit); }   // p_lit / p_delta entry
-    CSC_HDN void rc_block_full() { event(1); }   // cold: a 64 KiB RC block completed (csc_coder.cpp:97-104)
     CSC_HDN void flush_bits() {
         const u32 n = w_uni_u32(bq_n);
         if (!n) return;
         const u32 bits = bq_bits;
-        u32 v = 0;   // probability of decision `lane` (device) / scratch (host)
+        if (dec_n + n > S.dec_cap) { err = kErrOverflow; bq_n = 0; bq_bits = 0; return; }
 #if defined(__CUDA_ARCH__)
         if (CSC_LANE < n) {
-            u32 slot = M.bq[CSC_LANE];
+            const u32 slot = M.bq[CSC_LANE];
             u16 *pp = (slot & kSlotGlobal) ? S.p_lit + (slot & ~kSlotGlobal) : reinterpret_cast<u16 *>(&M) + slot;
-            v = *pp;
-            *pp = (u16)(((bits >> CSC_LANE) & 1) ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
+            const u32 v = *pp, bit = (bits >> CSC_LANE) & 1;
+            *pp = (u16)(bit ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
+            S.dec[dec_n + CSC_LANE] = (DecEntry)(v | (bit << 15));
         }
 #else
         for (u32 k = 0; k < n; k++) {
-            u32 slot = M.bq[k];
+            const u32 slot = M.bq[k];
             u16 *pp = (slot & kSlotGlobal) ? S.p_lit + (slot & ~kSlotGlobal) : reinterpret_cast<u16 *>(&M) + slot;
-            u32 pv = *pp;
-            *pp = (u16)(((bits >> k) & 1) ? pv + ((0xFFFu - pv) >> 5) : pv - (pv >> 5));
-            M.bq_p[k] = (u16)pv;
+            const u32 pv = *pp, bit = (bits >> k) & 1;
+            *pp = (u16)(bit ? pv + ((0xFFFu - pv) >> 5) : pv - (pv >> 5));
+            S.dec[dec_n + k] = (DecEntry)(pv | (bit << 15));
         }
 #endif
-        // the serial part: range/low recurrence with the whole coder state in registers
-        u64 lo = low;
-        u32 rg = range, cs = cachesize, ca = cache, on = rc_n, ob = rc_blk;
-        u8 *const out = S.rc_out;
-        const u32 cap = S.rc_cap, bsz = S.cfg.csc_blocksize;
-#pragma unroll 1
-        for (u32 k = 0; k < n; k++) {
-#if defined(__CUDA_ARCH__)
-            const u32 p = __shfl_sync(0xFFFFFFFFu, v, k);
-#else
-            const u32 p = M.bq_p[k];
-#endif
-            const u32 bound = (rg >> 12) * p;
-            if ((bits >> k) & 1) rg = bound;
-            else { lo += bound; rg -= bound; }
-            if (w_uni(rg < (1u << 24))) {   // RC_ShiftLow, csc_coder.cpp:89-112
-                rg <<= 8;
-                if (w_uni((u32)lo < 0xFF000000u || (u32)(lo >> 32) != 0)) {
-                    u32 t = ca;
-                    const u32 carry = (u32)(lo >> 32);
-                    do {
-                        if (on < cap) out[on] = (u8)(t + carry); else err = kErrOverflow;
-                        on++;
-                        if (w_uni(++ob == bsz)) {   // a 64 KiB RC block completed (csc_coder.cpp:97-104)
-                            if (ev_n < S.ev_cap) S.events[ev_n] = 1; else err = kErrOverflow;
-                            ev_n++;
-                            ob = 0;
-                        }
-                        t = 0xFF;
-                    } while (w_uni(--cs != 0));
-                    ca = ((u32)lo >> 24) & 0xFF;
-                }
-                cs++;
-                lo = (u64)((u32)lo << 8);
-            }
-        }
-        low = lo; range = rg; cachesize = cs; cache = ca; rc_n = on; rc_blk = ob;
+        dec_n += n;
         w_sync();
         bq_n = 0; bq_bits = 0;
     }
@@ -225,7 +166,7 @@ struct Encoder {
         bc_val = (bc_val << len) | val;
         bc_bits += len;
         while (bc_bits >= 8) {
-            put_bc((bc_val >> (bc_bits - 8)) & 0xFF);
+            put_bc((bc_val >> (bc_bits - 8)) & 0xFF, 2 * (dec_n - seg_dec0));   // after dec_n - seg_dec0 decisions of the segment
             bc_bits -= 8;
         }
     }
@@ -233,19 +174,19 @@ struct Encoder {
         if (len <= 16) direct16(val, len);
         else { direct16(val >> 16, len - 16); direct16(val & 0xFFFF, 16); }
     }
-    CSC_HDN void flush_segment(u32 seg, u32 rc0, u32 bc0, u32 ev0) {   // csc_coder.cpp:40-74
+    CSC_HDN void flush_segment(u32 seg) {   // csc_coder.cpp:40-74 (the RC half is RcCoder::flush)
         flush_bits();
-        for (int i = 0; i < 5; i++) shift_low();
-        // one byte is skipped, not stored (H3): the host substitutes the stale ring byte
-        if (rc_n < S.rc_cap) S.rc_out[rc_n] = 0; else err = kErrOverflow;
-        rc_n++; rc_blk++;
-        put_bc((bc_val << (8 - bc_bits)) & 0xFF);
-        put_bc(0);
         SegOut so;
-        so.rc_off = rc0; so.rc_len = rc_n - rc0;
-        so.bc_off = bc0; so.bc_len = bc_n - bc0;
-        so.ev_off = ev0; so.ev_len = ev_n - ev0;
-        S.segout[seg] = so;
+        so.dec_off = seg_dec0; so.dec_len = dec_n - seg_dec0;
+        // the two pad bytes of the raw-bit coder follow the five flush bytes of the range coder in time
+        put_bc((bc_val << (8 - bc_bits)) & 0xFF, 2 * (so.dec_len + 1));
+        put_bc(0, 2 * (so.dec_len + 1));
+        so.rc_off = 0; so.rc_len = 0; so.rev_off = 0; so.rev_len = 0;
+        so.bc_off = seg_bc0; so.bc_len = bc_n - seg_bc0;
+        so.bev_off = seg_bev0; so.bev_len = bev_n - seg_bev0;
+        if (CSC_LANE == 0) S.segout[seg] = so;
+        dec_n = (dec_n + 7u) & ~7u;   // the next segment's decisions start on a 16-byte boundary
+        seg_dec0 = dec_n; seg_bc0 = bc_n; seg_bev0 = bev_n;
         coder_reset();
     }
 
@@ -274,31 +215,20 @@ struct Encoder {
     CSC_HDN void encode_literal(u32 c) {   // csc_model.cpp:169-183
         trace(0, c, 0);
 #if defined(__CUDA_ARCH__)
-        // device fast path: the 9 decisions (flag + 8 tree nodes) are known up front, lane k owns decision k;
-        // probabilities are fetched/adapted in parallel and the range recurrence is unrolled over shuffles
+        // device fast path: the 9 decisions (flag + 8 tree nodes) are known up front, lane k owns decision k
         const u32 cc = w_uni_u32(c) | 0x100;   // (the reduction also tells the compiler the warp is converged here)
         const u32 lane = CSC_LANE;
-        u32 v = 0;
+        if (dec_n + 9 > S.dec_cap) { err = kErrOverflow; return; }
         if (lane < 9) {
             u16 *pp = lane == 0 ? &M.p_state[state * 3] : S.p_lit + ctx * 256 + (cc >> (9 - lane));
-            v = *pp;
+            const u32 v = *pp;
             const u32 bit = lane == 0 ? 0u : (cc >> (8 - lane)) & 1u;
             *pp = (u16)(bit ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
+            S.dec[dec_n + lane] = (DecEntry)(v | (bit << 15));
         }
+        dec_n += 9;
         state = (state * 4) & 0x3F;
         ctx = c;
-        u64 lo = low;
-        u32 rg = range;
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const u32 p = __shfl_sync(0xFFFFFFFFu, v, k);
-            const u32 bound = (rg >> 12) * p;
-            const bool bit = k == 0 ? false : ((cc >> (8 - k)) & 1u) != 0;
-            if (bit) rg = bound;
-            else { lo += bound; rg -= bound; }
-            if (w_uni(rg < (1u << 24))) { rg <<= 8; low = lo; shift_low(); lo = low; }
-        }
-        low = lo; range = rg;
         __syncwarp();
 #else
         enc_bit(M.p_state[state * 3 + 0], 0);
@@ -819,11 +749,8 @@ struct Encoder {
         }
     }
 
-    // ---------------------------------------------------- parser -> coder commands
-    // The lazy parser never reads model or coder state, so for -m1/-m2 the stream is cut in two:
-    // one warp parses and emits packet commands, a second warp of the same CTA runs the adaptive
-    // coder on them (k_encode, pair mode).  With ring == nullptr (optimal parser, host simulation)
-    // a command is executed on the spot.
+    // ---------------------------------------------------- packets
+    // The parsers hand packets to the model through emit(); a packet is executed on the spot.
     enum : u32 { OP_LIT = 1, OP_MATCH, OP_REP, OP_REP01, OP_INT, OP_BAD, OP_ENTROPY, OP_DELTA, OP_FLUSH, OP_END };
     CSC_HDN void exec(u32 op, u32 a, u32 b, u32 c) {
         if (err) return;
@@ -837,57 +764,12 @@ struct Encoder {
             case OP_ENTROPY: entropy_run(a, b); break;
             case OP_DELTA: delta_run(a, b, c); break;
             case OP_FLUSH:
-                flush_segment(a, seg_rc0, seg_bc0, seg_ev0);
-                seg_rc0 = rc_n; seg_bc0 = bc_n; seg_ev0 = ev_n;
+                flush_segment(a);
                 break;
             default: break;
         }
     }
-#if defined(__CUDACC__)
-    __device__ __forceinline__ bool spin(volatile u32 *flag, u32 mine, bool want_equal) {   // false on watchdog expiry
-        long long t0 = clock64();
-        while ((*flag == mine) == want_equal) {
-            __nanosleep(40);
-            if (clock64() - t0 > 8000000000ll) return false;   // ~4 s: never hang the GPU
-        }
-        return true;
-    }
-    __device__ __noinline__ void ring_push(u32 op, u32 a, u32 b, u32 c) {
-        if (head - tail >= ring_cap) {   // refresh our view of the consumer, wait while full
-            tail = *vtail;
-            if (head - tail >= ring_cap) {
-                if (!spin(vtail, tail, true)) { err = kErrUnsupported; return; }
-                tail = *vtail;
-            }
-        }
-        ring[head % ring_cap] = make_uint4(op, a, b, c);
-        __threadfence();
-        head++;
-        __syncwarp();
-        if (CSC_LANE == 0) *vhead = head;
-    }
-    __device__ __noinline__ uint4 ring_pop() {
-        if (tail == head) {
-            head = *vhead;
-            if (tail == head) {
-                if (!spin(vhead, tail, true)) { err = kErrUnsupported; return make_uint4(OP_END, (u32)kErrUnsupported, 0, 0); }
-                head = *vhead;
-            }
-        }
-        __threadfence();
-        uint4 v = __ldcg(&ring[tail % ring_cap]);
-        tail++;
-        __syncwarp();
-        if (CSC_LANE == 0) *vtail = tail;
-        return v;
-    }
-#endif
-    CSC_HDF void emit(u32 op, u32 a, u32 b, u32 c) {
-#if defined(__CUDA_ARCH__)
-        if (ring) { ring_push(op, a, b, c); return; }
-#endif
-        exec(op, a, b, c);
-    }
+    CSC_HDF void emit(u32 op, u32 a, u32 b, u32 c) { exec(op, a, b, c); }
 
     // ------------------------------------------------------------- lazy parser
     CSC_HDN void encode_nonlit(Cand u, u32 newctx) {   // csc_lz.cpp:127-154 (+ SetLiteralCtx of the caller)
@@ -1361,9 +1243,8 @@ struct Encoder {
         w_sync();
         for (u32 i = CSC_LANE; i < 64; i += CSC_NLANES) M.dsum[i] = 0;
         w_sync();
-        rc_n = bc_n = ev_n = 0;
-        seg_rc0 = seg_bc0 = seg_ev0 = 0;
-        head = tail = 0;
+        dec_n = bc_n = bev_n = 0;
+        seg_dec0 = seg_bc0 = seg_bev0 = 0;
         coder_reset();
         state = 0; ctx = 0; lp_rebuild = 0;
         rep[0] = rep[1] = rep[2] = rep[3] = S.cfg.wnd_size;   // csc_lz.cpp:46-49
@@ -1375,9 +1256,8 @@ struct Encoder {
             a += S.seg_size[s];
         }
     }
-    // whole stream in one warp (optimal parser, host simulation)
+    // whole stream in one warp
     CSC_HD void run() {
-        ring = nullptr;
         init_common();
         model_reset();
         parse_stream();
@@ -1386,25 +1266,6 @@ struct Encoder {
             if (S.trace_n) *S.trace_n = tr_n;
         }
     }
-#if defined(__CUDACC__)
-    // pair mode: this warp parses and feeds the ring
-    __device__ void run_parser() {
-        init_common();
-        parse_stream();
-        ring_push(OP_END, (u32)err, 0, 0);
-    }
-    // pair mode: this warp owns the model and the coder
-    __device__ void run_coder() {
-        init_common();
-        model_reset();
-        for (;;) {
-            uint4 c = ring_pop();
-            if (c.x == OP_END) { if (!err && (i32)c.y < 0) err = (i32)c.y; break; }
-            exec(c.x, c.y, c.z, c.w);
-        }
-        if (CSC_LANE == 0) *S.status = err;
-    }
-#endif
 };
 
 }  // namespace cscb

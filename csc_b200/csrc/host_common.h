@@ -188,6 +188,17 @@ struct Framer {
 };
 
 
+// Temporal order of a segment's block completions (1 = RC block, 0 = BC block) from the two time-stamp
+// lists the device passes keep (csc_defs.h: SegOut); RC stamps are odd, BC stamps even.
+inline void merge_events(const u32 *rc_ev, u32 nr, const u32 *bc_ev, u32 nb, std::vector<u8> &ev) {
+    ev.clear();
+    u32 i = 0, j = 0;
+    while (i < nr || j < nb) {
+        if (j >= nb || (i < nr && rc_ev[i] < bc_ev[j])) { ev.push_back(1); i++; }
+        else { ev.push_back(0); j++; }
+    }
+}
+
 // ---- MemIO de-framing (csc_memio.cpp:5-81) ---------------------------------------
 // Splits a libcsc stream (after the 10-byte header) into the concatenated RC and BC block
 // payloads plus the payload start offset of every block (+ one sentinel).

@@ -8,7 +8,8 @@
 //   k_mf_rows      sorted (stream,hash,pos) -> K nearest earlier same-hash positions per position
 //   k_mf_extend    forward match length of every (position, candidate) pair, capped at the
 //                  sub-block end                               (csc_mf.cpp:470, 8 B words)
-//   k_encode       one stream per warp: enc_engine.cuh
+//   k_encode       one stream per warp: enc_engine.cuh (parser + adaptive model -> decision lists)
+//   k_rc           one stream per thread: rc_engine.cuh (range-coder recurrence over the decision lists)
 //   k_decode       one stream per warp: dec_engine.cuh
 //   k_unfilter     inverse e8e9 / dictionary per decoded run   (csc_filters.cpp:337,600)
 //
@@ -21,6 +22,7 @@
 #include "blocks.cuh"
 #include "plan.h"
 #include "enc_engine.cuh"
+#include "rc_engine.cuh"
 #include "dec_engine.cuh"
 #include "radix_sort.cuh"
 
@@ -718,29 +720,14 @@ k_encode(const EncStream *__restrict__ streams, u32 ns, u32 *queue, const u32 *_
     }
 }
 
-// Pair mode for the lazy parsers (-m1/-m2): warp 2p parses stream s and feeds a command ring, warp
-// 2p+1 runs the adaptive coder on it.  The lazy parser never reads model state, so the two halves
-// of the serial work overlap, twice as many warps hide latency, and each warp's hot code is smaller.
-static const u32 kRingCap = 1024;
-__global__ void __launch_bounds__(kEncWarps * 32)
-k_encode_pair(const EncStream *__restrict__ streams, u32 ns, uint4 *rings) {
-    __shared__ ModelSmall sm[kEncWarps / 2];
-    __shared__ volatile u32 s_head[kEncWarps / 2], s_tail[kEncWarps / 2];
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 pair = warp >> 1, role = warp & 1;
-    const u32 gpair = blockIdx.x * (kEncWarps / 2) + pair, npairs = gridDim.x * (kEncWarps / 2);
-    for (u32 s = gpair; s < ns; s += npairs) {
-        asm volatile("bar.sync %0, 64;" ::"r"(pair + 1));
-        if (role == 0 && lane == 0) { s_head[pair] = 0; s_tail[pair] = 0; }
-        asm volatile("bar.sync %0, 64;" ::"r"(pair + 1));
-        EncStream S = streams[s];
-        Encoder E(S, sm[pair]);
-        E.ring = rings + (size_t)gpair * kRingCap;
-        E.ring_cap = kRingCap;
-        E.vhead = &s_head[pair];
-        E.vtail = &s_tail[pair];
-        if (role == 0) E.run_parser(); else E.run_coder();
-    }
+// The range-coder pass: one stream per thread, one warp per CTA so that the few hundred warps of a wave spread
+// over all SMs (the pass is a serial dependency chain per stream: latency, not throughput).
+__global__ void __launch_bounds__(32)
+k_rc(const EncStream *__restrict__ streams, u32 ns) {
+    const u32 s = blockIdx.x * 32 + threadIdx.x;
+    if (s >= ns) return;
+    RcCoder R;
+    R.run(streams[s]);
 }
 
 static const int kDecWarps = 4;

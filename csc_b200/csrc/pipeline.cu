@@ -88,9 +88,9 @@ struct Ctx {
     u32 *d_p2bits = nullptr;
     DevBuf packdesc, lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
-        dwnd, dout, doffs, druns, dmeta, doutptr, rings, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
-        flip, replan, subdesc, subscratch, swnd;
-    PinBuf h_segout, h_status, h_ev, h_rc, h_bc, h_meta, h_replan;
+        dwnd, dout, doffs, druns, dmeta, doutptr, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
+        flip, replan, subdesc, subscratch, rcev, bcev, dec, swnd;
+    PinBuf h_segout, h_status, h_rcev, h_bcev, h_rc, h_bc, h_meta, h_replan;
     Timer tm;
     CSCB200_Stats stats;
 };
@@ -169,7 +169,8 @@ struct EncJob {
     int status;
     // results (host, pinned staging): filled by encode_wave
     std::vector<SegOut> so;
-    const u8 *rc, *bc, *ev;
+    const u8 *rc, *bc;
+    const u32 *rc_ev, *bc_ev;   // block-completion time stamps (SegOut::rev_off / bev_off index these)
 };
 
 // ----------------------------------------------------------------------------- encode
@@ -181,7 +182,9 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     cudaStream_t st = C.st;
     // ---- layout
     std::vector<u64> goff(ns);
-    std::vector<u32> seg0(ns), sbits(ns), sK(ns), swnd(ns), sblk0(ns), rcoff(ns), bcoff(ns), rccap(ns), evcap(ns), evoff(ns);
+    std::vector<u32> seg0(ns), sbits(ns), sK(ns), swnd(ns), sblk0(ns), rcoff(ns), bcoff(ns), rccap(ns), evcap(ns), evoff(ns), deccap(ns);
+    std::vector<u64> decoff(ns);
+    u64 dectot = 0;
     std::vector<BlockDesc> blks;
     std::vector<SegDesc> segs;
     std::vector<u32> segsize, segblk0;
@@ -224,9 +227,15 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         rccap[s] = (u32)align_up((size_t)J.n + J.n / 8 + 66000, 16);
         rcoff[s] = (u32)rctot; bcoff[s] = (u32)rctot;
         rctot += rccap[s];
-        evcap[s] = (2 * rccap[s]) / 65536 + 8;
+        evcap[s] = rccap[s] / 65536 + 8;
         evoff[s] = (u32)evtot;
         evtot += evcap[s];
+        // decision list: at most 9 binary decisions per input byte (a literal), 8-entry alignment per segment
+        const u64 dc = (u64)J.n * 9 + 64 * (u64)J.segs.size() + 1024;
+        if (dc >= 0xFFFFFFF0ull) return kErrUnsupported;
+        deccap[s] = (u32)dc;
+        decoff[s] = dectot;
+        dectot += (dc + 7) & ~7ull;
         if (rctot >= 0xFFFF0000ull || total >= 0xFFFF0000ull) return kErrUnsupported;
     }
     const u32 nblk = (u32)blks.size(), nseg = (u32)segs.size(), npos = cpos;
@@ -262,7 +271,8 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     r |= C.ht.ensure((size_t)ns * 81920 * 4);
     r |= C.plit.ensure((size_t)ns * 131072 * 2);
     r |= C.ap.ensure((size_t)ns * (kApLimit + 2) * sizeof(ApUnit));
-    r |= C.rc.ensure(rctot); r |= C.bc.ensure(rctot); r |= C.ev.ensure(evtot);
+    r |= C.rc.ensure(rctot); r |= C.bc.ensure(rctot); r |= C.rcev.ensure(evtot * 4 + 16); r |= C.bcev.ensure(evtot * 4 + 16);
+    r |= C.dec.ensure(dectot * sizeof(DecEntry) + 16);
     r |= C.segout.ensure((size_t)nseg * sizeof(SegOut)); r |= C.status.ensure((size_t)ns * 4);
     r |= C.blkdesc.ensure((size_t)nblk * sizeof(BlockDesc)); r |= C.segdesc.ensure((size_t)nseg * sizeof(SegDesc));
     r |= C.binfo.ensure((size_t)nblk * 4); r |= C.bbpb.ensure((size_t)nblk * 4);
@@ -319,7 +329,8 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         S.ap = C.ap.as<ApUnit>() + (size_t)s * (kApLimit + 2);
         S.rc_out = C.rc.as<u8>() + rcoff[s]; S.rc_cap = rccap[s];
         S.bc_out = C.bc.as<u8>() + bcoff[s]; S.bc_cap = rccap[s];
-        S.events = C.ev.as<u8>() + evoff[s]; S.ev_cap = evcap[s];
+        S.dec = C.dec.as<DecEntry>() + decoff[s]; S.dec_cap = deccap[s];
+        S.rc_ev = C.rcev.as<u32>() + evoff[s]; S.bc_ev = C.bcev.as<u32>() + evoff[s]; S.ev_cap = evcap[s];
         S.segout = C.segout.as<SegOut>() + seg0[s];
         S.status = C.status.as<i32>() + s;
     }
@@ -444,26 +455,25 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         }
     } trace_fetch{C, tracing, st};
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, C.dev);
-    const bool pair_mode = es[0].cfg.lz_mode == 2 && getenv("CSC_B200_PAIR");   // experimental: measured slower in round 1
-    if (pair_mode) {
-        u32 grid = std::min<u32>((ns + kEncWarps / 2 - 1) / (kEncWarps / 2), (u32)nsm * 16);
-        if (C.rings.ensure((size_t)grid * (kEncWarps / 2) * kRingCap * sizeof(uint4))) return kErrCuda;
-        k_encode_pair<<<grid, kEncWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns, C.rings.as<uint4>());
-    } else {
+    {
         u32 grid = std::min<u32>((ns + kEncWarps - 1) / kEncWarps, (u32)nsm * 8);
         k_encode<<<grid, kEncWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns, d_queue, C.d_p2bits);
     }
     T.mark(st);                                                                   // 9
-    launches += 1;
+    k_rc<<<(ns + 31) / 32, 32, 0, st>>>(C.streams.as<EncStream>(), ns);
+    T.mark(st);                                                                   // 10
+    launches += 2;
     CK(cudaGetLastError());
     // ---- results
-    if (C.h_segout.ensure((size_t)nseg * sizeof(SegOut)) || C.h_status.ensure((size_t)ns * 4) || C.h_ev.ensure(evtot + 16) ||
+    if (C.h_segout.ensure((size_t)nseg * sizeof(SegOut)) || C.h_status.ensure((size_t)ns * 4) || C.h_rcev.ensure(evtot * 4 + 16) ||
+        C.h_bcev.ensure(evtot * 4 + 16) ||
         C.h_replan.ensure((size_t)ns * 8))
         return kErrCuda;
     CK(cudaMemcpyAsync(C.h_segout.p, C.segout.p, (size_t)nseg * sizeof(SegOut), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(C.h_status.p, C.status.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(C.h_replan.p, C.replan.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(C.h_ev.p, C.ev.p, evtot, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(C.h_rcev.p, C.rcev.p, evtot * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(C.h_bcev.p, C.bcev.p, evtot * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const SegOut *hso = C.h_segout.as<SegOut>();
     const i32 *hst = C.h_status.as<i32>();
@@ -500,7 +510,8 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         PackDesc &d = pd[s];
         memset(&d, 0, sizeof(d));
         if (jobs[s]->status < 0) continue;
-        jobs[s]->ev = C.h_ev.as<u8>() + evoff[s];
+        jobs[s]->rc_ev = C.h_rcev.as<u32>() + evoff[s];
+        jobs[s]->bc_ev = C.h_bcev.as<u32>() + evoff[s];
         if (jobs[s]->no_payload) continue;
         any_payload = true;
         d.rc_src = rcoff[s]; d.rc_dst = hrcoff[s]; d.rc_n = rcn[s];
@@ -518,22 +529,25 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         if (hbc) CK(cudaMemcpyAsync(C.h_bc.p, C.keys1.p, hbc, cudaMemcpyDeviceToHost, st));
         launches += 1;
     }
-    T.mark(st);                                                                   // 10
+    T.mark(st);                                                                   // 11
     CK(cudaStreamSynchronize(st));
     CSCB200_Stats &S = C.stats;
     S.ms_h2d += T.ms(0, 1); S.ms_analyze += T.ms(1, 2); S.ms_filters += T.ms(2, 3); S.ms_mf_hash += T.ms(3, 4);
     S.ms_mf_sort += T.ms(4, 5); S.ms_mf_rows += T.ms(5, 6); S.ms_mf_extend += T.ms(6, 7); S.ms_mf_chains += T.ms(7, 8);
-    S.ms_encode += T.ms(8, 9); S.ms_d2h += T.ms(9, 10); S.ms_total_gpu += T.ms(0, 10);
+    S.ms_encode += T.ms(8, 9); S.ms_rc += T.ms(9, 10); S.ms_d2h += T.ms(10, 11); S.ms_total_gpu += T.ms(0, 11);
     S.kernel_launches += launches; S.streams += ns; S.waves += 1;
     return ret;
 }
 
 // frame one encoded job through `sink`
+template <class Sink> void frame_segment(EncJob &J, size_t sg, Framer &fr, Sink &sink) {
+    const SegOut &o = J.so[sg];
+    std::vector<u8> ev;   // RC/BC block completions of the segment in temporal order (H4)
+    merge_events(J.rc_ev + o.rev_off, o.rev_len, J.bc_ev + o.bev_off, o.bev_len, ev);
+    fr.segment(sink, const_cast<u8 *>(J.rc) + o.rc_off, o.rc_len, J.bc + o.bc_off, o.bc_len, ev.data(), (u32)ev.size());
+}
 template <class Sink> void frame_job(EncJob &J, Framer &fr, Sink &sink) {
-    for (size_t s = 0; s < J.so.size(); s++) {
-        const SegOut &o = J.so[s];
-        fr.segment(sink, const_cast<u8 *>(J.rc) + o.rc_off, o.rc_len, J.bc + o.bc_off, o.bc_len, J.ev + o.ev_off, o.ev_len);
-    }
+    for (size_t s = 0; s < J.so.size(); s++) frame_segment(J, s, fr, sink);
 }
 
 // size of the framed stream without touching the payload (device-resident path)
@@ -541,8 +555,7 @@ size_t framed_size(const EncJob &J, bool with_props) {
     const u32 bs = J.props.csc_blocksize;
     size_t t = with_props ? CSC_PROP_SIZE : 0;
     for (const SegOut &o : J.so) {
-        u32 nr = 0, nb = 0;
-        for (u32 i = 0; i < o.ev_len; i++) (J.ev[o.ev_off + i] ? nr : nb)++;
+        const u32 nr = o.rev_len, nb = o.bev_len;
         u32 rrem = o.rc_len - nr * bs, brem = o.bc_len - nb * bs;
         t += (size_t)(nr + nb) * (1 + bs) + (rrem == bs ? 1 : 4) + rrem + (brem == bs ? 1 : 4) + brem;
     }
@@ -550,7 +563,7 @@ size_t framed_size(const EncJob &J, bool with_props) {
 }
 
 size_t per_stream_bytes() { return 81920 * 4 + 131072 * 2 + (kApLimit + 2) * sizeof(ApUnit) + 140000 * 2 + 4096; }
-size_t per_pos_bytes(u32 K) { return 2 + 24 + 6 * (size_t)K + 12 + 1 + 3; }
+size_t per_pos_bytes(u32 K) { return 2 + 24 + 6 * (size_t)K + 12 + 1 + 3 + 9 * sizeof(DecEntry); }
 
 // ----------------------------------------------------------------------------- decode
 struct DecJob {
@@ -752,7 +765,7 @@ struct Lease {
 void add_stats(CSCB200_Stats &a, const CSCB200_Stats &b) {   // devices work side by side: times are the slowest device's
     double *x = &a.ms_h2d;
     const double *y = &b.ms_h2d;
-    for (int i = 0; i < 14; i++) x[i] = std::max(x[i], y[i]);
+    for (int i = 0; i < 15; i++) x[i] = std::max(x[i], y[i]);
     a.bytes_in += b.bytes_in; a.bytes_out += b.bytes_out; a.mf_positions += b.mf_positions;
     a.kernel_launches += b.kernel_launches; a.streams += b.streams; a.waves += b.waves; a.replans += b.replans;
 }
@@ -771,7 +784,7 @@ int encode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_s
     for (int i = 0; i < n; i++) {
         EncJob &J = jobs[i];
         if (in_size[i] >= 0xF0000000ull) return kErrUnsupported;
-        J.in = in[i]; J.n = (u32)in_size[i]; J.status = 0; J.rc = J.bc = J.ev = nullptr;
+        J.in = in[i]; J.n = (u32)in_size[i]; J.status = 0; J.rc = J.bc = nullptr; J.rc_ev = J.bc_ev = nullptr;
         J.in_dev = device; J.no_payload = device;
         uint32_t d = (uint64_t)dict_size > in_size[i] ? (uint32_t)in_size[i] : dict_size;   // csa_worker.cpp:35
         props_init(&J.props, d, level);
@@ -1074,7 +1087,7 @@ int CSCEnc_Encode(CSCEncHandle p, ISeqInStream *is, ICompressProgress *progress)
     CbSink sink{h->os, false, 0};
     for (size_t sgi = h->segs_done; sgi < J.so.size(); sgi++) {
         const SegOut &o = J.so[sgi];
-        h->fr->segment(sink, const_cast<u8 *>(J.rc) + o.rc_off, o.rc_len, J.bc + o.bc_off, o.bc_len, J.ev + o.ev_off, o.ev_len);
+        frame_segment(J, sgi, *h->fr, sink);
         h->outsize += o.rc_len + o.bc_len;
     }
     h->segs_done = J.so.size();

@@ -1,0 +1,111 @@
+// rc_engine.cuh -- the range-coder pass: one stream per THREAD.
+//
+// The reference's EncodeBit (csc_coder.h:67-81) adapts a probability and then advances the coder
+// registers (range, 64-bit low with carry / cache bytes, csc_coder.cpp:89-112).  Only the second half is
+// serially dependent on every earlier decision of the segment, and it needs nothing but the sequence of
+// (probability, bit) pairs.  The parser / model engine (enc_engine.cuh) therefore only APPENDS those pairs
+// to the stream's decision list; this pass replays them: ~a dozen integer instructions per decision, no
+// model memory, no match finder, 32 independent streams per warp instead of one.
+//
+// Output per segment: the RC sub-stream (whose last byte is the one the reference skips instead of
+// storing, H3) and the time stamps of the 64 KiB block completions (csc_coder.cpp:97-104) for the host's
+// replay of the RC/BC block order (H4).
+#pragma once
+#include "csc_defs.h"
+
+namespace cscb {
+
+struct RcCoder {
+    // registers of Coder (csc_coder.h:44-50)
+    u64 low;
+    u32 range, cachesize, cache;
+    // output
+    u8 *out;
+    u32 cap, n, blk, bsize;
+    u32 *ev;
+    u32 ev_cap, ev_n;
+    i32 err;
+    // bytes are gathered into one aligned 8-byte word before they go to memory
+    u64 acc;
+
+    CSC_HDF void put(u32 b, u32 stamp) {
+        if (n < cap) {
+            acc |= (u64)(b & 0xFF) << (8 * (n & 7));
+            if ((n & 7) == 7) { *reinterpret_cast<u64 *>(out + (n & ~7u)) = acc; acc = 0; }
+        } else {
+            err = kErrOverflow;
+        }
+        n++;
+        if (++blk == bsize) {   // a 64 KiB RC block completed (csc_coder.cpp:97-104)
+            if (ev_n < ev_cap) ev[ev_n] = stamp; else err = kErrOverflow;
+            ev_n++;
+            blk = 0;
+        }
+    }
+    CSC_HDF void drain() {   // pending bytes of the gather word (the word stays open for the next segment)
+        if (n & 7) {
+            const u32 base = n & ~7u;
+            for (u32 k = 0; k < (n & 7); k++) if (base + k < cap) out[base + k] = (u8)(acc >> (8 * k));
+        }
+    }
+    CSC_HDF void shift_low(u32 stamp) {   // RC_ShiftLow, csc_coder.cpp:89-112
+        if ((u32)low < 0xFF000000u || (u32)(low >> 32) != 0) {
+            u32 t = cache;
+            const u32 carry = (u32)(low >> 32);
+            do {
+                put(t + carry, stamp);
+                t = 0xFF;
+            } while (--cachesize != 0);
+            cache = ((u32)low >> 24) & 0xFF;
+        }
+        cachesize++;
+        low = (u64)((u32)low << 8);
+    }
+    CSC_HDF void step(u32 e, u32 stamp) {   // the coder half of EncodeBit, csc_coder.h:67-81
+        const u32 bound = (range >> 12) * (e & 0xFFFu);
+        if (e & 0x8000u) range = bound;
+        else { low += bound; range -= bound; }
+        if (range < (1u << 24)) { range <<= 8; shift_low(stamp); }
+    }
+
+    // all segments of one stream; the decision lists were written by Encoder (enc_engine.cuh)
+    CSC_HD void run(const EncStream &S) {
+        out = S.rc_out; cap = S.rc_cap; bsize = S.cfg.csc_blocksize;
+        ev = S.rc_ev; ev_cap = S.ev_cap; ev_n = 0;
+        n = 0; err = 0; acc = 0;
+        if (*S.status < 0) return;
+        for (u32 sg = 0; sg < S.nseg; sg++) {
+            SegOut so = S.segout[sg];
+            low = 0; range = 0xFFFFFFFFu; cachesize = 1; cache = 0; blk = 0;   // Coder::Flush leaves the coder reset (:64-73)
+            const u32 rc0 = n, ev0 = ev_n;
+            const DecEntry *d = S.dec + so.dec_off;
+            const u32 cnt = so.dec_len;
+            u32 i = 0;
+#if defined(__CUDA_ARCH__)
+            for (; i + 8 <= cnt; i += 8) {   // dec_off is 8-aligned: one 16-byte load per 8 decisions
+                const uint4 v = *reinterpret_cast<const uint4 *>(d + i);
+                const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    step(w[k] & 0xFFFFu, 2 * (i + 2 * k) + 1);
+                    step(w[k] >> 16, 2 * (i + 2 * k + 1) + 1);
+                }
+            }
+#endif
+            for (; i < cnt; i++) step(d[i], 2 * i + 1);
+            // Coder::Flush (csc_coder.cpp:40-48): five more bytes, then one byte is skipped, not stored (H3):
+            // the host substitutes the stale ring byte
+            for (int k = 0; k < 5; k++) shift_low(2 * cnt + 1);
+            if (n < cap) { if ((n & 7) == 7) { *reinterpret_cast<u64 *>(out + (n & ~7u)) = acc; acc = 0; } }
+            else err = kErrOverflow;
+            n++; blk++;
+            so.rc_off = rc0; so.rc_len = n - rc0;
+            so.rev_off = ev0; so.rev_len = ev_n - ev0;
+            S.segout[sg] = so;
+        }
+        drain();
+        if (err) *S.status = err;
+    }
+};
+
+}  // namespace cscb

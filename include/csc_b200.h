@@ -57,7 +57,8 @@ void CSCB200_Trim(void);
 /* Timing / launch statistics of the last Encode/Decode call on this thread's context. */
 typedef struct {
     double ms_h2d, ms_analyze, ms_filters, ms_mf_hash, ms_mf_sort, ms_mf_rows, ms_mf_extend, ms_encode, ms_d2h,
-        ms_frame, ms_decode, ms_unfilter, ms_total_gpu, ms_mf_chains;   /* mf_hash..extend: 6-byte rows; mf_chains: 3-/2-byte chains */
+        ms_frame, ms_decode, ms_unfilter, ms_total_gpu, ms_mf_chains,   /* mf_hash..extend: 6-byte rows; mf_chains: 3-/2-byte chains */
+        ms_rc;                                                          /* ms_encode: parser + model; ms_rc: range-coder pass */
     uint64_t bytes_in, bytes_out, mf_positions;
     uint32_t kernel_launches, streams, waves;
     uint32_t replans;   /* streams encoded again because a duplicate-block outcome moved the sub-block grid of a wrapped window */

@@ -16,6 +16,7 @@
 #include "../../csc_b200/csrc/host_common.h"
 #include "../../csc_b200/csrc/plan.h"
 #include "../../csc_b200/csrc/enc_engine.cuh"
+#include "../../csc_b200/csrc/rc_engine.cuh"
 #include "../../csc_b200/csrc/dec_engine.cuh"
 
 using namespace cscb;
@@ -158,7 +159,9 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
             nblk += (s + kBlock - 1) / kBlock;
         }
         std::vector<u8> flip(nblk, 0);   // assumed outcomes of the duplicate-block test (plan.h); refined on kErrReplan
-        std::vector<u8> rc, bc, ev;
+        std::vector<u8> rc, bc;
+        std::vector<u32> rc_ev, bc_ev;
+        std::vector<DecEntry> dec;
         std::vector<SegOut> so;
         u32 tn = 0;
         for (;;) {
@@ -218,7 +221,9 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         std::vector<u16> p_lit(131072, 2048);
         std::vector<ApUnit> ap(kApLimit + 2);
         u32 rc_cap = n * 2 + 65536 * 2, bc_cap = n * 2 + 65536 * 2;
-        rc.assign(rc_cap, 0); bc.assign(bc_cap, 0); ev.assign(rc_cap / 32768 + bc_cap / 32768 + 64, 0);
+        rc.assign(rc_cap, 0); bc.assign(bc_cap, 0);
+        rc_ev.assign(rc_cap / 32768 + 64, 0); bc_ev.assign(bc_cap / 32768 + 64, 0);
+        dec.assign((size_t)n * 9 + 64 * seg.size() + 1024, 0);
         so.assign(seg.size(), SegOut());
         i32 status = 0;
         u32 replan[2] = {0, 0};
@@ -235,7 +240,8 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         S.flip = flip.data(); S.replan = replan;
         S.ht2 = ht2.data(); S.ht3 = ht3.data(); S.p_lit = p_lit.data(); S.p_delta = p_lit.data() + 65536; S.ap = ap.data();
         S.rc_out = rc.data(); S.rc_cap = rc_cap; S.bc_out = bc.data(); S.bc_cap = bc_cap;
-        S.events = ev.data(); S.ev_cap = (u32)ev.size(); S.segout = so.data(); S.status = &status;
+        S.dec = dec.data(); S.dec_cap = (u32)dec.size();
+        S.rc_ev = rc_ev.data(); S.bc_ev = bc_ev.data(); S.ev_cap = (u32)rc_ev.size(); S.segout = so.data(); S.status = &status;
         S.trace = trace; S.trace_cap = (u32)trace_cap; S.trace_n = &tn;
         ModelSmall *M = new ModelSmall;
         build_p2bits(M->p2bits);
@@ -246,11 +252,16 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         if (status == kErrReplan) { flip[replan[0]] = (u8)replan[1]; g_replans++; continue; }   // plan again with the observed outcome
         if (trace_n) *trace_n = tn;
         if (status < 0) return status;
+        RcCoder R;   // the range-coder pass over the decision lists (k_rc on the device)
+        R.run(S);
+        if (status < 0) return status;
         break;
         }
-        for (u32 s = 0; s < seg.size(); s++)
-            fr.segment(sink, rc.data() + so[s].rc_off, so[s].rc_len, bc.data() + so[s].bc_off, so[s].bc_len,
-                       ev.data() + so[s].ev_off, so[s].ev_len);
+        std::vector<u8> ev;
+        for (u32 s = 0; s < seg.size(); s++) {
+            merge_events(rc_ev.data() + so[s].rev_off, so[s].rev_len, bc_ev.data() + so[s].bev_off, so[s].bev_len, ev);
+            fr.segment(sink, rc.data() + so[s].rc_off, so[s].rc_len, bc.data() + so[s].bc_off, so[s].bc_len, ev.data(), (u32)ev.size());
+        }
     }
     fr.eof(sink);
     *out_n = res.size();
