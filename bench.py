@@ -5,12 +5,12 @@ Metric (BASELINE.json): compress MB/s (10^6 uncompressed bytes per second).
 Workload at N=1 (BASELINE.json configs[1]): libcsc -m2 (lazy parser, 6-byte table width 8),
 -d64m, 1 GiB of synthetic English-like text on one B200, split csarc -p style into
 independent 368 KiB chunks (one libcsc stream per chunk, dict = min(64 MiB, chunk); the chunk
-size is part of the parity key and is the same for the reference arm; 368 KiB makes 2850 streams
-per GiB, just under the 2960 warps the encoder kernel keeps resident on 148 SMs).  At N>1
-every rank compresses its own 1 GiB (weak scaling, contiguous chunk ranges, no collective).
+size is part of the parity key and is the same for the reference arm).  At N>1 every rank
+compresses its own 1 GiB (weak scaling, contiguous chunk ranges, no collective);
+`--scaling strong` splits one fixed job (`--total` bytes) over the ranks instead.
 
 A "step" is one pass of the whole hot path (analyzer -> filters -> match finder -> parser ->
-range coder) over the batch.
+model -> range coder) over the batch.
   value : whole-job MB/s with the chunks already resident in HBM (CSCB200_EncodeChunksDevice),
           timed with CUDA events on the library's launch stream, max over ranks.
   e2e   : the same through the host C ABI (CSCB200_EncodeChunks) from pinned host buffers,
@@ -19,7 +19,11 @@ range coder) over the batch.
                  figures for the match-finder / analyzer kernels ride along in "kernels".
   cpu_baseline : the unmodified reference (oracle/_ref) on this box's host cores, one handle
                  per chunk (csarc -p/-t model), bounded sample of the same workload.
-`--impl reference` times only that CPU arm.
+  parity_checked : chunks of the timed e2e output byte-compared with the unmodified reference.
+  levels / decode / chunk_sweep : the metric's other legs (-m1 / -m3 on text and on the mixed
+                 corpus of configs[2], decode of the -m1 / -m3 archives as in configs[4], the
+                 chunk-size / ratio trade-off), each measured the same way; `--quick` skips them.
+`--impl reference` times only the CPU arm, on the same bytes and with the same config keys.
 """
 from __future__ import annotations
 
@@ -40,17 +44,29 @@ LEVEL = 2
 DICT = 64 << 20
 CHUNK = 368 << 10
 TOTAL = 1 << 30
-WORKLOAD = "libcsc -m2 -d64m, 1 GiB synthetic English-like text, 2850 independent 368 KiB chunks per GPU"
+WIDTH = {1: 1, 2: 8, 3: 2, 4: 8, 5: 16}   # 6-byte table width per level (csc_enc.cpp:56-91; -m5: bounded-search rows)
 
 
-def gen_text(total: int, rank: int) -> np.ndarray:
+def workload_name(level, chunk, kind="English-like text"):
+    return f"libcsc -m{level} -d64m, synthetic {kind}, independent {chunk >> 10} KiB chunks (one stream per chunk), 1 GiB per GPU"
+
+
+def gen(kind: str, total: int, rank: int) -> np.ndarray:
     from csc_b200 import synth
     tile = 32 << 20
     out = np.empty(total, dtype=np.uint8)
+    fn = synth.text if kind == "text" else synth.mixed
     for i, off in enumerate(range(0, total, tile)):
         n = min(tile, total - off)
-        out[off:off + n] = synth.text(n, 12345 + rank * 1000 + i)
+        out[off:off + n] = fn(n, 12345 + rank * 1000 + i)
     return out
+
+
+def config_dict(level, chunk, total, kind="text"):
+    """identical for both arms (the driver compares them): no run-specific keys in here"""
+    return {"workload": workload_name(level, chunk, "English-like text" if kind == "text" else "mixed corpus (text / x86-like / delta tables / random)"),
+            "level": level, "dict": DICT, "chunk": chunk, "bytes_per_gpu": total,
+            "l2": "inputs (1 GiB/GPU) exceed the 126 MB L2"}
 
 
 class ClockSampler(threading.Thread):
@@ -99,13 +115,12 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(chunks, nthreads: int):
-    """unmodified reference, one handle per chunk on nthreads host threads; returns (seconds, out bytes)"""
+def cpu_reference_run(chunks, nthreads: int, level: int, outs=None):
+    """unmodified reference, one handle per chunk on nthreads host threads; returns (seconds, streams)"""
     from oracle import refbind
     t = time.perf_counter()
-    outs = refbind.run_chunks(chunks, DICT, LEVEL, nthreads)
-    dt = time.perf_counter() - t
-    return dt, sum(o.size for o in outs)
+    res = refbind.run_chunks(chunks, DICT, level, nthreads)
+    return time.perf_counter() - t, res
 
 
 def run_reference_arm(args):
@@ -117,43 +132,80 @@ def run_reference_arm(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built and /root/reference absent"}))
         return 0
     cores = os.cpu_count() or 1
-    sample = min(TOTAL, max(8, cores) * 32 * CHUNK)   # bounded sample of the same workload: 32 chunks per host thread
-    data = gen_text(sample, 0)
-    chunks = [data[o:o + CHUNK] for o in range(0, sample, CHUNK)]
-    for _ in range(args.warmup):
-        cpu_reference_run(chunks[:cores], cores)
-    times = []
+    total = args.total
+    data = gen("text", total, 0)
+    chunks = [data[o:o + args.chunk] for o in range(0, total, args.chunk)]
+    refbind.run_chunks(chunks[:cores], DICT, args.level, cores)   # page in, spin up
+    for _ in range(max(0, args.warmup - 1)):
+        refbind.run_chunks(chunks[: 4 * cores], DICT, args.level, cores)
+    times, comp = [], 0
     for _ in range(args.steps):
-        dt, _ = cpu_reference_run(chunks, cores)
+        dt, outs = cpu_reference_run(chunks, cores, args.level)
+        comp = sum(o.size for o in outs)
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    val = sample / (ms / 1e3) / 1e6
+    val = total / (ms / 1e3) / 1e6
     line = {"impl": "reference", "metric": "compress_MBps", "value": round(val, 2), "unit": "MB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "level": LEVEL, "dict": DICT, "chunk": CHUNK},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": config_dict(args.level, args.chunk, total), "ratio": round(comp / total, 5),
             "cpu_baseline": {"value": round(val, 2), "unit": "MB/s", "cores": cores, "kind": "reference",
-                             "sample": f"{sample >> 20} MiB of the workload per step ({len(chunks)} chunks), libcsc via oracle/_ref"},
+                             "sample": f"the whole workload per step ({total >> 20} MiB, {len(chunks)} chunks), unmodified libcsc "
+                                       f"(oracle/_ref), one handle per chunk on {cores} host threads"},
             "e2e": {"value": round(val, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
+class Arena:
+    """pinned host in / out buffers + a device copy of one corpus, chunked"""
+
+    def __init__(self, torch, api, data, chunk):
+        self.total = int(data.size)
+        self.chunk = chunk
+        self.n = (self.total + chunk - 1) // chunk
+        self.sizes = [min(chunk, self.total - i * chunk) for i in range(self.n)]
+        self.h_in = torch.empty(self.total, dtype=torch.uint8).pin_memory()
+        self.h_in.numpy()[:] = data
+        self.bound = api.encode_bound(chunk)
+        self.h_out = torch.empty(self.n * self.bound, dtype=torch.uint8).pin_memory()
+        self.d_in = self.h_in.cuda(non_blocking=False)
+        self.in_ptrs = [self.h_in.data_ptr() + i * chunk for i in range(self.n)]
+        self.out_ptrs = [self.h_out.data_ptr() + i * self.bound for i in range(self.n)]
+        self.dev_ptrs = [self.d_in.data_ptr() + i * chunk for i in range(self.n)]
+        self.caps = [self.bound] * self.n
+
+    def stream(self, i, size):
+        return self.h_out.numpy()[i * self.bound: i * self.bound + size]
+
+
+def timed_device(api, csc, A, level, steps):
+    """device-resident path: CUDA-event time of the library's launch stream, summed per kernel"""
+    kern, gpu_ms, launches, dsz = {}, 0.0, 0, None
+    for _ in range(steps):
+        dsz = api.encode_chunks_device(A.dev_ptrs, A.sizes, DICT, level)
+        st = csc.get_stats()
+        gpu_ms += st["ms_total_gpu"]
+        launches += st["kernel_launches"]
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                kern[k] = kern.get(k, 0.0) + v
+    return gpu_ms / steps, {k: v / steps for k, v in kern.items()}, launches, dsz
+
+
 def main():
-    global CHUNK, LEVEL, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--total", type=int, default=TOTAL, help="bytes per GPU (default 1 GiB)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--total", type=int, default=TOTAL, help="bytes per GPU (weak) or of the whole job (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the parity sample")
+    ap.add_argument("--quick", action="store_true", help="headline only: skip the levels / decode / chunk-sweep legs")
     ap.add_argument("--chunk", type=int, default=CHUNK, help="independent chunk size (part of the parity key)")
     ap.add_argument("--level", type=int, default=LEVEL)
     args = ap.parse_args()
-    if args.chunk != CHUNK or args.level != LEVEL:
-        CHUNK, LEVEL = args.chunk, args.level
-        WORKLOAD = f"libcsc -m{LEVEL} -d64m, synthetic English-like text, independent {CHUNK >> 10} KiB chunks"
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -170,21 +222,20 @@ def main():
     csc_b200.set_device(local)
     if not csc_b200.available():
         raise RuntimeError("no CUDA device: csc_b200 has no CPU fallback")
+    level, chunk = args.level, args.chunk
 
-    total = args.total
-    data = gen_text(total, rank)
-    nchunks = (total + CHUNK - 1) // CHUNK
-    sizes = [min(CHUNK, total - i * CHUNK) for i in range(nchunks)]
-    # pinned host buffers (e2e) and a device copy (kernel-only)
-    h_in = torch.empty(total, dtype=torch.uint8).pin_memory()
-    h_in.numpy()[:] = data
-    bound = api.encode_bound(CHUNK)
-    h_out = torch.empty(nchunks * bound, dtype=torch.uint8).pin_memory()
-    d_in = h_in.cuda(non_blocking=False)
-    in_ptrs = [h_in.data_ptr() + i * CHUNK for i in range(nchunks)]
-    out_ptrs = [h_out.data_ptr() + i * bound for i in range(nchunks)]
-    dev_ptrs = [d_in.data_ptr() + i * CHUNK for i in range(nchunks)]
-    caps = [bound] * nchunks
+    # weak: every rank its own `total`; strong: contiguous chunk range of one fixed job
+    if args.scaling == "strong":
+        nch = (args.total + chunk - 1) // chunk
+        lo, hi = (nch * rank + world - 1) // world, (nch * (rank + 1) + world - 1) // world
+        job = gen("text", args.total, 0)
+        data = job[lo * chunk: min(hi * chunk, args.total)]
+        job_bytes = args.total
+    else:
+        data = gen("text", args.total, rank)
+        job_bytes = args.total * world
+    total = int(data.size)
+    A = Arena(torch, api, data, chunk)
 
     def barrier():
         torch.cuda.synchronize()
@@ -194,38 +245,27 @@ def main():
 
     # ---- warm-up (allocations, clocks)
     for _ in range(max(args.warmup, 3)):
-        api.encode_chunks_device(dev_ptrs, sizes, DICT, LEVEL)
-    out_sizes = api.encode_chunks_raw(in_ptrs, sizes, out_ptrs, caps, DICT, LEVEL)
+        api.encode_chunks_device(A.dev_ptrs, A.sizes, DICT, level)
+    out_sizes = api.encode_chunks_raw(A.in_ptrs, A.sizes, A.out_ptrs, A.caps, DICT, level)
 
     # ---- timed: kernel-only (inputs resident in HBM)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    kern = {}
-    gpu_ms = 0.0
-    launches = 0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        dsz = api.encode_chunks_device(dev_ptrs, sizes, DICT, LEVEL)
-        st = csc_b200.get_stats()
-        gpu_ms += st["ms_total_gpu"]
-        launches += st["kernel_launches"]
-        for k, v in st.items():
-            if k.startswith("ms_"):
-                kern[k] = kern.get(k, 0.0) + v
+    ms_step, kern, launches, dsz = timed_device(api, csc_b200, A, level, args.steps)
     barrier()
     wall_dev = time.perf_counter() - t0
     # ---- timed: end to end through the host C ABI (pinned host in -> pinned host out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_sizes = api.encode_chunks_raw(in_ptrs, sizes, out_ptrs, caps, DICT, LEVEL)
+        out_sizes = api.encode_chunks_raw(A.in_ptrs, A.sizes, A.out_ptrs, A.caps, DICT, level)
     barrier()
     wall_e2e = time.perf_counter() - t0
     sampler.stop()
     assert dsz == out_sizes, "device-resident and host paths disagree on stream sizes"
 
-    ms_step = gpu_ms / args.steps
     ms_e2e = 1e3 * wall_e2e / args.steps
     comp = sum(out_sizes)
     ratio = comp / total
@@ -233,9 +273,9 @@ def main():
         t = torch.tensor([ms_step, ms_e2e, 1e3 * wall_dev / args.steps], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, ms_e2e, wall_dev_ms = [float(x) for x in t.tolist()]
-        c = torch.tensor([comp], device="cuda", dtype=torch.float64)
+        c = torch.tensor([comp, total], device="cuda", dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        ratio = float(c.item()) / (total * world)
+        ratio = float(c[0].item()) / float(c[1].item())
     else:
         wall_dev_ms = 1e3 * wall_dev / args.steps
     if rank != 0:
@@ -243,7 +283,6 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    job_bytes = total * world
     value = job_bytes / (ms_step / 1e3) / 1e6
     e2e = job_bytes / (ms_e2e / 1e3) / 1e6
     peaks = {}
@@ -253,60 +292,158 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    W = 8  # -m2 table width
-    per_kernel = {}
-    # algorithmic bytes per input byte of each stage
-    algo = {"ms_analyze": 1.0, "ms_filters": 2.0, "ms_mf_hash": 1.0 + 12.0, "ms_mf_sort": 3 * 2 * 12.0, "ms_mf_rows": 12.0 + 4.0 * W,
-            "ms_mf_extend": 1.0 + 4.0 * W + 2.0 * W, "ms_mf_chains": 2 * (1.0 + 12.0 + 2 * 2 * 12.0 + 12.0 + 4.0 + 1.0 + 4.0 + 2.0),
-            "ms_encode": 1.0 + ratio + 6.0 * (W + 2)}
+    W = WIDTH[level]
+
+    def kernel_table(kern, total, ratio, W):
+        """per-stage time, implementation bytes per input byte (what the stage really moves) and GB/s"""
+        impl = {"ms_analyze": 1.0, "ms_filters": 2.0, "ms_mf_hash": 1.0 + 12.0, "ms_mf_sort": 3 * 2 * 12.0, "ms_mf_rows": 12.0 + 4.0 * W,
+                "ms_mf_extend": 1.0 + 4.0 * W + 2.0 * W, "ms_mf_chains": 2 * (1.0 + 12.0 + 2 * 2 * 12.0 + 12.0 + 4.0 + 1.0 + 4.0 + 2.0),
+                "ms_encode": 1.0 + 6.0 * (W + 2), "ms_rc": 2.0 * 3.0 + ratio}
+        out = {}
+        for k, bpb in impl.items():
+            ms = kern.get(k, 0.0)
+            if ms > 0:
+                gbs = total * bpb / (ms / 1e3) / 1e9
+                out[k[3:]] = {"ms": round(ms, 3), "bytes_per_input_byte": bpb, "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 5)}
+        mf = sum(kern.get(k, 0.0) for k in ("ms_mf_hash", "ms_mf_sort", "ms_mf_rows", "ms_mf_extend", "ms_mf_chains"))
+        if mf > 0:   # the match-finder stage as a whole against SURVEY 8d's compulsory 1 + 6 (W + 2) bytes per position
+            gbs = total * (1.0 + 6.0 * (W + 2)) / (mf / 1e3) / 1e9
+            out["match_finder_total"] = {"ms": round(mf, 3), "bytes_per_input_byte": 1.0 + 6.0 * (W + 2), "GBps": round(gbs, 1),
+                                         "frac_of_hbm_peak": round(gbs / peak, 5), "note": "algorithmic bytes (SURVEY 8d), all MF kernels"}
+        return out
+
+    per_kernel = kernel_table(kern, total, ratio, W)
     # DRAM bytes of one k_encode launch from the committed ncu capture of this very configuration (else null)
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_encode_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_k_encode_traffic.json")))
         w = tj["workload"]
-        if (w["level"], w["chunk"], w["bytes_per_gpu"]) == (LEVEL, CHUNK, total):
-            traffic, traffic_src = int(tj["dram_bytes_per_launch"]), "profiles/r01_k_encode_traffic.json (ncu, one launch)"
+        if (w["level"], w["chunk"], w["bytes_per_gpu"]) == (level, chunk, total):
+            traffic, traffic_src = int(tj["dram_bytes_per_launch"]), "profiles/r02_k_encode_traffic.json (ncu, one launch)"
     except Exception:
         pass
-    for k, bpb in algo.items():
-        ms = kern.get(k, 0.0) / args.steps
-        if ms > 0:
-            gbs = total * bpb / (ms / 1e3) / 1e9
-            per_kernel[k[3:]] = {"ms": round(ms, 3), "algo_bytes_per_input_byte": bpb, "GBps": round(gbs, 1),
-                                 "frac_of_hbm_peak": round(gbs / peak, 5)}
-    enc_ms = kern.get("ms_encode", 0.0) / args.steps
-    achieved = total * (1.0 + ratio + 6.0 * (W + 2)) / (enc_ms / 1e3) / 1e9 if enc_ms else 0.0
+    enc_ms = kern.get("ms_encode", 0.0)
+    algo_bytes = total * (1.0 + 6.0 * (W + 2) + 2.0 * 3.0)   # window byte, W+2 candidates of 6 B, ~3 decisions of 2 B written
+    achieved = algo_bytes / (enc_ms / 1e3) / 1e9 if enc_ms else 0.0
     line = {
         "metric": "compress_MBps", "value": round(value, 2), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "level": LEVEL, "dict": DICT, "chunk": CHUNK, "bytes_per_gpu": total,
-                   "l2": "inputs (1 GiB/GPU) exceed the 126 MB L2", "ratio": round(ratio, 5),
-                   "stream_identical_to_libcsc": "checked in tests/test_gpu_parity.py",
-                   "wall_ms_per_step_device_path": round(wall_dev_ms, 2)},
+        "config": config_dict(level, chunk, args.total), "ratio": round(ratio, 5),
         "e2e": {"value": round(e2e, 2), "unit": "MB/s", "h2d_bytes_per_step": int(total), "d2h_bytes_per_step": int(comp)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_encode (parser + range coder, one stream per warp; latency-bound)",
+        "wall_ms_per_step_device_path": round(wall_dev_ms, 2),
+        "roofline": {"bound": "hbm", "kernel": "k_encode (parser + adaptive model, one stream per warp; latency-bound)",
                      "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 6),
                      "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_bytes_per_launch": int(total * (1.0 + ratio + 6.0 * (W + 2))), "peak_source": peak_src,
-                     "algorithmic_bytes": "(1 + ratio + 6*(W+2)) B per input byte: window byte, coded bytes, W+2 candidates of 6 B (SURVEY 8d)"},
+                     "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
+                     "algorithmic_bytes": "(1 + 6*(W+2) + 6) B per input byte: window byte, W+2 candidates of 6 B (SURVEY 8d), ~3 decisions of 2 B"},
         "kernels": per_kernel,
         "clocks": sampler.summary(),
     }
-    if not args.no_cpu:
-        from oracle import refbind
-        if refbind.available():
-            cores = os.cpu_count() or 1
-            sample = min(total, max(8, cores) * 32 * CHUNK)   # 32 chunks per host thread, after one warm-up pass
-            chunks = [data[o:o + CHUNK] for o in range(0, sample, CHUNK)]
-            cpu_reference_run(chunks[:cores], cores)
-            dt, _ = cpu_reference_run(chunks, cores)
-            line["cpu_baseline"] = {"value": round(sample / dt / 1e6, 2), "unit": "MB/s", "cores": cores, "kind": "reference",
-                                    "sample": f"first {sample >> 20} MiB of the workload ({len(chunks)} chunks), unmodified libcsc "
-                                              f"(oracle/_ref), one handle per chunk on {cores} threads"}
-        else:
-            line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+
+    from oracle import refbind
+    have_ref = refbind.available() and not args.no_cpu
+    cores = os.cpu_count() or 1
+    if have_ref:
+        # ---- parity of the timed output: first / middle / last / random chunks against the unmodified reference
+        rng = np.random.default_rng(7)
+        pick = sorted(set([0, 1, A.n // 2, A.n - 1] + [int(x) for x in rng.integers(0, A.n, size=44)]))
+        ins = [data[i * chunk: i * chunk + A.sizes[i]] for i in pick]
+        exp = refbind.run_chunks(ins, DICT, level, cores)
+        same = sum(1 for i, e in zip(pick, exp) if out_sizes[i] == e.size and bool((A.stream(i, out_sizes[i]) == e).all()))
+        line["parity_checked"] = {"n": len(pick), "identical": same, "against": "unmodified libcsc (oracle/_ref), same level / dict / chunking"}
+        # ---- CPU baseline: the reference on this box's host cores, bounded sample of the same chunks
+        sample = min(total, max(8, cores) * 32 * chunk)   # 32 chunks per host thread, after one warm-up pass
+        chunks = [data[o:o + chunk] for o in range(0, sample, chunk)]
+        cpu_reference_run(chunks[:cores], cores, level)
+        dt, _ = cpu_reference_run(chunks, cores, level)
+        line["cpu_baseline"] = {"value": round(sample / dt / 1e6, 2), "unit": "MB/s", "cores": cores, "kind": "reference",
+                                "sample": f"first {sample >> 20} MiB of the workload ({len(chunks)} chunks), unmodified libcsc "
+                                          f"(oracle/_ref), one handle per chunk on {cores} threads"}
+    elif not args.no_cpu:
+        line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+
+    if not args.quick and world == 1:
+        legs = {}
+
+        def leg(name, A2, data2, lvl, kind, with_cpu=True):
+            api.encode_chunks_device(A2.dev_ptrs, A2.sizes, DICT, lvl)
+            ms, kk, _, _ = timed_device(api, csc_b200, A2, lvl, 2)
+            api.encode_chunks_raw(A2.in_ptrs, A2.sizes, A2.out_ptrs, A2.caps, DICT, lvl)
+            t1 = time.perf_counter()
+            osz = api.encode_chunks_raw(A2.in_ptrs, A2.sizes, A2.out_ptrs, A2.caps, DICT, lvl)
+            e = time.perf_counter() - t1
+            r = sum(osz) / A2.total
+            Wl = WIDTH[lvl]
+            enc = kk.get("ms_encode", 0.0)
+            ach = A2.total * (1.0 + 6.0 * (Wl + 2) + 6.0) / (enc / 1e3) / 1e9 if enc else 0.0
+            d = {"value": round(A2.total / ms / 1e3, 2), "unit": "MB/s", "ms_per_step": round(ms, 2),
+                 "e2e": {"value": round(A2.total / e / 1e6, 2), "unit": "MB/s", "h2d_bytes_per_step": A2.total, "d2h_bytes_per_step": int(sum(osz))},
+                 "config": config_dict(lvl, A2.chunk, A2.total, kind), "ratio": round(r, 5),
+                 "roofline": {"bound": "hbm", "kernel": "k_encode", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6), "traffic": None},
+                 "kernels_ms": {k[3:]: round(v, 2) for k, v in kk.items() if v > 0.05}}
+            if have_ref and with_cpu:
+                smp = min(A2.total, cores * 8 * A2.chunk)
+                cs = [data2[o:o + A2.chunk] for o in range(0, smp, A2.chunk)]
+                dt2, ex = cpu_reference_run(cs, cores, lvl)
+                d["cpu_baseline"] = {"value": round(smp / dt2 / 1e6, 2), "unit": "MB/s", "cores": cores, "kind": "reference",
+                                     "sample": f"first {smp >> 20} MiB ({len(cs)} chunks)"}
+                idn = sum(1 for i, x in enumerate(ex) if osz[i] == x.size and bool((A2.stream(i, osz[i]) == x).all()))
+                d["parity_checked"] = {"n": len(ex), "identical": idn}
+            legs[name] = d
+            return osz
+
+        def decode_leg(name, A2, osz):
+            ins = [A2.out_ptrs[i] for i in range(A2.n)]
+            h_back = torch.empty(A2.total + 64 * A2.n, dtype=torch.uint8).pin_memory()
+            outs = [h_back.data_ptr() + i * (A2.chunk + 64) for i in range(A2.n)]
+            api.decode_chunks_raw(ins, osz, outs, A2.sizes)
+            t1 = time.perf_counter()
+            got = api.decode_chunks_raw(ins, osz, outs, A2.sizes)
+            e = time.perf_counter() - t1
+            st = csc_b200.get_stats()
+            ok = got == A2.sizes and all(bool((h_back.numpy()[i * (A2.chunk + 64): i * (A2.chunk + 64) + A2.sizes[i]] ==
+                                              A2.h_in.numpy()[i * A2.chunk: i * A2.chunk + A2.sizes[i]]).all()) for i in (0, A2.n // 2, A2.n - 1))
+            r = sum(osz) / A2.total
+            kms = st["ms_decode"] + st["ms_unfilter"]
+            return {"value": round(A2.total / st["ms_total_gpu"] / 1e3, 2), "unit": "MB/s (uncompressed, device time incl. copies)",
+                    "e2e": {"value": round(A2.total / e / 1e6, 2), "unit": "MB/s", "h2d_bytes_per_step": int(sum(osz)), "d2h_bytes_per_step": A2.total},
+                    "kernels_ms": {"decode": round(st["ms_decode"], 2), "unfilter": round(st["ms_unfilter"], 2)},
+                    "roofline": {"bound": "hbm", "kernel": "k_decode", "achieved": round(A2.total * (1 + r) / (kms / 1e3) / 1e9, 2) if kms else 0.0,
+                                 "peak": peak, "unit": "GB/s", "frac": round(A2.total * (1 + r) / (kms / 1e3) / 1e9 / peak, 6) if kms else 0.0, "traffic": None},
+                    "roundtrip_ok": bool(ok), "archive": name}
+
+        dec = {}
+        o1 = leg("m1_text", A, data, 1, "text")
+        dec["m1_text"] = decode_leg("m1_text", A, o1)
+        o3 = leg("m3_text", A, data, 3, "text")
+        dec["m3_text"] = decode_leg("m3_text", A, o3)
+        # the chunk-size / ratio trade-off of the headline level (csarc's own minimum split is 1 MiB, csarc.cpp:533-535)
+        sweep = []
+        for ck in (1 << 20, 4 << 20):
+            A3 = Arena(torch, api, data, ck)
+            api.encode_chunks_device(A3.dev_ptrs, A3.sizes, DICT, level)
+            ms, _, _, dz = timed_device(api, csc_b200, A3, level, 1)
+            sweep.append({"chunk": ck, "MBps": round(total / ms / 1e3, 2), "ratio": round(sum(dz) / total, 5)})
+            del A3
+        sweep.insert(0, {"chunk": chunk, "MBps": round(value, 2), "ratio": round(ratio, 5)})
+        if have_ref:
+            t1 = time.perf_counter()
+            one = refbind.encode(data[: 64 << 20], DICT, level)
+            sweep.append({"chunk": "unchunked (reference, first 64 MiB as ONE stream, 1 host thread)", "MBps": round((64 << 20) / (time.perf_counter() - t1) / 1e6, 2),
+                          "ratio": round(one.size / (64 << 20), 5)})
+        del A
+        torch.cuda.empty_cache()
+        mixed = gen("mixed", args.total, rank)
+        AM = Arena(torch, api, mixed, chunk)
+        om1 = leg("m1_mixed", AM, mixed, 1, "mixed")
+        dec["m1_mixed"] = decode_leg("m1_mixed", AM, om1)
+        om3 = leg("m3_mixed", AM, mixed, 3, "mixed")
+        dec["m3_mixed"] = decode_leg("m3_mixed", AM, om3)
+        line["levels"] = legs
+        line["decode"] = dec
+        line["chunk_sweep"] = sweep
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

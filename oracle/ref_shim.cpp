@@ -126,6 +126,39 @@ int ref_encode(const uint8_t *in, size_t n, uint32_t dict_size, int level, uint3
     return ret2;
 }
 
+// Same, but the input arrives through SEVERAL CSCEnc_Encode calls on one handle (csc_enc.cpp:160-191 keeps
+// model and window across calls): part k holds part_sizes[k] bytes.
+int ref_encode_parts(const uint8_t *in, const size_t *part_sizes, int nparts, uint32_t dict_size, int level,
+                     int with_props, uint8_t *out, size_t cap, size_t *out_n) {
+    CSCProps p;
+    CSCEncProps_Init(&p, dict_size, level);
+    MemOut mo;
+    mo.os.Write = mem_write;
+    mo.p = out; mo.cap = cap; mo.off = 0; mo.overflow = 0;
+    if (with_props) {
+        if (cap < CSC_PROP_SIZE) return -1;
+        CSCEnc_WriteProperties(&p, out, 0);
+        mo.off = CSC_PROP_SIZE;
+    }
+    CSCEncHandle h = CSCEnc_Create(&p, (ISeqOutStream *)&mo, &g_zero_alloc);
+    if (!h) return -2;
+    int ret = 0;
+    size_t off = 0;
+    for (int k = 0; k < nparts && ret >= 0; k++) {
+        MemIn mi;
+        mi.is.Read = mem_read;
+        mi.p = in + off; mi.n = part_sizes[k]; mi.off = 0; mi.read_size = 0;
+        ret = CSCEnc_Encode(h, (ISeqInStream *)&mi, NULL);
+        off += part_sizes[k];
+    }
+    int ret2 = CSCEnc_Encode_Flush(h);
+    CSCEnc_Destroy(h);
+    *out_n = mo.off;
+    if (mo.overflow) return -3;
+    if (ret < 0) return ret;
+    return ret2;
+}
+
 // Whole stream (starting with the 10-byte props header) through the reference
 // decoder, the call sequence of csa_worker.cpp:75-83.
 int ref_decode(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_n) {

@@ -125,6 +125,22 @@ def encode(data, dict_size: int, level: int, read_size: int = 0, flt_mask: int =
     return (res, tr) if trace else res
 
 
+def encode_parts(data, dict_size: int, level: int, part_sizes) -> np.ndarray:
+    """Reference stream when the input is fed through several CSCEnc_Encode calls on ONE handle."""
+    a = _u8(data)
+    assert sum(part_sizes) == a.size
+    l = lib()
+    l.ref_encode_parts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                   C.POINTER(C.c_size_t)]
+    ps = (C.c_size_t * len(part_sizes))(*part_sizes)
+    out = np.empty(out_bound(a.size), dtype=np.uint8)
+    n = C.c_size_t(0)
+    r = l.ref_encode_parts(a.ctypes.data, ps, len(part_sizes), dict_size, level, 1, out.ctypes.data, out.size, C.byref(n))
+    if r < 0:
+        raise RuntimeError(f"ref_encode_parts failed: {r}")
+    return out[: n.value].copy()
+
+
 def decode(stream, raw_size_hint: int) -> np.ndarray:
     a = _u8(stream)
     out = np.empty(max(raw_size_hint, 16) + 64, dtype=np.uint8)

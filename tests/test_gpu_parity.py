@@ -308,3 +308,147 @@ def test_reference_cli_relinked_against_the_product(gpu_lib, ref, tmp_path):
         assert subprocess.run([exe_ref, "d", str(a), str(back_ref)], capture_output=True).returncode == 0
         assert same(np.fromfile(back_gpu, dtype=np.uint8), d) and same(np.fromfile(back_ref, dtype=np.uint8), d)
 
+
+
+def test_relinked_csarc_on_the_gpu(gpu_lib, ref, tmp_path):
+    """The reference archiver (archiver/*.cpp, unmodified) relinked against libcsc_b200.so, on a B200: worker
+    threads (-t8), single-file split (-p), default 32 MB dictionary, a task LONGER than its dictionary (-d, window
+    wrap) and the compressed index all run through the library; archives extract with the stock csarc and the
+    other way round.  csa_worker.cpp:23-90, csarc.cpp:219-286,338-474."""
+    import subprocess
+    try:
+        exe, exe_ref = ref.cli("csarc_b200"), ref.cli("csarc_ref")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/csarc_* not built")
+    files = {"big.bin": synth.mixed(12 << 20, 41), "a.txt": synth.text(700000, 42), "b.exe": synth.exe(900000, 43),
+             "c.dat": synth.delta(300000, 4, 44)}
+    for n, d in files.items():
+        d.tofile(tmp_path / n)
+
+    def run(tool, *a):
+        r = subprocess.run([tool, *a], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (a, r.stdout[-500:], r.stderr[-500:])
+        return r
+
+    def extracted_ok(outdir, names):
+        for n in names:
+            assert same(np.fromfile(tmp_path / outdir / n, dtype=np.uint8), files[n]), (outdir, n)
+
+    # one big file split into tasks, 8 worker threads = 8 concurrent handles on the library
+    run(exe, "a", "-m1", "-t8", "-p8", "-f", "gpu_split.csa", "big.bin")
+    run(exe, "t", "-t8", "gpu_split.csa")
+    for tool, out in ((exe, "o1"), (exe_ref, "o2")):
+        os.mkdir(tmp_path / out)
+        run(tool, "x", "-t4", "-o", out + "/", "gpu_split.csa")
+        extracted_ok(out, ["big.bin"])
+    # several files, solid tasks by extension, -m3; a 2 MB dictionary makes the 12 MiB task wrap its window
+    names = list(files)
+    run(exe, "a", "-m3", "-d2m", "-t4", "-f", "gpu_multi.csa", *names)
+    run(exe_ref, "t", "-t4", "gpu_multi.csa")
+    os.mkdir(tmp_path / "o3")
+    run(exe_ref, "x", "-o", "o3/", "gpu_multi.csa")
+    extracted_ok("o3", names)
+    # the stock archiver's output through the GPU decoder
+    run(exe_ref, "a", "-m2", "-t4", "-p4", "-f", "ref.csa", "big.bin")
+    os.mkdir(tmp_path / "o4")
+    run(exe, "x", "-t8", "-o", "o4/", "ref.csa")
+    extracted_ok("o4", ["big.bin"])
+    # same level / dictionary / split: the two archivers write the same bytes (task order in the archive is by
+    # completion, so compare with one worker thread)
+    run(exe, "a", "-m2", "-t1", "-p4", "-f", "g1.csa", "big.bin")
+    run(exe_ref, "a", "-m2", "-t1", "-p4", "-f", "r1.csa", "big.bin")
+    assert same(np.fromfile(tmp_path / "g1.csa", dtype=np.uint8), np.fromfile(tmp_path / "r1.csa", dtype=np.uint8))
+
+
+def test_handles_from_eight_threads(gpu_lib, ref):
+    """csarc's threading model (csarc.cpp:338-409): one handle per worker thread, all live at once"""
+    import threading
+    data = [synth.mixed(900000 + 4099 * i, 50 + i) for i in range(8)]
+    exp = [ref.encode(d, d.size, 1 + i % 4) for i, d in enumerate(data)]
+    got, back, errs = [None] * 8, [None] * 8, []
+
+    def work(i):
+        try:
+            got[i] = gpu_lib.encode_stream(data[i], data[i].size, 1 + i % 4)
+            back[i] = gpu_lib.decode_stream(exp[i])
+        except Exception as e:   # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i in range(8):
+        assert same(got[i], exp[i]), i
+        assert same(back[i], data[i]), i
+
+
+def test_repeated_encode_calls_on_one_handle(gpu_lib, ref):
+    """CSCEnc_Encode may be called again on the same handle (csc_enc.cpp:160-191: model and window persist, every
+    Read() is one more flush segment); the stream equals the reference's for the concatenated input"""
+    from csc_b200 import api
+    l = api.lib()
+    d = synth.mixed(3 << 20, 61)
+    cuts = [0, 700000, 700000 + (1 << 21), d.size]
+    p = gpu_lib.props_init(d.size, 2)
+    out = bytearray()
+    hdr = (C.c_uint8 * 10)()
+    l.CSCEnc_WriteProperties(C.byref(p), hdr, 0)
+    out += bytes(hdr)
+    outs = api._OutStream(api.WRITE_FN(lambda _p, buf, size: (out.extend(C.string_at(buf, size)), size)[1]))
+    h = l.CSCEnc_Create(C.byref(p), C.byref(outs), None)
+    assert h
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = d[a:b]
+        st = {"off": 0}
+
+        def rd(_p, buf, psize, part=part, st=st):
+            want = min(psize[0], part.size - st["off"])
+            if want:
+                C.memmove(buf, part.ctypes.data + st["off"], want)
+            st["off"] += want
+            psize[0] = want
+            return 0
+
+        ins = api._InStream(api.READ_FN(rd))
+        assert l.CSCEnc_Encode(h, C.byref(ins), None) == 0
+    assert l.CSCEnc_Encode_Flush(h) == 0
+    l.CSCEnc_Destroy(h)
+    got = np.frombuffer(bytes(out), dtype=np.uint8)
+    assert same(gpu_lib.decode_stream(got), d)
+    assert same(got, ref.encode_parts(d, d.size, 2, [b - a for a, b in zip(cuts[:-1], cuts[1:])]))
+
+
+def test_decoder_stops_at_the_end_of_its_stream(gpu_lib, ref):
+    """CSCDec_Decode never asks its ISeqInStream for bytes behind the stream's last block (csc_memio.cpp:19-57 reads
+    header, size and payload per block): a reader that fails on over-read, with other data behind the stream"""
+    from csc_b200 import api
+    l = api.lib()
+    d = synth.mixed(2500000, 71)
+    s = ref.encode(d, d.size, 2)
+    blob = np.concatenate([s, np.frombuffer(b"TRAILING-ARCHIVE-DATA" * 100, dtype=np.uint8)])
+    p = gpu_lib.CSCProps()
+    hdr = (C.c_uint8 * 10)(*blob[:10].tolist())
+    l.CSCDec_ReadProperties(C.byref(p), hdr)
+    st = {"off": 10, "over": False}
+    out = bytearray()
+
+    def rd(_p, buf, psize):
+        want = psize[0]
+        if st["off"] + want > s.size:
+            st["over"] = True
+            return -1
+        C.memmove(buf, blob.ctypes.data + st["off"], want)
+        st["off"] += want
+        return 0
+
+    ins = api._InStream(api.READ_FN(rd))
+    outs = api._OutStream(api.WRITE_FN(lambda _p, buf, size: (out.extend(C.string_at(buf, size)), size)[1]))
+    h = l.CSCDec_Create(C.byref(p), C.byref(ins), None)
+    assert h
+    assert l.CSCDec_Decode(h, C.byref(outs), None) == 0
+    l.CSCDec_Destroy(h)
+    assert not st["over"] and st["off"] == s.size
+    assert same(np.frombuffer(bytes(out), dtype=np.uint8), d)
