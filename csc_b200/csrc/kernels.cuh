@@ -382,16 +382,16 @@ k_filter_runs(u8 *lz, u8 *tmp, const GRun *__restrict__ runs, const u32 *__restr
 }
 
 // ------------------------------------------------------------------ match finder
-// One CTA per 8 KiB block (= sub-block of the reference window copy).  Keys are
-// (stream << key_shift) | HASH6 so that one batch-wide stable sort groups equal hashes of
-// one stream in position order.
+// One CTA per sub-block of the reference window copy.  The sort key is the hash value alone: the radix
+// sort is segmented by stream (radix_sort.cuh), so a stable sort of the hashes groups equal hashes of one
+// stream in position order.
 static const int kMfThreads = 256;
 // Each thread hashes 4 consecutive positions from three staged words (funnel shifts instead of byte loads)
 // and writes its keys / positions as 16-byte vectors; the HASH2%16 / HASH6==0 bitmaps are assembled per
 // 32 positions with shuffles (one atomic per non-empty word instead of one per set bit).
 __global__ void __launch_bounds__(kMfThreads)
 k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u32 *__restrict__ stream_bits,
-          const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_wnd, u32 key_shift, u64 *__restrict__ keys,
+          const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_wnd, u32 key_shift, RsKey *__restrict__ keys,
           u32 *__restrict__ vals, u32 *Z2, u32 *Z6, u32 which) {
     __shared__ __align__(16) u32 sw[kBlock / 4 + 8];
     const BlockDesc bd = blk[blockIdx.x];
@@ -425,7 +425,6 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
     }
     const u32 bits = stream_bits[bd.stream];
     const u64 bitbase = (stream_goff[bd.stream]) + bd.x;   // bitmaps are indexed by batch byte offset
-    const u64 skey = (u64)bd.stream << key_shift;
     const bool excluded = which < 6 && (bd.flags & 1);
     const bool vec = (bd.cpos & 3) == 0;
     const u32 lane = threadIdx.x & 31;
@@ -433,7 +432,7 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
         const bool in = i0 < bd.size;
         u32 w0 = 0, w1 = 0, w2 = 0, w3 = 0;
         if (in) { w0 = sw[i0 >> 2]; w1 = sw[(i0 >> 2) + 1]; w2 = sw[(i0 >> 2) + 2]; w3 = sw[(i0 >> 2) + 3]; }
-        u64 k[4];
+        RsKey k[4];
         u32 z2 = 0, z6 = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -444,8 +443,8 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
             else if (which == 6) h = bits ? ((v ^ ((u & 0xFFFF) << 13)) * 2654435761u) >> (32 - bits) : 0;   // HASH6 csc_mf.cpp:35-42
             else if (which == 3) h = ((v & 0xFF) << 8) ^ (((v >> 8) & 0xFF) << 5) ^ ((v >> 16) & 0xFF);   // HASH3 :30-33
             else h = h2;                                                                          // HASH2 :23-28
-            // blocks left out of a 2-/3-byte chain carry flag bit 63 and sort into the all-ones bucket, where k_mf_rows skips them
-            k[j] = excluded ? ((1ull << 63) | skey | ((1u << key_shift) - 1)) : (skey | h);
+            // blocks left out of a 2-/3-byte chain carry flag bit 31 and sort into the all-ones bucket, where k_mf_rows skips them
+            k[j] = excluded ? (0x80000000u | ((1u << key_shift) - 1)) : h;
             if (in && i0 + j < bd.size) {
                 if ((h2 & 15) == 0) z2 |= 1u << j;
                 if (bits && h == 0) z6 |= 1u << j;
@@ -454,8 +453,7 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
         if (in) {
             const u32 c = bd.cpos + i0, x = bd.x + i0;
             if (vec && i0 + 4 <= bd.size) {
-                reinterpret_cast<ulonglong2 *>(keys + c)[0] = make_ulonglong2(k[0], k[1]);
-                reinterpret_cast<ulonglong2 *>(keys + c)[1] = make_ulonglong2(k[2], k[3]);
+                *reinterpret_cast<uint4 *>(keys + c) = make_uint4(k[0], k[1], k[2], k[3]);
                 *reinterpret_cast<uint4 *>(vals + c) = make_uint4(x, x + 1, x + 2, x + 3);
             } else {
 #pragma unroll
@@ -476,49 +474,55 @@ k_mf_hash(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u3
     }
 }
 
-__global__ void k_mf_rows(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u32 n, u32 key_shift,
-                          const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_K, u32 *__restrict__ P6,
-                          const u32 *__restrict__ pos_stream, u32 kforce, u32 row_stride, u32 col0) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u64 k = keys[i];
-    if (k >> 63) return;   // position of a block left out of this chain (array pre-filled with kNone)
-    const u32 s = (u32)(k >> key_shift);
-    const u32 K = kforce ? kforce : stream_K[s];
+// Rows from the sorted array, one CTA per sort tile (a tile never spans two streams).  Element i of a stream's
+// sorted range has its same-hash predecessors right in front of it, in position order.
+__global__ void __launch_bounds__(256)
+k_mf_rows(const RsKey *__restrict__ keys, const u32 *__restrict__ vals, const RsTile *__restrict__ tiles,
+          const u64 *__restrict__ stream_goff, const u32 *__restrict__ stream_K, u32 *__restrict__ P6, u32 kforce, u32 row_stride,
+          u32 col0) {
+    const RsTile t = tiles[blockIdx.x];
+    const u32 K = kforce ? kforce : stream_K[t.stream];
     if (!K) return;
-    // row_stride != 0: write K entries at column col0 of a wider row (-m5 merges several such lists)
-    u32 *row = P6 + (stream_goff[s] + vals[i]) * (row_stride ? row_stride : K) + col0;
-    if (kforce != 1 && K <= 8) {
-        // 6-byte rows (no flagged entries): the K predecessors in the sorted array are read with independent
-        // loads, the row is the prefix of them that still has this element's (stream, hash) key
-        u64 kk[8];
-        u32 vv[8];
+    const u64 sg = stream_goff[t.stream];
+    for (u32 jj = threadIdx.x; jj < t.count; jj += 256) {
+        const u32 i = t.start + jj;
+        const RsKey k = keys[i];
+        if (k >> 31) continue;   // position of a block left out of this chain (array pre-filled with kNone)
+        const u32 before = i - t.sstart;   // elements of this stream in front of i
+        // row_stride != 0: write K entries at column col0 of a wider row (-m5 merges several such lists)
+        u32 *row = P6 + (sg + vals[i]) * (row_stride ? row_stride : K) + col0;
+        if (kforce != 1 && K <= 8) {
+            // 6-byte rows (no flagged entries): the K predecessors in the sorted array are read with independent
+            // loads, the row is the prefix of them that still has this element's hash
+            RsKey kk[8];
+            u32 vv[8];
 #pragma unroll
-        for (u32 c = 0; c < 8; c++) {
-            const bool in = c < K && i > c;
-            kk[c] = in ? keys[i - 1 - c] : ~k;
-            vv[c] = in ? vals[i - 1 - c] : kNone;
+            for (u32 c = 0; c < 8; c++) {
+                const bool in = c < K && before > c;
+                kk[c] = in ? keys[i - 1 - c] : ~k;
+                vv[c] = in ? vals[i - 1 - c] : kNone;
+            }
+            bool ok = true;
+#pragma unroll
+            for (u32 c = 0; c < 8; c++) { ok = ok && kk[c] == k; vv[c] = ok ? vv[c] : kNone; }
+            if (K == 8 && !row_stride) {
+                reinterpret_cast<uint4 *>(row)[0] = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+                reinterpret_cast<uint4 *>(row)[1] = make_uint4(vv[4], vv[5], vv[6], vv[7]);
+            } else {
+#pragma unroll
+                for (u32 c = 0; c < 8; c++) if (c < K) row[c] = vv[c];
+            }
+            continue;
         }
-        bool ok = true;
-#pragma unroll
-        for (u32 c = 0; c < 8; c++) { ok = ok && kk[c] == k; vv[c] = ok ? vv[c] : kNone; }
-        if (K == 8 && !row_stride) {
-            reinterpret_cast<uint4 *>(row)[0] = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-            reinterpret_cast<uint4 *>(row)[1] = make_uint4(vv[4], vv[5], vv[6], vv[7]);
-        } else {
-#pragma unroll
-            for (u32 c = 0; c < 8; c++) if (c < K) row[c] = vv[c];
+        bool live = true;
+        u32 j = i;
+        for (u32 c = 0; c < K; c++) {
+            // previous element of the same hash run; flagged entries only occur in the all-ones bucket
+            while (live && j > t.sstart && (keys[j - 1] >> 31) && ((keys[j - 1] ^ k) << 1) == 0) j--;
+            live = live && j > t.sstart && keys[j - 1] == k;
+            row[c] = live ? vals[j - 1] : kNone;
+            if (live) j--;
         }
-        return;
-    }
-    bool live = true;
-    u32 j = i;
-    for (u32 c = 0; c < K; c++) {
-        // previous element of the same (stream, hash) run; flagged entries only occur in the all-ones bucket
-        while (live && j > 0 && (keys[j - 1] >> 63) && ((keys[j - 1] ^ k) << 1) == 0) j--;
-        live = live && j > 0 && keys[j - 1] == k;
-        row[c] = live ? vals[j - 1] : kNone;
-        if (live) j--;
     }
 }
 
@@ -622,48 +626,112 @@ template <> struct RowIO<8> {
     }
 };
 
+// Forward match lengths L6[p][k] = LCP(p, P6[p][k]) capped at the sub-block end.
+//
+// One CTA per sub-block, one LANE per position: a warp walks 1024 consecutive positions 32 at a time, so the
+// rows arrive as coalesced kilobytes and the lengths leave the same way.  Most compares disappear: if
+// (p-1, e-1) sits at the same rank of the previous position's row with length m >= 1, then LCP(p, e) = m - 1
+// exactly (same cap), the common case in repetitive data where whole phrases repeat.  Such an entry is
+// LINKED to its left neighbour; the others are chain HEADS and touch the window (8-byte words; matches that
+// run long are finished by the whole warp).  The lengths then flow from the heads down the lanes as a
+// segmented copy-scan of (length + lane), five shuffle steps per rank.  A link whose predecessor ends with
+// length 0 (hash collision) breaks its chain: the entry behind it becomes a head and the scan is repeated.
 template <int K>
-__global__ void __launch_bounds__(kMfThreads, K == 8 ? 4 : 1)
+__global__ void __launch_bounds__(kMfThreads)
 k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const u64 *__restrict__ stream_goff,
             const u32 *__restrict__ P6, u16 *__restrict__ L6) {
     const BlockDesc bd = blk[blockIdx.x];
+    if (!bd.size) return;
     const u64 sg = stream_goff[bd.stream];
     const u8 *base = lz + sg;
-    const u32 i0 = threadIdx.x * 32;
-    if (i0 >= bd.size) return;
-    const u32 i1 = min(i0 + 32, bd.size);
-    u32 pe[K], pl[K];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, FULL = 0xFFFFFFFFu;
+    const u32 span = 32 * 32;                                  // positions per warp
+    const u32 w0 = warp * span;
+    if (w0 >= bd.size) return;
+    const u32 w1 = min(w0 + span, bd.size);
+    u32 le[K], ll[K];                                          // row and lengths of the previous group's last lane
 #pragma unroll
-    for (int k = 0; k < K; k++) { pe[k] = kNone; pl[k] = 0; }
-    u32 e[K], en[K];
-    RowIO<K>::load(P6 + (sg + bd.x + i0) * K, en);
-    for (u32 i = i0; i < i1; i++) {
+    for (int k = 0; k < K; k++) { le[k] = kNone; ll[k] = 0; }
+    for (u32 g0 = w0; g0 < w1; g0 += 32) {
+        const u32 i = g0 + lane;
+        const bool in = i < w1;
         const u32 x = bd.x + i;
-        const u32 limit = bd.size - i;
+        const u32 limit = in ? bd.size - i : 0;
         const u64 at = (sg + x) * K;
+        u32 e[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) e[k] = en[k];
-        if (i + 1 < i1) RowIO<K>::load(P6 + at + K, en);   // next row in flight while this one is resolved
-        u32 l[K];
+        for (int k = 0; k < K; k++) e[k] = kNone;
+        if (in) RowIO<K>::load(P6 + at, e);
+        // links: the same rank of the left neighbour holds e - 1
+        u32 v[K];          // heads: length + lane (final); linked entries: the head's value, filled by the scan
+        u32 linkm = 0;     // bit k: entry k is linked to lane - 1
+        u32 headm = 0;     // bit k: entry k is a head whose v is final
+        u32 todo = 0;      // bit k: head that still needs its compare
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            l[k] = 0;
+            u32 pe = __shfl_up_sync(FULL, e[k], 1);
+            if (lane == 0) pe = le[k];
+            const bool has = e[k] != kNone && e[k] != 0 && pe == e[k] - 1;
+            v[k] = 0;
             if (e[k] == kNone) continue;
-            bool got = false;
-            if (e[k] > 0) {
-                if (pe[k] == e[k] - 1 && pl[k] >= 1) { l[k] = pl[k] - 1; got = true; }   // usual case: same rank
-                else {
+            if (lane == 0 && has && ll[k] >= 1) { v[k] = ll[k] - 1; headm |= 1u << k; }   // known from the previous group
+            else if (lane != 0 && has) linkm |= 1u << k;
+            else todo |= 1u << k;
+        }
+        for (;;) {
+            // ---- compares of the new heads
+            u32 longm = 0;
 #pragma unroll
-                    for (int j = 0; j < K; j++)
-                        // a new or a dropped candidate shifts the ranks by one or two: look only there
-                        if (j != k && j >= k - 2 && j <= k + 2 && !got && pe[j] == e[k] - 1 && pl[j] >= 1) { l[k] = pl[j] - 1; got = true; }
+            for (int k = 0; k < K; k++) {
+                if ((todo >> k) & 1) {
+                    const u32 cap = limit < 64 ? limit : 64;
+                    const u32 l = lcp_words(base + x, base + e[k], cap);
+                    v[k] = l + lane;
+                    if (l == 64 && limit > 64) longm |= 1u << k;
                 }
             }
-            if (!got) l[k] = lcp_words(base + x, base + e[k], limit);
-        }
-        RowIO<K>::store(L6 + at, l, e);
+            if (__any_sync(FULL, longm != 0)) {
 #pragma unroll
-        for (int k = 0; k < K; k++) { pe[k] = e[k]; pl[k] = l[k]; }
+                for (int k = 0; k < K; k++) {   // long matches: the warp finishes them 128 bytes per step
+                    u32 m = __ballot_sync(FULL, (longm >> k) & 1);
+                    while (m) {
+                        const u32 src = (u32)__ffs((int)m) - 1;
+                        m &= m - 1;
+                        const u32 sx = __shfl_sync(FULL, x, src), se = __shfl_sync(FULL, e[k], src), sl = __shfl_sync(FULL, limit, src);
+                        const u32 ext = 64 + lcp_bytes(base + sx + 64, base + se + 64, sl - 64);
+                        if (lane == src) v[k] = ext + lane;
+                    }
+                }
+            }
+            headm |= todo;
+            // ---- segmented copy-scan down the lanes, per rank: a linked entry takes the value of its chain's head
+            u32 done = headm;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 od = __shfl_up_sync(FULL, done, d);
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const u32 ov = __shfl_up_sync(FULL, v[k], d);
+                    if (lane >= (u32)d && ((linkm & ~done) >> k) & 1) v[k] = ov;
+                }
+                if (lane >= (u32)d) done |= od & linkm;
+            }
+            // ---- a chain only holds while its lengths stay >= 1: head length - offset must not go below 0.  The entry
+            // right behind a length 0 (value - lane == -1) is compared afresh and heads the rest of its chain.
+            todo = 0;
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (((linkm >> k) & 1) && v[k] - lane == 0xFFFFFFFFu) todo |= 1u << k;
+            if (!__any_sync(FULL, todo != 0)) break;
+            linkm &= ~todo;
+        }
+        // lengths = v - lane (never negative once every chain held)
+        u32 l[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) l[k] = e[k] == kNone ? 0 : v[k] - lane;
+        if (in) RowIO<K>::store(L6 + at, l, e);
+#pragma unroll
+        for (int k = 0; k < K; k++) { le[k] = __shfl_sync(FULL, e[k], 31); ll[k] = __shfl_sync(FULL, l[k], 31); }
     }
 }
 

@@ -248,6 +248,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
             for (u32 j = 0; j < nts; j++) {
                 RsTile t;
                 t.start = cstart + j * kRsTile; t.count = std::min(kRsTile, n_s - j * kRsTile); t.hbase = hb + j; t.nts = nts;
+                t.stream = s; t.sstart = cstart;
                 rst.push_back(t);
             }
             cstart += n_s; hb += 256 * nts;
@@ -259,7 +260,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     // ---- device memory
     int r = 0;
     r |= C.lz.ensure(total); r |= C.tmp.ensure(total);
-    r |= C.keys0.ensure((size_t)npos * 8 + 16); r |= C.keys1.ensure((size_t)npos * 8 + 16);
+    r |= C.keys0.ensure((size_t)npos * 4 + 16); r |= C.keys1.ensure((size_t)npos * 4 + 16);
     r |= C.vals0.ensure((size_t)npos * 4 + 16); r |= C.vals1.ensure((size_t)npos * 4 + 16);
     r |= C.P6.ensure(total * K * 4); r |= C.L6.ensure(total * K * 2);
     const size_t bmbytes = total / 8 + 64;
@@ -286,12 +287,12 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     u32 launches = 1;
     static bool smem_opt_in = false;
     if (!smem_opt_in) {
-        CK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRsTile * 12)));
+        CK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRsTile * 8)));
         smem_opt_in = true;
     }
     // sorts (keys0,vals0) by the low `hbits` key bits inside every stream; returns the buffers holding the result
-    auto sort_pairs = [&](u32 hbits, u64 *&kres, u32 *&vres) -> int {
-        u64 *ka = C.keys0.as<u64>(), *kb = C.keys1.as<u64>();
+    auto sort_pairs = [&](u32 hbits, RsKey *&kres, u32 *&vres) -> int {
+        RsKey *ka = C.keys0.as<RsKey>(), *kb = C.keys1.as<RsKey>();
         u32 *va = C.vals0.as<u32>(), *vb = C.vals1.as<u32>();
         for (u32 shift = 0; shift < hbits; shift += 8) {
             const u32 bits = std::min<u32>(8, hbits - shift), mask = (1u << bits) - 1;
@@ -299,7 +300,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
             rs_scan_a<<<rsNb, kRsThreads, 0, st>>>(C.rsH.as<u32>(), rsHn, C.rsB.as<u32>());
             rs_scan_b<<<1, kRsThreads, 0, st>>>(C.rsB.as<u32>(), rsNb);
             rs_scan_c<<<rsNb, kRsThreads, 0, st>>>(C.rsH.as<u32>(), rsHn, C.rsB.as<u32>());
-            rs_scatter<<<nrst, kRsThreads, kRsTile * 12, st>>>(ka, va, kb, vb, C.rstiles.as<RsTile>(), shift, mask, C.rsH.as<u32>());
+            rs_scatter<<<nrst, kRsThreads, kRsTile * 8, st>>>(ka, va, kb, vb, C.rstiles.as<RsTile>(), shift, mask, C.rsH.as<u32>());
             std::swap(ka, kb); std::swap(va, vb);
             launches += 5;
         }
@@ -388,23 +389,22 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     T.mark(st);                                                                   // 3
     launches += 3;
     // ---- match finder precomputation: 6-byte rows, then the 3-byte and 2-byte chains
-    const u32 *pos_stream = nullptr;
     k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), key_shift,
-                                           C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), 6);
+                                           C.keys0.as<RsKey>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), 6);
     T.mark(st);                                                                   // 4
-    u64 *ksorted = nullptr;
+    RsKey *ksorted = nullptr;
     u32 *vsorted = nullptr;
     sort_pairs(key_shift, ksorted, vsorted);
     T.mark(st);                                                                   // 5
-    k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(),
-                                                  C.P6.as<u32>(), pos_stream, bounded ? kBtKA : 0, bounded ? kBtRowK : 0, 0);
+    k_mf_rows<<<nrst, 256, 0, st>>>(ksorted, vsorted, C.rstiles.as<RsTile>(), C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
+                                    bounded ? kBtKA : 0, bounded ? kBtRowK : 0, 0);
     if (bounded) {   // two more candidate lists by 8- and 12-byte context, then one distance-ordered row
         for (u32 which = kBtCtxB; which <= kBtCtxC; which += kBtCtxC - kBtCtxB) {
             k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), key_shift,
-                                                   C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
+                                                   C.keys0.as<RsKey>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
             sort_pairs(key_shift, ksorted, vsorted);
-            k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, key_shift, C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
-                                                          pos_stream, which == kBtCtxB ? kBtKB : kBtKC, kBtRowK, which == kBtCtxB ? kBtKA : kBtKA + kBtKB);
+            k_mf_rows<<<nrst, 256, 0, st>>>(ksorted, vsorted, C.rstiles.as<RsTile>(), C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
+                                            which == kBtCtxB ? kBtKB : kBtKC, kBtRowK, which == kBtCtxB ? kBtKA : kBtKA + kBtKB);
         }
         k_mf_merge<<<nsub, 256, 0, st>>>(C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), C.P6.as<u32>());
         launches += 5;
@@ -421,9 +421,9 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         u32 *P = which == 3 ? C.P3.as<u32>() : C.P2.as<u32>();
         u16 *L = which == 3 ? C.L3.as<u16>() : C.L2.as<u16>();
         k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), shift,
-                                               C.keys0.as<u64>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
+                                               C.keys0.as<RsKey>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
         sort_pairs(shift, ksorted, vsorted);
-        k_mf_rows<<<(npos + 255) / 256, 256, 0, st>>>(ksorted, vsorted, npos, shift, C.sgoff.as<u64>(), C.sK.as<u32>(), P, pos_stream, 1, 0, 0);
+        k_mf_rows<<<nrst, 256, 0, st>>>(ksorted, vsorted, C.rstiles.as<RsTile>(), C.sgoff.as<u64>(), C.sK.as<u32>(), P, 1, 0, 0);
         k_mf_extend<1><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
     }
     T.mark(st);                                                                   // 8

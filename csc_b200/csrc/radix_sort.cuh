@@ -1,4 +1,4 @@
-// radix_sort.cuh -- segmented LSD radix sort of (key u64, position u32) pairs, hand-written for
+// radix_sort.cuh -- segmented LSD radix sort of (hash key u32, position u32) pairs, hand-written for
 // the match-finder precomputation ("parallel hash-key sort").
 //
 // The pairs arrive grouped by stream and in position order inside a stream.  Every pass is a
@@ -6,11 +6,12 @@
 // each stream's range: tiles never span two streams and the digit histogram is laid out as
 // [stream][digit][tile-of-stream], so one exclusive scan over that array yields, for every
 // (tile, digit), the destination of its first element inside the stream's own range.  The stream id
-// therefore never has to be sorted (7 passes instead of 11 for the three hash kinds), and equal
-// hashes keep their position order -- which is what turns the sorted array into hash chains.
+// therefore never has to be sorted NOR carried in the key (7 passes instead of 11 for the three hash
+// kinds, 8 bytes per element instead of 12), and equal hashes keep their position order -- which is
+// what turns the sorted array into hash chains.
 //
-// Per pass: rs_hist (8 B/elem read) -> 3 scan kernels over the histogram -> rs_scatter (12 B read +
-// 12 B write per element; ranks by warp match_any, tile reordered in shared memory so that the global
+// Per pass: rs_hist (4 B/elem read) -> 3 scan kernels over the histogram -> rs_scatter (8 B read +
+// 8 B write per element; ranks by warp match_any, tile reordered in shared memory so that the global
 // writes are coalesced runs).
 #pragma once
 #include <cuda_runtime.h>
@@ -23,20 +24,23 @@ static const u32 kRsTile = 4096;     // elements per tile
 static const u32 kRsThreads = 256;   // 8 warps, 512 elements each
 static const u32 kRsPerThread = kRsTile / kRsThreads;
 
+typedef u32 RsKey;   // hash value; bit 31 flags an element that is left out of its chain (sorts last)
 struct RsTile {
     u32 start;    // first element (compact index)
     u32 count;    // <= kRsTile
     u32 hbase;    // histogram index of (this tile, digit 0)
     u32 nts;      // tiles of this tile's stream = histogram stride between digits
+    u32 stream;   // the stream all elements of the tile belong to
+    u32 sstart;   // first element of that stream
 };
 
 __global__ void __launch_bounds__(kRsThreads)
-rs_hist(const u64 *__restrict__ keys, const RsTile *__restrict__ tiles, u32 shift, u32 mask, u32 *__restrict__ H) {
+rs_hist(const RsKey *__restrict__ keys, const RsTile *__restrict__ tiles, u32 shift, u32 mask, u32 *__restrict__ H) {
     __shared__ u32 h[256];
     const RsTile t = tiles[blockIdx.x];
     h[threadIdx.x] = 0;
     __syncthreads();
-    for (u32 i = threadIdx.x; i < t.count; i += kRsThreads) atomicAdd(&h[(u32)(keys[t.start + i] >> shift) & mask], 1u);
+    for (u32 i = threadIdx.x; i < t.count; i += kRsThreads) atomicAdd(&h[(keys[t.start + i] >> shift) & mask], 1u);
     __syncthreads();
     H[t.hbase + threadIdx.x * t.nts] = h[threadIdx.x];
 }
@@ -97,11 +101,11 @@ __global__ void __launch_bounds__(kRsThreads) rs_scan_c(u32 *H, u32 n, const u32
 // Register-lean on purpose (4 CTAs per SM): phase 1 keeps only the 16 ranks of a thread; the keys and
 // positions are read again in phase 3, when they still sit in L1/L2.
 __global__ void __launch_bounds__(kRsThreads, 4)
-rs_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout, u32 *__restrict__ vout,
+rs_scatter(const RsKey *__restrict__ kin, const u32 *__restrict__ vin, RsKey *__restrict__ kout, u32 *__restrict__ vout,
            const RsTile *__restrict__ tiles, u32 shift, u32 mask, const u32 *__restrict__ Hs) {
     extern __shared__ __align__(16) unsigned char dyn[];
-    u64 *skey = reinterpret_cast<u64 *>(dyn);                      // [kRsTile]
-    u32 *sval = reinterpret_cast<u32 *>(dyn + kRsTile * 8);        // [kRsTile]
+    RsKey *skey = reinterpret_cast<RsKey *>(dyn);                  // [kRsTile]
+    u32 *sval = reinterpret_cast<u32 *>(dyn + kRsTile * 4);        // [kRsTile]
     __shared__ u16 wcnt[kRsThreads / 32][256];
     __shared__ u32 gofs[256], lbase[256], s_w[kRsThreads / 32];
     const RsTile t = tiles[blockIdx.x];
@@ -113,13 +117,13 @@ rs_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__rest
     // phase 1: each warp ranks its 512 consecutive elements, 32 at a time, in order
     u32 rk[kRsPerThread];
     const u32 wbeg = warp * (kRsTile / (kRsThreads / 32));
-    const u64 *kt = kin + t.start;
+    const RsKey *kt = kin + t.start;
     const u32 *vt = vin + t.start;
 #pragma unroll
     for (u32 r = 0; r < kRsPerThread; r++) {
         const u32 i = wbeg + r * 32 + lane;
         const bool live = i < t.count;
-        const u32 dg = live ? ((u32)(kt[i] >> shift) & mask) : 0xFFFFFFFFu;
+        const u32 dg = live ? ((kt[i] >> shift) & mask) : 0xFFFFFFFFu;
         const u32 peers = __match_any_sync(0xFFFFFFFFu, dg);
         const u32 below = __popc(peers & ((1u << lane) - 1));
         u32 base = 0;
@@ -142,8 +146,8 @@ rs_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__rest
     for (u32 r = 0; r < kRsPerThread; r++) {
         const u32 i = wbeg + r * 32 + lane;
         if (i < t.count) {
-            const u64 kk = kt[i];
-            const u32 dg = (u32)(kk >> shift) & mask;
+            const RsKey kk = kt[i];
+            const u32 dg = (kk >> shift) & mask;
             const u32 p = lbase[dg] + wcnt[warp][dg] + rk[r];
             skey[p] = kk;
             sval[p] = vt[i];
@@ -152,8 +156,8 @@ rs_scatter(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__rest
     __syncthreads();
     // phase 4: coalesced runs to the digit's destination inside the stream range
     for (u32 i = threadIdx.x; i < t.count; i += kRsThreads) {
-        const u64 kk = skey[i];
-        const u32 dg = (u32)(kk >> shift) & mask;
+        const RsKey kk = skey[i];
+        const u32 dg = (kk >> shift) & mask;
         const u32 dst = gofs[dg] + (i - lbase[dg]);
         kout[dst] = kk;
         vout[dst] = sval[i];

@@ -28,12 +28,14 @@ struct RcCoder {
     // bytes are gathered into one aligned 8-byte word before they go to memory
     u64 acc;
 
+    // One output byte.  Written without data-dependent branches on the common path: 32 streams share a warp,
+    // and whatever one lane has to execute all lanes wait for.
     CSC_HDF void put(u32 b, u32 stamp) {
-        if (n < cap) {
-            acc |= (u64)(b & 0xFF) << (8 * (n & 7));
-            if ((n & 7) == 7) { *reinterpret_cast<u64 *>(out + (n & ~7u)) = acc; acc = 0; }
-        } else {
-            err = kErrOverflow;
+        const u32 sh = (n & 7) * 8;
+        acc |= (u64)(b & 0xFF) << sh;
+        if (sh == 56) {   // the aligned 8-byte word is complete
+            if (n < cap) *reinterpret_cast<u64 *>(out + (n & ~7u)) = acc; else err = kErrOverflow;
+            acc = 0;
         }
         n++;
         if (++blk == bsize) {   // a 64 KiB RC block completed (csc_coder.cpp:97-104)
@@ -42,29 +44,26 @@ struct RcCoder {
             blk = 0;
         }
     }
-    CSC_HDF void drain() {   // pending bytes of the gather word (the word stays open for the next segment)
-        if (n & 7) {
-            const u32 base = n & ~7u;
-            for (u32 k = 0; k < (n & 7); k++) if (base + k < cap) out[base + k] = (u8)(acc >> (8 * k));
-        }
+    CSC_HDF void drain() {   // pending bytes of the gather word
+        const u32 base = n & ~7u;
+        for (u32 k = 0; k < (n & 7); k++) { if (base + k < cap) out[base + k] = (u8)(acc >> (8 * k)); else err = kErrOverflow; }
     }
     CSC_HDF void shift_low(u32 stamp) {   // RC_ShiftLow, csc_coder.cpp:89-112
-        if ((u32)low < 0xFF000000u || (u32)(low >> 32) != 0) {
-            u32 t = cache;
-            const u32 carry = (u32)(low >> 32);
-            do {
-                put(t + carry, stamp);
-                t = 0xFF;
-            } while (--cachesize != 0);
-            cache = ((u32)low >> 24) & 0xFF;
+        const u32 lo32 = (u32)low, carry = (u32)(low >> 32);
+        if (lo32 < 0xFF000000u || carry) {
+            put(cache + carry, stamp);
+            while (cachesize > 1) { put(0xFF + carry, stamp); cachesize--; }   // pending 0xFF bytes (rare)
+            cache = lo32 >> 24;
+            cachesize = 0;
         }
         cachesize++;
-        low = (u64)((u32)low << 8);
+        low = (u64)(lo32 << 8);
     }
     CSC_HDF void step(u32 e, u32 stamp) {   // the coder half of EncodeBit, csc_coder.h:67-81
         const u32 bound = (range >> 12) * (e & 0xFFFu);
-        if (e & 0x8000u) range = bound;
-        else { low += bound; range -= bound; }
+        const bool one = (e & 0x8000u) != 0;
+        low += one ? 0u : bound;
+        range = one ? bound : range - bound;
         if (range < (1u << 24)) { range <<= 8; shift_low(stamp); }
     }
 
@@ -82,13 +81,17 @@ struct RcCoder {
             const u32 cnt = so.dec_len;
             u32 i = 0;
 #if defined(__CUDA_ARCH__)
-            for (; i + 8 <= cnt; i += 8) {   // dec_off is 8-aligned: one 16-byte load per 8 decisions
-                const uint4 v = *reinterpret_cast<const uint4 *>(d + i);
-                const u32 w[4] = {v.x, v.y, v.z, v.w};
+            if (cnt >= 8) {   // dec_off is 8-aligned: one 16-byte load per 8 decisions, the next one always in flight
+                uint4 nx = *reinterpret_cast<const uint4 *>(d);
+                for (; i + 8 <= cnt; i += 8) {
+                    const uint4 v = nx;
+                    if (i + 16 <= cnt) nx = *reinterpret_cast<const uint4 *>(d + i + 8);
+                    const u32 w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    step(w[k] & 0xFFFFu, 2 * (i + 2 * k) + 1);
-                    step(w[k] >> 16, 2 * (i + 2 * k + 1) + 1);
+                    for (int k = 0; k < 4; k++) {
+                        step(w[k] & 0xFFFFu, 2 * (i + 2 * k) + 1);
+                        step(w[k] >> 16, 2 * (i + 2 * k + 1) + 1);
+                    }
                 }
             }
 #endif
@@ -96,8 +99,7 @@ struct RcCoder {
             // Coder::Flush (csc_coder.cpp:40-48): five more bytes, then one byte is skipped, not stored (H3):
             // the host substitutes the stale ring byte
             for (int k = 0; k < 5; k++) shift_low(2 * cnt + 1);
-            if (n < cap) { if ((n & 7) == 7) { *reinterpret_cast<u64 *>(out + (n & ~7u)) = acc; acc = 0; } }
-            else err = kErrOverflow;
+            if ((n & 7) == 7) { if (n < cap) *reinterpret_cast<u64 *>(out + (n & ~7u)) = acc; else err = kErrOverflow; acc = 0; }
             n++; blk++;
             so.rc_off = rc0; so.rc_len = n - rc0;
             so.rev_off = ev0; so.rev_len = ev_n - ev0;
