@@ -64,25 +64,34 @@ void build_mf_cpu(const u8 *lz, u32 n, const std::vector<SubBlock> &subs, u32 wn
 
 // -m5 bounded search rows (csc_defs.h: kBt*): nearest earlier positions by 6-byte hash, 8- and 12-byte context
 // hash, merged by distance, duplicates removed -- what k_mf_hash / k_mf_rows / k_mf_merge compute on the device.
+// EXPERIMENT hook: CSC_M5_CLASSES="6:5,8:5,12:6" overrides the context classes (len:count), generic byte hash.
 void build_mf5_cpu(const u8 *lz, u32 n, const std::vector<SubBlock> &subs, u32 wnd, std::vector<u32> &P6, std::vector<u16> &L6) {
     const u32 bits = kBtHashBits, K = kBtRowK;
-    std::vector<u32> lastA((size_t)1 << bits, kNone), lastB((size_t)1 << bits, kNone), lastC((size_t)1 << bits, kNone);
-    std::vector<u32> prevA(n, kNone), prevB(n, kNone), prevC(n, kNone);
+    struct Cls { u32 len, cnt; std::vector<u32> last, prev; };
+    std::vector<Cls> cls;
+    const char *env = getenv("CSC_M5_CLASSES");
+    if (env) {
+        for (const char *q = env; *q;) { char *e; u32 l = strtoul(q, &e, 10); q = e + 1; u32 c = strtoul(q, &e, 10); q = *e ? e + 1 : e; cls.push_back({l, c, {}, {}}); }
+    } else {
+        cls.push_back({6, kBtKA, {}, {}}); cls.push_back({kBtCtxB, kBtKB, {}, {}}); cls.push_back({kBtCtxC, kBtKC, {}, {}});
+    }
+    for (auto &c : cls) { c.last.assign((size_t)1 << bits, kNone); c.prev.assign(n, kNone); }
     P6.assign((size_t)n * K, kNone);
     L6.assign((size_t)n * K, 0);
     for (const SubBlock &sb : subs) {
         u32 sb_end = sb.x + sb.size;
         for (u32 x = sb.x; x < sb_end; x++) {
             u32 avail = sb_end - x;
-            u32 hA = hash6_at(lz, x, sb_end, wnd, bits), hB = hash_ctx_at(lz, x, sb_end, wnd, kBtCtxB, bits),
-                hC = hash_ctx_at(lz, x, sb_end, wnd, kBtCtxC, bits);
-            prevA[x] = lastA[hA]; lastA[hA] = x;
-            prevB[x] = lastB[hB]; lastB[hB] = x;
-            prevC[x] = lastC[hC]; lastC[hC] = x;
             std::vector<u32> c;
-            u32 q = prevA[x]; for (u32 k = 0; k < kBtKA && q != kNone; k++) { c.push_back(q); q = prevA[q]; }
-            q = prevB[x]; for (u32 k = 0; k < kBtKB && q != kNone; k++) { c.push_back(q); q = prevB[q]; }
-            q = prevC[x]; for (u32 k = 0; k < kBtKC && q != kNone; k++) { c.push_back(q); q = prevC[q]; }
+            for (auto &cl : cls) {
+                u32 h;
+                if (cl.len == 6) h = hash6_at(lz, x, sb_end, wnd, bits);
+                else if (!env) h = hash_ctx_at(lz, x, sb_end, wnd, cl.len, bits);
+                else { u32 f = 2166136261u; for (u32 k = 0; k < cl.len; k++) f = (f ^ window_byte(lz, x + k, sb_end, wnd)) * 16777619u; h = (f * 0x27D4EB2Fu) >> (32 - bits); }
+                cl.prev[x] = cl.last[h]; cl.last[h] = x;
+                u32 q = cl.prev[x];
+                for (u32 k = 0; k < cl.cnt && q != kNone; k++) { c.push_back(q); q = cl.prev[q]; }
+            }
             std::sort(c.begin(), c.end(), [](u32 u, u32 v) { return u > v; });
             c.erase(std::unique(c.begin(), c.end()), c.end());
             for (u32 k = 0; k < K && k < c.size(); k++) {
