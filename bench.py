@@ -227,7 +227,7 @@ def main():
     # weak: every rank its own `total`; strong: contiguous chunk range of one fixed job
     if args.scaling == "strong":
         nch = (args.total + chunk - 1) // chunk
-        lo, hi = (nch * rank + world - 1) // world, (nch * (rank + 1) + world - 1) // world
+        lo, hi = api.chunk_range(nch, rank, world)   # the library's own partition rule
         job = gen("text", args.total, 0)
         data = job[lo * chunk: min(hi * chunk, args.total)]
         job_bytes = args.total

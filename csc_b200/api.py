@@ -20,7 +20,7 @@ _SO = os.environ.get("CSC_B200_LIB") or os.path.join(_HERE, "csrc", "libcsc_b200
 EXPORTS = ["CSCEncProps_Init", "CSCEnc_WriteProperties", "CSCEnc_EstMemUsage", "CSCEnc_Create", "CSCEnc_Destroy",
            "CSCEnc_Encode", "CSCEnc_Encode_Flush", "CSCDec_ReadProperties", "CSCDec_Create", "CSCDec_Destroy",
            "CSCDec_Decode", "CSCB200_EncodeBound", "CSCB200_EncodeChunks", "CSCB200_DecodeChunks",
-           "CSCB200_EncodeChunksDevice", "CSCB200_SetDevice", "CSCB200_SetDevices", "CSCB200_DeviceCount", "CSCB200_Trim",
+           "CSCB200_EncodeChunksDevice", "CSCB200_SetDevice", "CSCB200_SetDevices", "CSCB200_DeviceCount", "CSCB200_Trim", "CSCB200_ChunkRange",
            "CSCB200_GetStats", "CSCB200_Available"]
 
 
@@ -106,6 +106,13 @@ def set_devices(devs) -> None:
     r = lib().CSCB200_SetDevices(arr, len(devs))
     if r < 0:
         raise RuntimeError(f"CSCB200_SetDevices({devs}) failed: {r}")
+
+
+def chunk_range(n_chunks: int, rank: int, world: int):
+    """chunks [lo, hi) of part ``rank`` of ``world`` -- the library's own partition rule (no GPU needed)"""
+    lo, hi = C.c_int(0), C.c_int(0)
+    lib().CSCB200_ChunkRange(n_chunks, rank, world, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
 
 
 def device_count() -> int:

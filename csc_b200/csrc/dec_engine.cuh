@@ -128,7 +128,32 @@ struct Decoder {
         }
         state = (state * 4 + 1) & 0x3F;
     }
-    CSC_HD u32 decode_literal_sym(u16 *row) { return tree(row, 0x100) & 0xFF; }
+    // 8 bits under one order-1 row (decode_literal, csc_dec.cpp:155-167).  On the device the 512-byte row is fetched
+    // ONCE, 16 bytes per lane, instead of with eight dependent loads along the tree path; the probability of node i
+    // then comes from lane i / 8 by shuffle and only that lane stores the adapted value.
+    CSC_HD u32 decode_literal_sym(u16 *row) {
+#if defined(__CUDA_ARCH__)
+        const uint4 r = reinterpret_cast<const uint4 *>(row)[CSC_LANE];
+        u32 i = 1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (range < (1u << 24)) { range <<= 8; code = (code << 8) + rc_byte(); }
+            const u32 sub = i & 7, owner = i >> 3;
+            const u32 word = sub < 4 ? (sub < 2 ? r.x : r.y) : (sub < 6 ? r.z : r.w);
+            u32 p = (__shfl_sync(0xFFFFFFFFu, word, owner) >> ((sub & 1) * 16)) & 0xFFFFu;
+            const u32 bound = (range >> 12) * p;
+            u32 bit;
+            if (code < bound) { range = bound; p += (0xFFFu - p) >> 5; bit = 1; }
+            else { range -= bound; code -= bound; p -= p >> 5; bit = 0; }
+            if (CSC_LANE == owner) row[i] = (u16)p;
+            i = i + i + bit;
+        }
+        w_sync();
+        return i & 0xFF;
+#else
+        return tree(row, 0x100) & 0xFF;
+#endif
+    }
 
     // copy len bytes from x - dist (overlap allowed, csc_dec.cpp:516-518)
     CSC_HD void lz_copy(u32 dist, u32 len) {

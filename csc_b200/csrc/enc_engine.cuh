@@ -78,6 +78,7 @@ struct Encoder {
     u32 vld, W, K, good;
     bool tmode, want_tables;   // 2-/3-byte tables: false = chains + liveness bits, true = real tables (after a flip)
     bool wrap;                 // the stream is longer than its window: ring semantics apply (csc_lz.cpp:91-92)
+    bool tracing;              // debug trace requested (tests)
     u32 seg_dec0, seg_bc0, seg_bev0;
 
     CSC_HD Encoder(const EncStream &s, ModelSmall &m) : S(s), M(m) {}
@@ -102,7 +103,7 @@ struct Encoder {
         }
     }
     CSC_HD void trace(u32 k, u32 a, u32 b) {
-        if (S.trace) {
+        if (tracing) {
             if (tr_n < S.trace_cap) { S.trace[tr_n * 3] = k; S.trace[tr_n * 3 + 1] = a; S.trace[tr_n * 3 + 2] = b; }
             tr_n++;
         }
@@ -272,53 +273,124 @@ struct Encoder {
         }
         encode_matchlen_1(len);
     }
+    // ---- non-literal packets, lane-parallel -------------------------------------------------------------
+    // Every binary decision of a packet is a pure function of (state, length code, distance): decision k is
+    // worked out by lane k (slot + bit), all probabilities are fetched / adapted / appended in one go, the same
+    // shape as the literal fast path.  A packet never uses a slot twice.  Length codes >= 143 (matches longer
+    // than 144 bytes: the p_longlen escape chain) take the serial statement below.
+    CSC_HDF u32 slot_of(const u16 &pr) const { return (u32)(&pr - reinterpret_cast<const u16 *>(&M)); }
+    CSC_HDF static u32 len_ndec(u32 len) { return len < 8 ? 4u : len < 16 ? 5u : 9u; }
+    // decision j of encode_matchlen_1(len) (csc_model.cpp:113-145), len < 143
+    CSC_HDF u32 len_dec(u32 len, u32 j, u32 &bit) const {
+        if (len < 8) {
+            if (j == 0) { bit = 0; return slot_of(M.p_matchlen_slot[0]); }
+            const u32 c = (len | 8) << (j - 1);
+            bit = (c >> 2) & 1;
+            return slot_of(M.p_matchlen_extra1[c >> 3]);
+        }
+        if (j == 0) { bit = 1; return slot_of(M.p_matchlen_slot[0]); }
+        if (len < 16) {
+            if (j == 1) { bit = 0; return slot_of(M.p_matchlen_slot[1]); }
+            const u32 c = ((len - 8) | 8) << (j - 2);
+            bit = (c >> 2) & 1;
+            return slot_of(M.p_matchlen_extra2[c >> 3]);
+        }
+        if (j == 1) { bit = 1; return slot_of(M.p_matchlen_slot[1]); }
+        const u32 c = ((len - 16) | 0x80) << (j - 2);
+        bit = (c >> 6) & 1;
+        return slot_of(M.p_matchlen_extra3[c >> 7]);
+    }
+    // fetch / adapt / append decisions [k0, k1) of the current packet; slot_bit(k, bit) names decision k
+    template <class F> CSC_HDF void packet_decisions(u32 k0, u32 k1, F slot_bit) {
+        if (dec_n + (k1 - k0) > S.dec_cap) { err = kErrOverflow; return; }
+#if defined(__CUDA_ARCH__)
+        const u32 k = k0 + CSC_LANE;
+        if (k < k1) {
+#else
+        for (u32 k = k0; k < k1; k++) {
+#endif
+            u32 bit;
+            u16 *pp = reinterpret_cast<u16 *>(&M) + slot_bit(k, bit);
+            const u32 v = *pp;
+            *pp = (u16)(bit ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
+            S.dec[dec_n + (k - k0)] = (DecEntry)(v | (bit << 15));
+        }
+        dec_n += k1 - k0;
+        w_sync();
+    }
     CSC_HDN void encode_rep0len1() {   // csc_model.cpp:198-207
         trace(2, 0, 0);
-        enc_bit(M.p_state[state * 3 + 0], 1);
-        enc_bit(M.p_state[state * 3 + 1], 0);
-        enc_bit(M.p_state[state * 3 + 2], 0);
+        const u32 st = state;
+        packet_decisions(0, 3, [&](u32 k, u32 &bit) { bit = k == 0 ? 1u : 0u; return slot_of(M.p_state[st * 3 + k]); });
         ctx = 0;
         state = (state * 4 + 2) & 0x3F;
-        flush_bits();
     }
     CSC_HDN void encode_rep(u32 idx, u32 lencode) {   // csc_model.cpp:218-232
         trace(3, lencode, idx);
-        enc_bit(M.p_state[state * 3 + 0], 1);
-        enc_bit(M.p_state[state * 3 + 1], 0);
-        enc_bit(M.p_state[state * 3 + 2], 1);
-        u32 b1 = (idx >> 1) & 1, b0 = idx & 1;
-        enc_bit(M.p_repdist[state * 3 + 0], b1);
-        enc_bit(M.p_repdist[state * 3 + 1 + b1], b0);
-        encode_matchlen_2(lencode);
+        idx = w_uni_u32(idx);
+        lencode = w_uni_u32(lencode);
+        const u32 st = state, b1 = (idx >> 1) & 1, b0 = idx & 1;
+        if (lencode < 143) {
+            const u32 nl = len_ndec(lencode);
+            packet_decisions(0, 5 + nl, [&](u32 k, u32 &bit) {
+                if (k < 3) { bit = k == 1 ? 0u : 1u; return slot_of(M.p_state[st * 3 + k]); }
+                if (k == 3) { bit = b1; return slot_of(M.p_repdist[st * 3 + 0]); }
+                if (k == 4) { bit = b0; return slot_of(M.p_repdist[st * 3 + 1 + b1]); }
+                return len_dec(lencode, k - 5, bit);
+            });
+        } else {
+            enc_bit(M.p_state[st * 3 + 0], 1);
+            enc_bit(M.p_state[st * 3 + 1], 0);
+            enc_bit(M.p_state[st * 3 + 2], 1);
+            enc_bit(M.p_repdist[st * 3 + 0], b1);
+            enc_bit(M.p_repdist[st * 3 + 1 + b1], b0);
+            encode_matchlen_2(lencode);
+            flush_bits();
+        }
         state = (state * 4 + 3) & 0x3F;
-        flush_bits();
     }
     CSC_HDN void encode_match(u32 dist, u32 lencode) {   // csc_model.cpp:301-366
         trace(1, lencode, dist);
         dist = w_uni_u32(dist);
         lencode = w_uni_u32(lencode);
-        enc_bit(M.p_state[state * 3 + 0], 1);
-        enc_bit(M.p_state[state * 3 + 1], 1);
-        encode_matchlen_2(lencode);
+        const u32 st = state;
         u32 base, sbits;
         if (lencode == 0) { base = 0; sbits = 3; }
         else if (lencode <= 2) { base = 16 * (lencode - 1) + 8; sbits = 4; }
         else if (lencode <= 5) { base = 32 * (lencode - 3) + 8 + 32; sbits = 5; }
         else { base = 32 * 3 + 8 + 32; sbits = 5; }
-        u32 slot = dist_slot(dist);
-        u16 *p = M.p_dist + base;
-        u32 c = slot | (1u << sbits);
-        do { enc_bit(p[c >> sbits], (c >> (sbits - 1)) & 1); c <<= 1; } while (w_uni(c < (1u << (sbits * 2))));
+        const u32 slot = dist_slot(dist);
+        const u32 cs = slot | (1u << sbits);
+        if (lencode < 143) {
+            const u32 nl = len_ndec(lencode);
+            packet_decisions(0, 2 + nl + sbits, [&](u32 k, u32 &bit) {
+                if (k < 2) { bit = 1; return slot_of(M.p_state[st * 3 + k]); }
+                if (k < 2 + nl) return len_dec(lencode, k - 2, bit);
+                const u32 c = cs << (k - 2 - nl);   // distance-slot tree
+                bit = (c >> (sbits - 1)) & 1;
+                return slot_of(M.p_dist[base + (c >> sbits)]);
+            });
+        } else {
+            enc_bit(M.p_state[st * 3 + 0], 1);
+            enc_bit(M.p_state[st * 3 + 1], 1);
+            encode_matchlen_2(lencode);
+            u16 *p = M.p_dist + base;
+            u32 c = cs;
+            do { enc_bit(p[c >> sbits], (c >> (sbits - 1)) & 1); c <<= 1; } while (w_uni(c < (1u << (sbits * 2))));
+            flush_bits();
+        }
         if (w_uni(slot > 2)) {
-            u32 ebits = slot - 2;
-            u32 elen = dist - (1u << ebits) - 1;
-            if (w_uni(ebits > 4)) direct(elen >> 4, ebits - 4);
-            c = rev4(elen & 0x0F) | 0x10;
-            p = M.p_matchdist_extra + (ebits - 1) * 16;
-            do { enc_bit(p[c >> 4], (c >> 3) & 1); c <<= 1; } while (w_uni(c < 0x100));
+            const u32 ebits = slot - 2;
+            const u32 elen = dist - (1u << ebits) - 1;
+            if (w_uni(ebits > 4)) direct(elen >> 4, ebits - 4);   // raw bits between the slot and the four modelled low bits
+            const u32 ce = rev4(elen & 0x0F) | 0x10;
+            packet_decisions(0, 4, [&](u32 k, u32 &bit) {
+                const u32 c = ce << k;
+                bit = (c >> 3) & 1;
+                return slot_of(M.p_matchdist_extra[(ebits - 1) * 16 + (c >> 4)]);
+            });
         }
         state = (state * 4 + 1) & 0x3F;
-        flush_bits();
     }
     CSC_HDN void encode_int(u32 num) {   // csc_model.cpp:389-414
         u32 slot = num ? ilog2(num) : 0;
@@ -797,7 +869,7 @@ struct Encoder {
                 // the one probe site: u1 at x, or the lazy look-ahead u2 at x + 1
                 const u32 px = have ? x + 1 : x;
                 const u32 nc = fm_core(h, px, end - px, rep[0], rep[1], rep[2], rep[3]);
-                if (S.trace) trace_cands(px, nc);
+                if (tracing) trace_cands(px, nc);
                 Cand c = best_of(h, nc);
                 if (p_uni(!have)) { u1 = c; have = true; continue; }
                 if (p_uni(second_better(u1, c))) {
@@ -954,7 +1026,7 @@ struct Encoder {
             if (p_uni(!in_round || apcur < aplimit)) {
                 prefetch_core(h, x + 1, end);
                 const u32 n = fm_core(h, x, end - x, r0, r1, r2, r3);
-                if (S.trace) trace_cands(x, n);
+                if (tracing) trace_cands(x, n);
                 price_table(n, ns, t0, td, tp, t1d, t1p);
             }
             if (p_uni(!in_round)) {
@@ -1238,6 +1310,7 @@ struct Encoder {
         err = 0; tr_n = 0;
         tmode = false; want_tables = false;
         wrap = S.n > S.cfg.wnd_size;
+        tracing = S.trace != nullptr;
         gs = 5;
         while (((S.n + 63) >> gs) > 2048) gs++;   // 2048 summary bits cover the stream
         w_sync();

@@ -209,6 +209,7 @@ struct DecInput {
 inline int deframe(const u8 *s, size_t n, u32 bsize, DecInput &d) {
     size_t i = 0;
     d.rc.clear(); d.bc.clear(); d.rc_off.clear(); d.bc_off.clear();
+    d.rc.reserve(n + 16); d.bc.reserve(n / 4 + 64);
     while (i < n) {
         u8 fb = s[i++];
         u32 sz;

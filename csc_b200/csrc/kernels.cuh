@@ -815,18 +815,85 @@ k_decode(const DecStream *__restrict__ streams, u32 ns, u32 *queue) {
     }
 }
 
-// inverse filters: one thread per (stream, run); `out` already holds a copy of the window
-__global__ void k_unfilter(const DecStream *__restrict__ streams, u32 ns, u32 max_runs, u8 *const *__restrict__ outs,
-                           const DictTables *__restrict__ D) {
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 s = t / max_runs, r = t % max_runs;
-    if (s >= ns) return;
-    const DecStream &S = streams[s];
-    if (*S.status < 0 || r >= *S.n_runs) return;
-    const DecRun rn = S.runs[r];
-    u8 *out = outs[s];
-    if (rn.type == DT_EXE) e8e9_run(out + rn.off, rn.size, true);
-    else if (rn.type == DT_ENGTXT) dict_inverse(S.wnd + rn.off, rn.size, out + rn.off, *D);
+// dictionary inverse (csc_filters.cpp:337-369), one CTA per run.  A byte starts a token unless it is the second
+// byte of an escape pair (254, x >= 0x82); whether a 254 in front of it is itself a token start depends on the
+// parity of the run of 254s it ends, so every thread re-synchronises with a short look-back (pathological runs
+// fall back to the scalar statement).  Token output lengths -> block scan -> every thread writes its tokens; the
+// output is the first `size` bytes of the expansion (the forward transform pads its tail with spaces).
+__device__ void dict_inverse_cta(const u8 *src, u32 size, u8 *dst, const DictTables *Dg, u8 *s, u32 *s_warp) {
+    __shared__ u32 s_base, s_fallback;
+    if (threadIdx.x == 0) { s_base = 0; s_fallback = 0; }
+    __syncthreads();
+    const u32 max_symbol = Dg->max_symbol;
+    for (u32 t0 = 0; t0 < size; t0 += kFltTile) {
+        const u32 tn = min((u32)kFltTile, size - t0);
+        for (u32 i = threadIdx.x; i < kFltLook + tn + 8; i += kFltThreads) {
+            long long g = (long long)t0 + i - kFltLook;
+            s[i] = (g >= 0 && g < (long long)size) ? src[g] : (u8)0;
+        }
+        __syncthreads();
+        const u8 *w = s + kFltLook;   // w[i] = src[t0 + i]
+        const u32 a = threadIdx.x * kFltSpan, b = min(a + kFltSpan, tn);
+        u32 pos = a, cnt = 0;
+        if (a < tn) {
+            // is w[a] swallowed by an escape?  count the 254s right in front of it
+            if (w[a] >= 0x82) {
+                int k = 0;
+                while (k < (int)kFltLook && (long long)t0 + a - 1 - k >= 0 && w[(int)a - 1 - k] == 254) k++;
+                if (k == (int)kFltLook && (long long)t0 + a - 1 - k >= 0) s_fallback = 1;
+                if (k & 1) pos = a + 1;
+            }
+            for (u32 i = pos; i < b;) {
+                const u32 c = w[i];
+                if (c >= 0x82 && c < max_symbol) { const u8 *wd = Dg->word[c]; u32 l = 0; while (wd[l]) l++; cnt += l; i++; }
+                else if (c == 254 && t0 + i + 1 < size && w[i + 1] >= 0x82) { cnt += 1; i += 2; }
+                else { cnt += 1; i++; }
+            }
+        }
+        u32 tile_total;
+        u32 off = block_exscan(cnt, s_warp, &tile_total);
+        if (a < tn && !s_fallback) {
+            u32 o = s_base + off;
+            for (u32 i = pos; i < b && o < size;) {
+                const u32 c = w[i];
+                if (c >= 0x82 && c < max_symbol) {
+                    const u8 *wd = Dg->word[c];
+                    for (u32 j = 0; wd[j] && o < size; j++) dst[o++] = wd[j];
+                    i++;
+                } else if (c == 254 && t0 + i + 1 < size && w[i + 1] >= 0x82) { dst[o++] = w[i + 1]; i += 2; }
+                else { dst[o++] = (u8)c; i++; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tile_total;
+        __syncthreads();
+        if (s_fallback) break;
+    }
+    if (s_fallback) {   // exactness first
+        if (threadIdx.x == 0) dict_inverse(src, size, dst, *Dg);
+        __syncthreads();
+        return;
+    }
+    for (u32 o = s_base + threadIdx.x; o < size; o += kFltThreads) dst[o] = 0;   // (an expansion shorter than the run: csc_filters.cpp:367)
+}
+
+// inverse filters: one CTA per stream walks the run list the decoder left; `out` already holds a copy of the window
+__global__ void __launch_bounds__(kFltThreads)
+k_unfilter(const DecStream *__restrict__ streams, u32 ns, u8 *const *__restrict__ outs, const DictTables *__restrict__ D) {
+    __shared__ u8 s[kFltLook + kFltTile + 16];
+    __shared__ u32 s_warp[kFltThreads / 32];
+    const u32 sid = blockIdx.x;
+    if (sid >= ns) return;
+    const DecStream &S = streams[sid];
+    if (*S.status < 0) return;
+    const u32 nr = *S.n_runs;
+    u8 *out = outs[sid];
+    for (u32 r = 0; r < nr; r++) {
+        const DecRun rn = S.runs[r];
+        if (rn.type == DT_EXE) e8e9_run_cta(out + rn.off, rn.size, true, s, s_warp);
+        else if (rn.type == DT_ENGTXT) dict_inverse_cta(S.wnd + rn.off, rn.size, out + rn.off, D, s, s_warp);
+        __syncthreads();
+    }
 }
 
 }  // namespace cscb

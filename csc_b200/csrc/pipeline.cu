@@ -148,6 +148,18 @@ int ctx_init(Ctx &C, int dev) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// fn(i) for i in [0, n) on up to 16 host threads (framing / de-framing / staging copies are per-stream work)
+template <class Fn> void parallel_for(size_t n, size_t grain, Fn fn) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(std::min(hw, 16u), (n + grain - 1) / std::max<size_t>(grain, 1));
+    std::atomic<size_t> next{0};
+    auto work = [&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n) break; fn(i); } };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto &th : pool) th.join();
+}
+
 // bounded memory sink for framed output
 struct MemSink {
     u8 *p; size_t cap, off; bool overflow;
@@ -585,17 +597,22 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
     std::vector<u32> runcap(ns);
     size_t wtot = 0, rctot = 0, offtot = 0, runtot = 0;
     auto t0 = std::chrono::steady_clock::now();
-    for (u32 s = 0; s < ns; s++) {
+    std::atomic<int> bad{0};
+    parallel_for(ns, 8, [&](size_t s) {   // de-framing is independent per stream
         DecJob &J = *jobs[s];
         J.status = 0; J.out_size = 0;
         if (!J.predeframed) {
-            if (J.n < CSC_PROP_SIZE) { J.status = -1; return -1; }
+            if (J.n < CSC_PROP_SIZE) { J.status = -1; bad = 1; return; }
             memset(&J.props, 0, sizeof(J.props));
             read_props(&J.props, J.in);
         }
-        if (J.props.dict_size > 1024u * 1048576u || J.props.dict_size < 32 * 1024 || !J.props.csc_blocksize) { J.status = -1; return -1; }
-        if (!J.predeframed && deframe(J.in + CSC_PROP_SIZE, J.n - CSC_PROP_SIZE, J.props.csc_blocksize, J.di) < 0) { J.status = -1; return -1; }
-        if (J.di.rc_off.size() < 2 || J.di.bc_off.size() < 2) { J.status = -1; return -1; }
+        if (J.props.dict_size > 1024u * 1048576u || J.props.dict_size < 32 * 1024 || !J.props.csc_blocksize) { J.status = -1; bad = 1; return; }
+        if (!J.predeframed && deframe(J.in + CSC_PROP_SIZE, J.n - CSC_PROP_SIZE, J.props.csc_blocksize, J.di) < 0) { J.status = -1; bad = 1; return; }
+        if (J.di.rc_off.size() < 2 || J.di.bc_off.size() < 2) { J.status = -1; bad = 1; }
+    });
+    if (bad) return -1;
+    for (u32 s = 0; s < ns; s++) {
+        DecJob &J = *jobs[s];
         woff[s] = wtot; wtot = align_up(wtot + J.out_cap + 64, 256);
         rcoff[s] = rctot; rctot = align_up(rctot + J.di.rc.size(), 16);
         bcoff[s] = rctot; rctot = align_up(rctot + J.di.bc.size(), 16);
@@ -634,11 +651,14 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
     Timer &T = C.tm;
     T.n = 0;
     T.mark(st);                                                                   // 0
-    for (u32 s = 0; s < ns; s++) {
+    // the sub-streams of all jobs go through one pinned staging buffer: one upload instead of two per stream
+    if (C.h_rc.ensure(rctot + 64)) return kErrCuda;
+    parallel_for(ns, 8, [&](size_t s) {
         DecJob &J = *jobs[s];
-        CK(cudaMemcpyAsync(C.rc.as<u8>() + rcoff[s], J.di.rc.data(), J.di.rc.size(), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(C.rc.as<u8>() + bcoff[s], J.di.bc.data(), J.di.bc.size(), cudaMemcpyHostToDevice, st));
-    }
+        memcpy(C.h_rc.as<u8>() + rcoff[s], J.di.rc.data(), J.di.rc.size());
+        memcpy(C.h_rc.as<u8>() + bcoff[s], J.di.bc.data(), J.di.bc.size());
+    });
+    CK(cudaMemcpyAsync(C.rc.p, C.h_rc.p, rctot, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.doffs.p, offs.data(), offtot * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.streams.p, ds.data(), (size_t)ns * sizeof(DecStream), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(C.doutptr.p, outp.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, st));
@@ -652,9 +672,7 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
     k_decode<<<grid, kDecWarps * 32, 0, st>>>(C.streams.as<DecStream>(), ns, C.counters.as<u32>() + 1);
     T.mark(st);                                                                   // 2
     CK(cudaMemcpyAsync(C.dout.p, C.dwnd.p, wtot, cudaMemcpyDeviceToDevice, st));
-    u32 max_runs = *std::max_element(runcap.begin(), runcap.end());
-    u64 nthreads = (u64)ns * max_runs;
-    k_unfilter<<<(u32)((nthreads + 127) / 128), 128, 0, st>>>(C.streams.as<DecStream>(), ns, max_runs, C.doutptr.as<u8 *>(), C.d_DT);
+    k_unfilter<<<ns, kFltThreads, 0, st>>>(C.streams.as<DecStream>(), ns, C.doutptr.as<u8 *>(), C.d_DT);
     T.mark(st);                                                                   // 3
     CK(cudaGetLastError());
     if (C.h_meta.ensure((size_t)ns * 16)) return kErrCuda;
@@ -942,6 +960,9 @@ void CSCB200_DebugTrace(uint32_t *buf, size_t cap_triples, size_t *n_out) {
 }
 
 int CSCB200_Available(void) { return device_count() > 0 ? 1 : 0; }
+// the contiguous chunk range [lo, hi) of part k of g (chunk c belongs to part c * g / n): the rule the batched
+// calls fan out by, exported so that a one-process-per-GPU launcher (bench.py under torchrun) partitions identically
+void CSCB200_ChunkRange(int n_chunks, int k, int g, int *lo, int *hi) { chunk_range(n_chunks, k, g, *lo, *hi); }
 int CSCB200_DeviceCount(void) { return device_count(); }
 
 int CSCB200_SetDevice(int device) {

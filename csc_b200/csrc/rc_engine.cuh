@@ -25,16 +25,15 @@ struct RcCoder {
     u32 *ev;
     u32 ev_cap, ev_n;
     i32 err;
-    // bytes are gathered into one aligned 8-byte word before they go to memory
-    u64 acc;
+    // bytes are gathered into one aligned 4-byte word before they go to memory
+    u32 acc;
 
-    // One output byte.  Written without data-dependent branches on the common path: 32 streams share a warp,
-    // and whatever one lane has to execute all lanes wait for.
+    // One output byte (cold path: pending 0xFF runs, flush).
     CSC_HDF void put(u32 b, u32 stamp) {
-        const u32 sh = (n & 7) * 8;
-        acc |= (u64)(b & 0xFF) << sh;
-        if (sh == 56) {   // the aligned 8-byte word is complete
-            if (n < cap) *reinterpret_cast<u64 *>(out + (n & ~7u)) = acc; else err = kErrOverflow;
+        const u32 sh = (n & 3) * 8;
+        acc |= (b & 0xFF) << sh;
+        if (sh == 24) {   // the aligned 4-byte word is complete
+            if (n < cap) *reinterpret_cast<u32 *>(out + (n & ~3u)) = acc; else err = kErrOverflow;
             acc = 0;
         }
         n++;
@@ -45,26 +44,54 @@ struct RcCoder {
         }
     }
     CSC_HDF void drain() {   // pending bytes of the gather word
-        const u32 base = n & ~7u;
-        for (u32 k = 0; k < (n & 7); k++) { if (base + k < cap) out[base + k] = (u8)(acc >> (8 * k)); else err = kErrOverflow; }
+        const u32 base = n & ~3u;
+        for (u32 k = 0; k < (n & 3); k++) { if (base + k < cap) out[base + k] = (u8)(acc >> (8 * k)); else err = kErrOverflow; }
     }
-    CSC_HDF void shift_low(u32 stamp) {   // RC_ShiftLow, csc_coder.cpp:89-112
+    CSC_HDF void shift_low(u32 stamp) {   // RC_ShiftLow, csc_coder.cpp:89-112 (cold path: flush)
         const u32 lo32 = (u32)low, carry = (u32)(low >> 32);
         if (lo32 < 0xFF000000u || carry) {
             put(cache + carry, stamp);
-            while (cachesize > 1) { put(0xFF + carry, stamp); cachesize--; }   // pending 0xFF bytes (rare)
+            while (cachesize > 1) { put(0xFF + carry, stamp); cachesize--; }   // pending 0xFF bytes
             cache = lo32 >> 24;
             cachesize = 0;
         }
         cachesize++;
         low = (u64)(lo32 << 8);
     }
-    CSC_HDF void step(u32 e, u32 stamp) {   // the coder half of EncodeBit, csc_coder.h:67-81
+    // The coder half of EncodeBit (csc_coder.h:67-81) with RC_ShiftLow folded in.  32 streams share a warp and
+    // whatever one lane has to execute all lanes wait for, so the common case -- no renormalisation, or one byte
+    // leaving the cache -- is written as selects; only a pending run of 0xFF bytes, a completed output word's
+    // bounds failure or a completed 64 KiB block branch.
+    CSC_HDF void step(u32 e, u32 stamp) {
         const u32 bound = (range >> 12) * (e & 0xFFFu);
         const bool one = (e & 0x8000u) != 0;
         low += one ? 0u : bound;
         range = one ? bound : range - bound;
-        if (range < (1u << 24)) { range <<= 8; shift_low(stamp); }
+        const bool need = range < (1u << 24);
+        range = need ? range << 8 : range;
+        const u32 lo32 = (u32)low, carry = (u32)(low >> 32);
+        const bool emit = need && (lo32 < 0xFF000000u || carry != 0);
+        if (emit && cachesize > 1) {   // rare: a run of 0xFF bytes was waiting for this carry decision
+            put(cache + carry, stamp);
+            while (cachesize > 1) { put(0xFF + carry, stamp); cachesize--; }
+        } else {
+            const u32 sh = (n & 3) * 8;
+            acc |= emit ? ((cache + carry) & 0xFF) << sh : 0u;
+            if (emit && sh == 24) {
+                if (n < cap) *reinterpret_cast<u32 *>(out + (n & ~3u)) = acc; else err = kErrOverflow;
+                acc = 0;
+            }
+            n += emit ? 1u : 0u;
+            blk += emit ? 1u : 0u;
+            if (blk == bsize) {   // a 64 KiB RC block completed (csc_coder.cpp:97-104)
+                if (ev_n < ev_cap) ev[ev_n] = stamp; else err = kErrOverflow;
+                ev_n++;
+                blk = 0;
+            }
+        }
+        cache = emit ? lo32 >> 24 : cache;
+        cachesize = need ? (emit ? 1u : cachesize + 1) : cachesize;
+        low = need ? (u64)(lo32 << 8) : low;
     }
 
     // all segments of one stream; the decision lists were written by Encoder (enc_engine.cuh)
@@ -99,7 +126,7 @@ struct RcCoder {
             // Coder::Flush (csc_coder.cpp:40-48): five more bytes, then one byte is skipped, not stored (H3):
             // the host substitutes the stale ring byte
             for (int k = 0; k < 5; k++) shift_low(2 * cnt + 1);
-            if ((n & 7) == 7) { if (n < cap) *reinterpret_cast<u64 *>(out + (n & ~7u)) = acc; else err = kErrOverflow; acc = 0; }
+            if ((n & 3) == 3) { if (n < cap) *reinterpret_cast<u32 *>(out + (n & ~3u)) = acc; else err = kErrOverflow; acc = 0; }
             n++; blk++;
             so.rc_off = rc0; so.rc_len = n - rc0;
             so.rev_off = ev0; so.rev_len = ev_n - ev0;

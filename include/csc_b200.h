@@ -51,6 +51,9 @@ int CSCB200_EncodeChunksDevice(int n, const uint8_t *const *d_in, const size_t *
 int CSCB200_SetDevice(int device);
 int CSCB200_SetDevices(const int *devices, int n);
 int CSCB200_DeviceCount(void);
+/* Chunks [*lo, *hi) of n_chunks that part k of g owns (chunk c -> part c * g / n_chunks): the partition of the
+ * fan-out above, for launchers that run one process per GPU instead (needs no device). */
+void CSCB200_ChunkRange(int n_chunks, int k, int g, int *lo, int *hi);
 /* Frees the device and pinned memory cached by idle contexts. */
 void CSCB200_Trim(void);
 

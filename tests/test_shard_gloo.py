@@ -1,5 +1,6 @@
-"""world_size-2 gloo test of the multi-GPU host logic (no GPU needed): contiguous chunk ranges,
-nothing lost or duplicated, ordered concatenation on rank 0, max-over-ranks timing reduction."""
+"""world_size-2 gloo test of the multi-GPU host logic (no GPU needed): the library's contiguous chunk ranges
+(CSCB200_ChunkRange, the rule CSCB200_EncodeChunks fans out by and bench.py partitions by), nothing lost or
+duplicated, ordered concatenation on rank 0, max-over-ranks timing reduction."""
 import os
 import socket
 import sys
@@ -12,7 +13,11 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
-from csc_b200 import shard  # noqa: E402
+from csc_b200 import api as shard  # noqa: E402  (the product's own partition rule, CSCB200_ChunkRange)
+
+
+def _owner(c, n, w):
+    return c * w // n
 
 
 def test_chunk_ranges_partition_exactly():
@@ -23,7 +28,7 @@ def test_chunk_ranges_partition_exactly():
                 lo, hi = shard.chunk_range(n, r, w)
                 assert 0 <= lo <= hi <= n
                 got += list(range(lo, hi))
-                assert all(shard.owner(c, n, w) == r for c in range(lo, hi))
+                assert all(_owner(c, n, w) == r for c in range(lo, hi))
             assert got == list(range(n))
 
 
