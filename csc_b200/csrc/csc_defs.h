@@ -84,7 +84,23 @@ struct alignas(16) ApUnit {   // one position of the optimal parser's path (APUn
 };
 
 
-struct Cand { u32 len; u32 dist; };   // MFUnit: dist code 0 literal, 1..4 rep, 4+d match
+struct Cand { u32 len; u32 dist; };
+
+// ---- table candidates of one position, precomputed (k_mf_tlist) ----------------------------------------------
+// What find_match (csc_mf.cpp:303-485) takes from the 2-/3-/6-byte tables at position x does not depend on the
+// parse as long as every table entry it looks at is still in the tables ("alive"): the distance filter, the
+// length filter started at 1 and the bound[] cut are functions of the candidate rows alone.  The rep-distance
+// probes in front of it (:266-299) only raise the starting length R, which drops the entries with len <= R, or
+// stop the search altogether.  TRec holds that list (strictly increasing lengths, cut at the first good_len
+// match); `far` is the largest distance of any entry consulted, so "all alive" is checked against the stream's
+// highest dead position.  cnt == kTOver: more than four entries, take the general path.
+struct alignas(16) TRec {
+    u32 d[4];
+    u16 l[4];
+    u32 far;
+    u32 cnt;
+};
+static const u32 kTOver = 0xFF;   // MFUnit: dist code 0 literal, 1..4 rep, 4+d match
 
 // ---- small adaptive-probability tables (csc_model.h:95-123), 12-bit in u16 --
 struct ModelSmall {
@@ -104,6 +120,7 @@ struct ModelSmall {
     u32 row_l[8];
     u32 cl[kMaxCand];     // scratch: candidate list of the current find_match (len, dist code)
     u32 cd[kMaxCand];
+    u32 dead_hi;          // 1 + highest position ever marked dead in D6/D23 (0: none): entries at or above it are alive
     u32 dsum[64];         // coarse summary of the liveness bitmaps D6/D23: bit g set = some position of granule g may be dead
     u32 bq[32];           // pending range-coder decisions of the current packet: probability slot ids
     u16 bq_p[32];         //   ... and the probabilities fetched for them (lane-parallel)
@@ -151,6 +168,7 @@ struct EncStream {
     const u32 *P3; const u16 *L3;
     const u32 *P2; const u16 *L2;
     u32 *D23;
+    TRec *T;               // [n] precomputed table candidates (k_mf_tlist); null: general path only (wrapped streams)
     const u8 *blk_nolz;    // [nblk] block left out of the 2-/3-byte chains (statically typed BAD/ENTROPY/DLT)
     const u8 *flip;        // [nblk] outcome of the duplicate-block test the static plan assumed (plan.h); may be null
     u32 *replan;           // [2] out: block and observed outcome when the assumption failed (status kErrReplan)

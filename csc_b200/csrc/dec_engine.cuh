@@ -83,6 +83,30 @@ struct Decoder {
         bc_bits -= len;
         return r;
     }
+    // `size` whole bytes through the raw-bit reader: the payload shifted by the bits pending in front of it.
+    // Lane-parallel per BC block; the block bookkeeping is that of bc_byte().
+    CSC_HD void raw_bytes(u8 *dst, u32 size) {
+        while (size && bc_bits >= 8) { *dst++ = (u8)direct16(8); size--; }   // (never: at most 7 bits stay pending)
+        const u32 k = bc_bits;
+        u32 pend = bc_val & ((1u << k) - 1);
+        while (size) {
+            if (bc_pos >= S.bc_len || bc_blk >= S.n_bc_blk || bc_end <= bc_pos) { if (!err) err = kErrRead; break; }
+            const u32 take = size < bc_end - bc_pos ? size : bc_end - bc_pos;
+            const u8 *src = S.bc + bc_pos;
+            for (u32 i = CSC_LANE; i < take; i += CSC_NLANES) {
+                const u32 v = src[i], p = i ? src[i - 1] : pend;
+                dst[i] = (u8)((p << (8 - k)) | (v >> k));
+            }
+            pend = src[take - 1] & ((1u << k) - 1);
+            dst += take; size -= take; bc_pos += take;
+            if (bc_pos == bc_end) {
+                bc_blk++;
+                bc_end = bc_blk < S.n_bc_blk ? S.bc_blk_off[bc_blk + 1] : bc_pos;
+            }
+        }
+        bc_val = pend;
+        w_sync();
+    }
     CSC_HD u32 direct(u32 len) {
         if (len <= 16) return direct16(len);
         u32 hi = direct16(len - 16) << 16;
@@ -249,7 +273,7 @@ struct Decoder {
             } else if (type == DT_BAD) {
                 size = decode_int();
                 if (size > maxb || x + size > S.out_cap) { err = -1; break; }
-                for (u32 k = 0; k < size; k++) S.wnd[x + k] = (u8)direct16(8);
+                raw_bytes(S.wnd + x, size);
                 x += size;
             } else if (type == DT_ENTROPY) {
                 size = decode_int();

@@ -54,6 +54,8 @@ struct MfCtx {
     const u32 *Z6;
     u32 *D6, *D23, *ht2, *ht3, *cl, *cd;
     u32 *dsum; u32 gs;     // liveness summary (ModelSmall::dsum) and its granule shift
+    u32 *dhi;              // ModelSmall::dead_hi
+    const TRec *T;         // precomputed table candidates, or null (wrapped stream)
     u32 vld, W, K, good;
     u32 wnd;               // window size when the stream wraps, else 0 (no ring arithmetic on the hot path)
     bool tmode;
@@ -86,7 +88,7 @@ struct Encoder {
         MfCtx h;
         h.lz = S.lz; h.P6 = S.P6; h.L6 = S.L6; h.P3 = S.P3; h.L3 = S.L3; h.P2 = S.P2; h.L2 = S.L2; h.Z6 = S.Z6;
         h.D6 = S.D6; h.D23 = S.D23; h.ht2 = S.ht2; h.ht3 = S.ht3; h.cl = M.cl; h.cd = M.cd;
-        h.dsum = M.dsum; h.gs = gs;
+        h.dsum = M.dsum; h.gs = gs; h.dhi = &M.dead_hi; h.T = wrap ? nullptr : S.T;
         h.vld = vld; h.W = W; h.K = K; h.good = good; h.tmode = tmode;
         h.wnd = wrap ? S.cfg.wnd_size : 0;
         return h;
@@ -447,9 +449,10 @@ struct Encoder {
     // on).  Dead positions are rare, so a 2048-bit summary in shared memory answers most look-ups: a clear
     // summary bit means no position of that granule was ever marked in D6 or D23.
     CSC_HDF static bool maybe_dead(const MfCtx &h, u32 e) { const u32 g = e >> h.gs; return (h.dsum[g >> 5] >> (g & 31)) & 1u; }
-    CSC_HDF static void sum_mark(const MfCtx &h, u32 e) { const u32 g = e >> h.gs; s_or(&h.dsum[g >> 5], 1u << (g & 31)); }
+    CSC_HDF static void sum_mark(const MfCtx &h, u32 e) { const u32 g = e >> h.gs; s_or(&h.dsum[g >> 5], 1u << (g & 31)); s_max(h.dhi, e + 1); }
     CSC_HDF static void sum_mark_range(const MfCtx &h, u32 a, u32 b) {   // [a, b), warp-uniform call
         if (a >= b) return;
+        if (CSC_LANE == 0) s_max(h.dhi, b);
         const u32 g0 = a >> h.gs, g1 = (b - 1) >> h.gs;
         for (u32 g = g0 + CSC_LANE; g <= g1; g += CSC_NLANES) s_or(&h.dsum[g >> 5], 1u << (g & 31));
         w_sync();
@@ -524,6 +527,53 @@ struct Encoder {
         return ml >= h.good;
     }
 
+    // ---- precomputed table candidates (csc_defs.h: TRec) ------------------------------------------------
+    // The table half of find_match (csc_mf.cpp:303-485) at position x with every consulted entry alive, no rep
+    // match in front (minlen 1) and chain-mode tables: the statement k_mf_tlist runs for every position.
+    CSC_HDF static TRec tlist_of(u32 x, u32 limit, u32 vld, u32 W, u32 K, u32 good, u32 e2, u32 l2, u32 e3, u32 l3, const u32 *row,
+                                 const u16 *lrow) {
+        TRec t;
+        for (int i = 0; i < 4; i++) { t.d[i] = 0; t.l[i] = 0; }
+        t.far = 0; t.cnt = 0;
+        if (limit <= 1) return t;   // find_match returns nothing here whatever the tables hold
+        u32 far = 0, minlen = 1, dist = 0, cnt = 0;
+        bool stop = false;
+        const u32 pos = vld + x;
+        for (int which = 2; which <= 3 && !stop; which++) {
+            const u32 e = which == 2 ? e2 : e3, ml = which == 2 ? l2 : l3;
+            const u32 d = e == kNone ? pos : x - e;
+            if (e != kNone && d > far) far = d;
+            if (d <= dist) continue;
+            dist = d;
+            if (d >= vld || (which == 2 && x == d)) continue;   // (`wpos > dist`, csc_mf.cpp:306)
+            if (ml <= minlen) continue;
+            minlen = ml;
+            if (ml <= 6 && d >= mf_bound(ml)) continue;
+            if (cnt < 4) { t.d[cnt] = d; t.l[cnt] = (u16)ml; }
+            cnt++;
+            stop = ml >= good;
+        }
+        for (u32 k = 0; k < W && k < K; k++) {   // consulted entries count for `far` even behind a stop
+            const u32 e = row[k];
+            if (e == kNone) break;
+            const u32 d = x - e, ml = lrow[k];
+            if (d > far) far = d;
+            if (stop || d <= dist) continue;
+            dist = d;
+            if (d >= vld || ml <= minlen) continue;
+            minlen = ml;
+            if (ml <= 6 && d >= mf_bound(ml)) continue;
+            if (cnt < 4) { t.d[cnt] = d; t.l[cnt] = (u16)ml; }
+            cnt++;
+            stop = ml >= good;
+        }
+        t.far = far;
+        t.cnt = cnt > 4 ? kTOver : cnt;
+        return t;
+    }
+    // the record of x may stand in for the tables: nothing it consulted has been marked dead
+    CSC_HDF static bool trec_valid(const MfCtx &h, u32 x, u32 cnt, u32 far) { return cnt != kTOver && x - far >= *h.dhi; }
+
 #if defined(__CUDACC__)
     // ---- lane-parallel find_match (device) ------------------------------------------------------
     // Lane c owns candidate c of the reference probe order: 0-3 rep distances, 4 the 2-byte table,
@@ -548,8 +598,58 @@ struct Encoder {
         u32 e = __shfl_up_sync(0xFFFFFFFFu, v, 1);
         return lane ? e : 0;
     }
+    // find_match from the precomputed record: lanes 0-3 probe the rep distances, lanes 4-7 hold the table
+    // candidates; the length filter is a prefix maximum over those eight lanes.
+    static __device__ __forceinline__ u32 fm_fast(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3, u32 tcnt) {
+        const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
+        if (limit <= 1) return 0;
+        const u8 *cur = h.lz + x;
+        const bool is_rep = lane < 4;
+        u32 d = 0, L = 0;
+        bool usable = false, cmp = false;
+        if (is_rep) {
+            d = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : r3;
+            usable = d < h.vld;
+            if (usable) {
+                const u8 *m = cur - d;
+                cmp = m[1] == cur[1];
+                if (cmp) L = lane_lcp(cur, m, limit < 64 ? limit : 64);
+            }
+        } else if (lane < 4 + tcnt) {
+            const TRec *t = h.T + x;
+            d = t->d[lane - 4];
+            L = t->l[lane - 4];
+            usable = true;
+        }
+        u32 more = __ballot_sync(FULL, cmp && L == 64 && limit > 64);
+        while (more) {   // long rep matches are finished by the whole warp
+            const u32 src = (u32)__ffs((int)more) - 1;
+            more &= more - 1;
+            const u32 dd = __shfl_sync(FULL, d, src);
+            const u32 ext = 64 + lcp_bytes(cur + 64, cur - dd + 64, limit - 64);
+            if (lane == src) L = ext;
+        }
+        u32 v = usable ? L : 0;   // running maximum of the usable lengths in front of each lane (starts at 1)
+#pragma unroll
+        for (int sft = 1; sft < 8; sft <<= 1) { const u32 t = __shfl_up_sync(FULL, v, sft); if (lane >= (u32)sft) v = max(v, t); }
+        const u32 prev = __shfl_up_sync(FULL, v, 1);
+        const u32 run = max(1u, lane ? prev : 0u);
+        bool acc = lane < 8 && usable && L > run;
+        const u32 stopm = __ballot_sync(FULL, acc && L >= h.good);
+        if (stopm && lane > (u32)__ffs((int)stopm) - 1) acc = false;
+        const u32 has11 = __ballot_sync(FULL, lane == 0 && usable && L >= 2) & 1u;
+        const u32 accm = __ballot_sync(FULL, acc);
+        if (has11 && lane == 0) { h.cl[0] = 1; h.cd[0] = 1; }
+        if (acc) { const u32 idx = has11 + (u32)__popc(accm & ((1u << lane) - 1)); h.cl[idx] = L; h.cd[idx] = is_rep ? 1 + lane : 4 + d; }
+        __syncwarp();
+        return has11 + (u32)__popc(accm);
+    }
     static __device__ __forceinline__ u32 fm_lanes(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
         const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
+        if (h.T && !h.tmode) {
+            const u32 tcnt = h.T[x].cnt, far = h.T[x].far;
+            if (trec_valid(h, x, tcnt, far)) return fm_fast(h, x, limit, r0, r1, r2, r3, tcnt);
+        }
         const u8 *cur = h.lz + x;
         const u32 pos = h.vld + x;
         const bool is_rep = lane < 4, is_tab = lane == 4 || lane == 5, is_row = lane >= 8 && lane < 8 + h.K;
@@ -699,6 +799,13 @@ struct Encoder {
             if (ml > minlen) { minlen = ml; push_cand(h, cnt, ml, 1 + i); stop = ml >= h.good; }
         }
         if (stop) dist = 0xFFFFFFFFu;
+        if (h.T && !h.tmode && trec_valid(h, x, h.T[x].cnt, h.T[x].far)) {   // the precomputed table half (csc_defs.h: TRec)
+            const TRec &t = h.T[x];
+            if (limit > 1 && !stop)
+                for (u32 i = 0; i < t.cnt; i++)
+                    if (t.l[i] > minlen) { minlen = t.l[i]; push_cand(h, cnt, t.l[i], 4 + t.d[i]); }
+            return cnt;
+        }
         // 2-byte and 3-byte single-slot tables (:303-366).  `wpos > dist` (:306): a 2-byte candidate at window
         // offset 0 of the lap is dropped but still poisons dist.
         const u32 d2 = pos - e2, d3 = pos - e3;
@@ -843,6 +950,54 @@ struct Encoder {
     }
     CSC_HDF void emit(u32 op, u32 a, u32 b, u32 c) { exec(op, a, b, c); }
 
+#if defined(__CUDA_ARCH__)
+    // ---- literal runs (device) ---------------------------------------------------------------------------
+    // Number of leading positions of [x, end), at most 32, where find_match is certain to come back empty: no
+    // table candidate in the (valid) precomputed record and no rep distance that matches two bytes.  Lane j
+    // looks at position x + j; literals change neither the rep distances nor the liveness of anything, so the
+    // answers are independent.  (The 32 records it touches are the ones the next find_match calls read.)
+    static __device__ __forceinline__ u32 literal_run(const MfCtx &h, u32 x, u32 end, u32 r0, u32 r1, u32 r2, u32 r3) {
+        const u32 p = x + CSC_LANE;
+        bool hit = true;
+        if (p < end) {
+            if (end - p <= 1) hit = false;
+            else {
+                const TRec *t = h.T + p;
+                const u32 tc = t->cnt, far = t->far;
+                hit = tc != 0 || p - far < *h.dhi;
+                if (!hit) {
+                    const u32 w = (u32)h.lz[p] | ((u32)h.lz[p + 1] << 8);
+                    if (r0 < h.vld) hit |= ((u32)h.lz[p - r0] | ((u32)h.lz[p + 1 - r0] << 8)) == w;
+                    if (r1 < h.vld) hit |= ((u32)h.lz[p - r1] | ((u32)h.lz[p + 1 - r1] << 8)) == w;
+                    if (r2 < h.vld) hit |= ((u32)h.lz[p - r2] | ((u32)h.lz[p + 1 - r2] << 8)) == w;
+                    if (r3 < h.vld) hit |= ((u32)h.lz[p - r3] | ((u32)h.lz[p + 1 - r3] << 8)) == w;
+                }
+            }
+        }
+        const u32 m = __ballot_sync(0xFFFFFFFFu, hit);
+        return m ? (u32)__ffs((int)m) - 1 : 32u;
+    }
+    // n literals starting at x, three per step: lane 9 j codes the packet flag of literal j (its state is the
+    // literal state chain of the ones in front), lanes 9 j + 1 .. 9 j + 8 its tree levels (csc_model.cpp:169-183)
+    __device__ __noinline__ void emit_literals(u32 x, u32 n) {
+        const u32 lane = CSC_LANE, j = lane / 9, kk = lane - 9 * j;
+        if (dec_n + 9 * n > S.dec_cap) { err = kErrOverflow; return; }
+#pragma unroll 1
+        for (u32 i = 0; i < n; i += 3) {
+            const u32 nb = n - i < 3 ? n - i : 3;
+            const bool on = j < nb;
+            u32 c = 0, pc = 0;
+            if (on) { c = S.lz[x + i + j]; pc = j ? S.lz[x + i + j - 1] : ctx; }
+            const u32 stj = j == 0 ? state : j == 1 ? (state * 4) & 0x3F : (state * 16) & 0x3F;
+            const u32 cc = c | 0x100;
+            u16 *pp = kk == 0 ? &M.p_state[stj * 3] : S.p_lit + pc * 256 + (cc >> (9 - kk));
+            batch_decisions(on, pp, kk == 0 ? 0u : (cc >> (8 - kk)) & 1u, 9 * nb);
+            state = nb == 1 ? (state * 4) & 0x3F : nb == 2 ? (state * 16) & 0x3F : 0u;
+            ctx = S.lz[x + i + nb - 1];
+        }
+    }
+#endif
+
     // ------------------------------------------------------------- lazy parser
     CSC_HDN void encode_nonlit(Cand u, u32 newctx) {   // csc_lz.cpp:127-154 (+ SetLiteralCtx of the caller)
         if (u.dist <= 4) {
@@ -865,6 +1020,12 @@ struct Encoder {
         u1.len = 1; u1.dist = 0;
         bool have = false;
         while (p_uni(x < end)) {
+#if defined(__CUDA_ARCH__)
+            if (!have && h.T && !h.tmode && !tracing) {   // a run of literals is found and coded in one go
+                const u32 nl = literal_run(h, x, end, rep[0], rep[1], rep[2], rep[3]);
+                if (nl) { emit_literals(x, nl); x += nl; continue; }
+            }
+#endif
             if (p_uni(!have || !(u1.len == 1 || u1.len >= h.good))) {
                 // the one probe site: u1 at x, or the lazy look-ahead u2 at x + 1
                 const u32 px = have ? x + 1 : x;
@@ -994,6 +1155,12 @@ struct Encoder {
         t0.len = 1; t0.dist = 0;
         LV_FOR(j) { wp.v[LV_AT(j)] = 0; wd.v[LV_AT(j)] = 0; wb.v[LV_AT(j)] = 0; td.v[LV_AT(j)] = 0; tp.v[LV_AT(j)] = 0; }
         while (p_uni(in_round || i < size)) {
+#if defined(__CUDA_ARCH__)
+            if (!in_round && h.T && !h.tmode && !tracing) {   // outside a round a position without candidates is a literal
+                const u32 nl = literal_run(h, x, end, rep[0], rep[1], rep[2], rep[3]);
+                if (nl) { emit_literals(x, nl); i += nl; x += nl; continue; }
+            }
+#endif
             const u32 lit = h.lz[x];
             u32 ns = state, r0 = rep[0], r1 = rep[1], r2 = rep[2], r3 = rep[3];
             if (p_uni(in_round)) {   // apcur >= 1
@@ -1138,10 +1305,68 @@ struct Encoder {
     }
     CSC_HDN void bad_run(u32 a, u32 size) {   // CompressBad, csc_model.cpp:463-469
         encode_int(size);
-        for (u32 i = 0; i < size; i++) direct16(S.lz[a + i], 8);
+        // `size` raw bytes through the bit coder (csc_coder.cpp:76-87) are the run itself shifted by the bits that
+        // were pending in front of it: output byte i = pending/previous byte's low k bits, then the top 8 - k bits
+        // of byte i.  The block completions inside the run all carry the same time stamp (no decision in between).
+        const u32 k = bc_bits, stamp = 2 * (dec_n - seg_dec0);
+        const u32 pend = bc_val & ((1u << k) - 1);
+        if (bc_n + size > S.bc_cap) { err = kErrOverflow; return; }
+        for (u32 i = CSC_LANE; i < size; i += CSC_NLANES) {
+            const u32 v = S.lz[a + i], p = i ? S.lz[a + i - 1] : pend;
+            S.bc_out[bc_n + i] = (u8)((p << (8 - k)) | (v >> k));
+        }
+        const u32 tot = bc_blk + size, nev = tot / S.cfg.csc_blocksize;
+        if (bev_n + nev > S.ev_cap) err = kErrOverflow;
+        else for (u32 e = CSC_LANE; e < nev; e += CSC_NLANES) S.bc_ev[bev_n + e] = stamp;
+        bev_n += nev;
+        bc_blk = tot % S.cfg.csc_blocksize;
+        bc_n += size;
+        if (size) bc_val = S.lz[a + size - 1];
+        w_sync();
     }
+#if defined(__CUDA_ARCH__)
+    // A batch of binary decisions, one per lane (`on`), in lane order.  Lanes that name the same probability see
+    // it as the earlier lanes of the batch leave it (the adaptation is replayed from their bits), and the last of
+    // them stores the result: exactly the serial statement, whatever the collisions.
+    __device__ __forceinline__ void batch_decisions(bool on, u16 *pp, u32 bit, u32 n) {
+        const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
+        const unsigned long long key = on ? (unsigned long long)(uintptr_t)pp : (unsigned long long)lane;
+        const u32 peers = __match_any_sync(FULL, key);
+        const u32 bitsm = __ballot_sync(FULL, on && bit);
+        if (on) {
+            u32 v = *pp;
+            u32 earlier = peers & ((1u << lane) - 1);
+            while (earlier) {
+                const u32 l = (u32)__ffs((int)earlier) - 1;
+                earlier &= earlier - 1;
+                v = ((bitsm >> l) & 1u) ? v + ((0xFFFu - v) >> 5) : v - (v >> 5);
+            }
+            S.dec[dec_n + lane] = (DecEntry)(v | (bit << 15));
+            if ((peers >> lane) == 1u) *pp = (u16)(bit ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));   // last user of the slot
+        }
+        dec_n += n;
+        __syncwarp();
+    }
+#endif
     CSC_HDN void entropy_run(u32 a, u32 size) {   // CompressLiterals, csc_model.cpp:448-461
         encode_int(size);
+        flush_bits();
+#if defined(__CUDA_ARCH__)
+        // four literals per step: lane 8 j + k codes tree level k of byte j under the row of the byte in front of it
+        if (dec_n + 8 * size > S.dec_cap) { err = kErrOverflow; return; }
+        const u32 lane = CSC_LANE, j = lane >> 3, kk = lane & 7;
+#pragma unroll 1
+        for (u32 i = 0; i < size; i += 4) {
+            const u32 nb = size - i < 4 ? size - i : 4;
+            const bool on = j < nb;
+            u32 c = 0, pc = 0;
+            if (on) { c = S.lz[a + i + j]; pc = (i + j) ? S.lz[a + i + j - 1] : 0; }
+            if (i == 0 && j == 0) pc = ctx;
+            const u32 cc = c | 0x100;
+            batch_decisions(on, S.p_lit + pc * 256 + (cc >> (8 - kk)), (cc >> (7 - kk)) & 1, 8 * nb);
+        }
+        if (size) ctx = S.lz[a + size - 1];
+#else
         for (u32 i = 0; i < size; i++) {
             u32 c = S.lz[a + i];
             u32 row = ctx * 256;
@@ -1149,6 +1374,7 @@ struct Encoder {
             lit_bits(row, c);
             flush_bits();
         }
+#endif
     }
     // byte k of Forward_Delta's output (csc_filters.cpp:132-164) without materialising it
     CSC_HD u32 delta_byte(u32 a, u32 size, u32 chn, u32 k) const {
@@ -1169,33 +1395,69 @@ struct Encoder {
         }
         return (S.lz[a + j] - prev) & 0xFF;
     }
+    // CompressRLE's run rule at residual i (csc_model.cpp:476-497): three equal neighbours and more than ten equal
+    // bytes from i on.  Pure function of the residuals, so every lane can evaluate it for its own position.
+    CSC_HDF static bool rle_starts(const u8 *f, u32 i, u32 size) {
+        if (i == 0 || size - i <= 3) return false;
+        const u32 c0 = f[i];
+        if (f[i - 1] != c0 || f[i + 1] != c0 || f[i + 2] != c0) return false;
+        if (i + 10 >= size) return false;
+        for (u32 t = 3; t <= 10; t++) if (f[i + t] != c0) return false;
+        return true;
+    }
     CSC_HDN void delta_run(u32 a, u32 size, u32 chn) {   // Forward_Delta + CompressRLE, csc_model.cpp:471-513
-        // the filtered run is materialised lane-parallel into the stream's scratch, then coded serially
+        // the filtered run is materialised lane-parallel into the stream's scratch, then coded
         u8 *f = S.tmp + a;
 #pragma unroll 1
         for (u32 k = CSC_LANE; k < size; k += CSC_NLANES) f[k] = (u8)delta_byte(a, size, chn, k);
         w_sync();
         encode_int(size);
-        u32 sctx = 0;
+        flush_bits();
         for (u32 i = 0; i < size;) {
+#if defined(__CUDA_ARCH__)
+            // up to three literals per step: lane 9 j codes the flag of residual i + j, lanes 9 j + 1 .. 9 j + 8 its
+            // tree levels under the row of the residual in front of it; a residual that starts a run ends the batch
+            const u32 lane = CSC_LANE, j = lane / 9, kk = lane - 9 * j;
+            const bool mine = j < 3 && i + j < size;
+            const u32 runm = __ballot_sync(0xFFFFFFFFu, mine && kk == 0 && rle_starts(f, i + j, size));   // bits 0, 9, 18
+            u32 nb = size - i < 3 ? size - i : 3;
+            if (runm & 1u) nb = 0; else if (runm & (1u << 9)) nb = 1; else if ((runm & (1u << 18)) && nb > 2) nb = 2;
+            if (nb) {
+                if (dec_n + 9 * nb > S.dec_cap) { err = kErrOverflow; return; }
+                const bool on = j < nb;
+                u32 c = 0, pc = 0;
+                if (on) { c = f[i + j]; pc = (i + j) ? f[i + j - 1] : 0; }
+                const u32 cc = c | 0x100;
+                u16 *pp = kk == 0 ? &M.p_rle_flag : S.p_delta + pc * 256 + (cc >> (9 - kk));
+                batch_decisions(on, pp, kk == 0 ? 0u : (cc >> (8 - kk)) & 1u, 9 * nb);
+                i += nb;
+                continue;
+            }
+            {
+                const u32 c0 = f[i];
+                u32 jj = i + 11;   // rle_starts: f[i .. i + 10] are equal
+                while (jj < size && f[jj] == c0) jj++;
+                enc_bit(M.p_rle_flag, 1);
+                encode_matchlen_2(jj - i - 11);
+                flush_bits();
+                i = jj;
+            }
+#else
             const u32 c0 = f[i];
-            if (i > 0 && size - i > 3 && f[i - 1] == c0 && c0 == f[i + 1] && c0 == f[i + 2]) {
-                u32 j = i + 3;
+            if (rle_starts(f, i, size)) {
+                u32 j = i + 11;
                 while (j < size && f[j] == c0) j++;
-                if (j - i > 10) {
-                    sctx = c0;
-                    enc_bit(M.p_rle_flag, 1);
-                    encode_matchlen_2(j - i - 11);
-                    flush_bits();
-                    i = j;
-                    continue;
-                }
+                enc_bit(M.p_rle_flag, 1);
+                encode_matchlen_2(j - i - 11);
+                flush_bits();
+                i = j;
+                continue;
             }
             enc_bit(M.p_rle_flag, 0);
-            lit_bits(65536 + sctx * 256, c0);   // p_delta follows p_lit
+            lit_bits(65536 + (i ? f[i - 1] : 0u) * 256, c0);   // p_delta follows p_lit; the context is the residual in front
             flush_bits();
-            sctx = c0;
             i++;
+#endif
         }
     }
 
@@ -1315,6 +1577,7 @@ struct Encoder {
         while (((S.n + 63) >> gs) > 2048) gs++;   // 2048 summary bits cover the stream
         w_sync();
         for (u32 i = CSC_LANE; i < 64; i += CSC_NLANES) M.dsum[i] = 0;
+        if (CSC_LANE == 0) M.dead_hi = 0;
         w_sync();
         dec_n = bc_n = bev_n = 0;
         seg_dec0 = seg_bc0 = seg_bev0 = 0;

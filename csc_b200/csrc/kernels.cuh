@@ -8,8 +8,9 @@
 //   k_mf_rows      sorted (stream,hash,pos) -> K nearest earlier same-hash positions per position
 //   k_mf_extend    forward match length of every (position, candidate) pair, capped at the
 //                  sub-block end                               (csc_mf.cpp:470, 8 B words)
+//   k_mf_tlist     thread per position: table candidates of find_match under the all-alive assumption (TRec)
 //   k_encode       one stream per warp: enc_engine.cuh (parser + adaptive model -> decision lists)
-//   k_rc           one stream per thread: rc_engine.cuh (range-coder recurrence over the decision lists)
+//   k_rc           one stream per warp, warp-uniform: rc_engine.cuh (range-coder recurrence over the decision lists)
 //   k_decode       one stream per warp: dec_engine.cuh
 //   k_unfilter     inverse e8e9 / dictionary per decoded run   (csc_filters.cpp:337,600)
 //
@@ -735,6 +736,38 @@ k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const 
     }
 }
 
+// ------------------------------------------------------------------ precomputed table candidates
+// One thread per position: the table half of find_match under the all-alive assumption (enc_engine.cuh:
+// tlist_of), 32 bytes per position.  Rows, chains and records are read / written as whole sectors by
+// neighbouring threads.  Sub-blocks the static plan types as not LZ-parsed are skipped (their records are never
+// read: a duplicate-block flip moves the stream to table mode), and so are wrapped streams.
+__global__ void __launch_bounds__(256)
+k_mf_tlist(const BlockDesc *__restrict__ blk, const EncStream *__restrict__ streams) {
+    const BlockDesc bd = blk[blockIdx.x];
+    if (!bd.size || (bd.flags & 1)) return;
+    const EncStream &S = streams[bd.stream];
+    if (!S.T || S.n > S.cfg.wnd_size) return;
+    const u32 vld = S.cfg.vld_rge, W = S.cfg.ht_width, K = S.K, good = S.cfg.good_len;
+    for (u32 i = threadIdx.x; i < bd.size; i += 256) {
+        const u32 x = bd.x + i;
+        u32 row[16];
+        u16 lrow[16];
+        if (K == 8) {
+            const uint4 a = reinterpret_cast<const uint4 *>(S.P6 + (size_t)x * 8)[0], b = reinterpret_cast<const uint4 *>(S.P6 + (size_t)x * 8)[1];
+            const uint4 l = *reinterpret_cast<const uint4 *>(S.L6 + (size_t)x * 8);
+            row[0] = a.x; row[1] = a.y; row[2] = a.z; row[3] = a.w; row[4] = b.x; row[5] = b.y; row[6] = b.z; row[7] = b.w;
+            lrow[0] = (u16)l.x; lrow[1] = (u16)(l.x >> 16); lrow[2] = (u16)l.y; lrow[3] = (u16)(l.y >> 16);
+            lrow[4] = (u16)l.z; lrow[5] = (u16)(l.z >> 16); lrow[6] = (u16)l.w; lrow[7] = (u16)(l.w >> 16);
+        } else {
+            for (u32 k = 0; k < K && k < 16; k++) { row[k] = S.P6[(size_t)x * K + k]; lrow[k] = S.L6[(size_t)x * K + k]; }
+        }
+        const TRec t = Encoder::tlist_of(x, bd.size - i, vld, W, K, good, S.P2[x], S.L2[x], S.P3[x], S.L3[x], row, lrow);
+        uint4 *o = reinterpret_cast<uint4 *>(S.T + x);
+        o[0] = make_uint4(t.d[0], t.d[1], t.d[2], t.d[3]);
+        o[1] = make_uint4((u32)t.l[0] | ((u32)t.l[1] << 16), (u32)t.l[2] | ((u32)t.l[3] << 16), t.far, t.cnt);
+    }
+}
+
 // ------------------------------------------------------------------ result packing
 // The RC / BC sub-streams of all streams of a wave are gathered into one dense buffer each, so that the
 // download is two large copies instead of two small ones per stream.  Offsets and sizes are 16-byte aligned.
@@ -788,14 +821,17 @@ k_encode(const EncStream *__restrict__ streams, u32 ns, u32 *queue, const u32 *_
     }
 }
 
-// The range-coder pass: one stream per thread, one warp per CTA so that the few hundred warps of a wave spread
-// over all SMs (the pass is a serial dependency chain per stream: latency, not throughput).
-__global__ void __launch_bounds__(32)
+// The range-coder pass: one stream per warp (rc_engine.cuh), all lanes redundant; the pass is a serial dependency
+// chain per stream, so the warps only have to be spread over all SMs.
+static const int kRcWarps = 4;
+__global__ void __launch_bounds__(kRcWarps * 32)
 k_rc(const EncStream *__restrict__ streams, u32 ns) {
-    const u32 s = blockIdx.x * 32 + threadIdx.x;
+    __shared__ uint4 stage[kRcWarps][32];
+    const u32 warp = threadIdx.x >> 5;
+    const u32 s = blockIdx.x * kRcWarps + warp;
     if (s >= ns) return;
     RcCoder R;
-    R.run(streams[s]);
+    R.run(streams[s], stage[warp]);
 }
 
 static const int kDecWarps = 4;

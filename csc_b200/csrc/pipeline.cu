@@ -89,7 +89,7 @@ struct Ctx {
     DevBuf packdesc, lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
         dwnd, dout, doffs, druns, dmeta, doutptr, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
-        flip, replan, subdesc, subscratch, rcev, bcev, dec, swnd;
+        flip, replan, subdesc, subscratch, rcev, bcev, dec, T, swnd;
     PinBuf h_segout, h_status, h_rcev, h_bcev, h_rc, h_bc, h_meta, h_replan;
     Timer tm;
     CSCB200_Stats stats;
@@ -278,6 +278,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     const size_t bmbytes = total / 8 + 64;
     r |= C.Z2.ensure(bmbytes); r |= C.Z6.ensure(bmbytes); r |= C.D6.ensure(bmbytes); r |= C.D23.ensure(bmbytes);
     r |= C.P3.ensure(total * 4); r |= C.P2.ensure(total * 4); r |= C.L3.ensure(total * 2); r |= C.L2.ensure(total * 2);
+    r |= C.T.ensure(total * sizeof(TRec));
     r |= C.nolz.ensure(nblk + 16); r |= C.flip.ensure(nblk + 16); r |= C.replan.ensure((size_t)ns * 8);
     r |= C.subdesc.ensure((size_t)nsub * sizeof(BlockDesc)); r |= C.subscratch.ensure((size_t)nsub * sizeof(SubBlock));
     r |= C.swnd.ensure((size_t)ns * 4);
@@ -336,6 +337,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         S.P3 = C.P3.as<u32>() + goff[s]; S.L3 = C.L3.as<u16>() + goff[s];
         S.P2 = C.P2.as<u32>() + goff[s]; S.L2 = C.L2.as<u16>() + goff[s];
         S.D23 = C.D23.as<u32>() + goff[s] / 32; S.blk_nolz = C.nolz.as<u8>();
+        S.T = (J.n > S.cfg.wnd_size || bounded) ? nullptr : C.T.as<TRec>() + goff[s];
         S.flip = C.flip.as<u8>(); S.replan = C.replan.as<u32>() + 2 * (size_t)s;
         S.ht2 = C.ht.as<u32>() + (size_t)s * 81920; S.ht3 = S.ht2 + 16384;
         S.p_lit = C.plit.as<u16>() + (size_t)s * 131072; S.p_delta = S.p_lit + 65536;
@@ -438,8 +440,9 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         k_mf_rows<<<nrst, 256, 0, st>>>(ksorted, vsorted, C.rstiles.as<RsTile>(), C.sgoff.as<u64>(), C.sK.as<u32>(), P, 1, 0, 0);
         k_mf_extend<1><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
     }
+    k_mf_tlist<<<nsub, 256, 0, st>>>(C.subdesc.as<BlockDesc>(), C.streams.as<EncStream>());
     T.mark(st);                                                                   // 8
-    launches += 3 + 1 + 2 * 3;
+    launches += 3 + 1 + 2 * 3 + 1;
     if (g_dump.on && ns == 1) {
         CK(cudaStreamSynchronize(st));
         u32 n1 = jobs[0]->n;
@@ -472,7 +475,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         k_encode<<<grid, kEncWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns, d_queue, C.d_p2bits);
     }
     T.mark(st);                                                                   // 9
-    k_rc<<<(ns + 31) / 32, 32, 0, st>>>(C.streams.as<EncStream>(), ns);
+    k_rc<<<(ns + kRcWarps - 1) / kRcWarps, kRcWarps * 32, 0, st>>>(C.streams.as<EncStream>(), ns);
     T.mark(st);                                                                   // 10
     launches += 2;
     CK(cudaGetLastError());
@@ -575,7 +578,7 @@ size_t framed_size(const EncJob &J, bool with_props) {
 }
 
 size_t per_stream_bytes() { return 81920 * 4 + 131072 * 2 + (kApLimit + 2) * sizeof(ApUnit) + 140000 * 2 + 4096; }
-size_t per_pos_bytes(u32 K) { return 2 + 24 + 6 * (size_t)K + 12 + 1 + 3 + 9 * sizeof(DecEntry); }
+size_t per_pos_bytes(u32 K) { return 2 + 24 + 6 * (size_t)K + 12 + 1 + 3 + 9 * sizeof(DecEntry) + sizeof(TRec); }
 
 // ----------------------------------------------------------------------------- decode
 struct DecJob {

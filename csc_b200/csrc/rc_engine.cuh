@@ -1,11 +1,18 @@
-// rc_engine.cuh -- the range-coder pass: one stream per THREAD.
+// rc_engine.cuh -- the range-coder pass: one stream per WARP, warp-uniform.
 //
 // The reference's EncodeBit (csc_coder.h:67-81) adapts a probability and then advances the coder
 // registers (range, 64-bit low with carry / cache bytes, csc_coder.cpp:89-112).  Only the second half is
 // serially dependent on every earlier decision of the segment, and it needs nothing but the sequence of
 // (probability, bit) pairs.  The parser / model engine (enc_engine.cuh) therefore only APPENDS those pairs
-// to the stream's decision list; this pass replays them: ~a dozen integer instructions per decision, no
-// model memory, no match finder, 32 independent streams per warp instead of one.
+// to the stream's decision list; this pass replays them: about a dozen integer instructions per decision, no
+// model memory, no match finder.
+//
+// The pass is a dependency chain per stream (latency, not throughput), so what counts is the length of that
+// chain.  A thread-per-stream layout (round 2, first version) made every lane of a warp pay for the
+// renormalisation / byte-output path of any lane: ~140 cycles per decision.  Here all 32 lanes of a warp run
+// the same stream redundantly: branches are uniform and mostly not taken, the decision list is fetched 512
+// bytes per load instruction by the whole warp and staged in shared memory one block ahead, and the chain is
+// the ~25 cycles of the range recurrence itself.
 //
 // Output per segment: the RC sub-stream (whose last byte is the one the reference skips instead of
 // storing, H3) and the time stamps of the 64 KiB block completions (csc_coder.cpp:97-104) for the host's
@@ -58,44 +65,16 @@ struct RcCoder {
         cachesize++;
         low = (u64)(lo32 << 8);
     }
-    // The coder half of EncodeBit (csc_coder.h:67-81) with RC_ShiftLow folded in.  32 streams share a warp and
-    // whatever one lane has to execute all lanes wait for, so the common case -- no renormalisation, or one byte
-    // leaving the cache -- is written as selects; only a pending run of 0xFF bytes, a completed output word's
-    // bounds failure or a completed 64 KiB block branch.
-    CSC_HDF void step(u32 e, u32 stamp) {
+    CSC_HDF void step(u32 e, u32 stamp) {   // the coder half of EncodeBit, csc_coder.h:67-81
         const u32 bound = (range >> 12) * (e & 0xFFFu);
-        const bool one = (e & 0x8000u) != 0;
-        low += one ? 0u : bound;
-        range = one ? bound : range - bound;
-        const bool need = range < (1u << 24);
-        range = need ? range << 8 : range;
-        const u32 lo32 = (u32)low, carry = (u32)(low >> 32);
-        const bool emit = need && (lo32 < 0xFF000000u || carry != 0);
-        if (emit && cachesize > 1) {   // rare: a run of 0xFF bytes was waiting for this carry decision
-            put(cache + carry, stamp);
-            while (cachesize > 1) { put(0xFF + carry, stamp); cachesize--; }
-        } else {
-            const u32 sh = (n & 3) * 8;
-            acc |= emit ? ((cache + carry) & 0xFF) << sh : 0u;
-            if (emit && sh == 24) {
-                if (n < cap) *reinterpret_cast<u32 *>(out + (n & ~3u)) = acc; else err = kErrOverflow;
-                acc = 0;
-            }
-            n += emit ? 1u : 0u;
-            blk += emit ? 1u : 0u;
-            if (blk == bsize) {   // a 64 KiB RC block completed (csc_coder.cpp:97-104)
-                if (ev_n < ev_cap) ev[ev_n] = stamp; else err = kErrOverflow;
-                ev_n++;
-                blk = 0;
-            }
-        }
-        cache = emit ? lo32 >> 24 : cache;
-        cachesize = need ? (emit ? 1u : cachesize + 1) : cachesize;
-        low = need ? (u64)(lo32 << 8) : low;
+        if (e & 0x8000u) range = bound;
+        else { low += bound; range -= bound; }
+        if (range < (1u << 24)) { range <<= 8; shift_low(stamp); }
     }
 
     // all segments of one stream; the decision lists were written by Encoder (enc_engine.cuh)
-    CSC_HD void run(const EncStream &S) {
+    CSC_HD void run(const EncStream &S, void *stage_mem) {   // stage_mem: 512 bytes of shared memory per warp (device)
+        (void)stage_mem;
         out = S.rc_out; cap = S.rc_cap; bsize = S.cfg.csc_blocksize;
         ev = S.rc_ev; ev_cap = S.ev_cap; ev_n = 0;
         n = 0; err = 0; acc = 0;
@@ -108,18 +87,35 @@ struct RcCoder {
             const u32 cnt = so.dec_len;
             u32 i = 0;
 #if defined(__CUDA_ARCH__)
-            if (cnt >= 8) {   // dec_off is 8-aligned: one 16-byte load per 8 decisions, the next one always in flight
-                uint4 nx = *reinterpret_cast<const uint4 *>(d);
-                for (; i + 8 <= cnt; i += 8) {
-                    const uint4 v = nx;
-                    if (i + 16 <= cnt) nx = *reinterpret_cast<const uint4 *>(d + i + 8);
-                    const u32 w[4] = {v.x, v.y, v.z, v.w};
+            // dec_off is 8-aligned: the warp fetches 256 decisions (512 bytes) per load, one block ahead of the
+            // one being coded, and every lane reads them back 8 at a time from shared memory (broadcast)
+            if (cnt >= 8) {
+                const u32 lane = threadIdx.x & 31u, full = cnt & ~7u;
+                const uint4 *g = reinterpret_cast<const uint4 *>(d);
+                uint4 *stage = reinterpret_cast<uint4 *>(stage_mem);
+                uint4 nx = make_uint4(0, 0, 0, 0);
+                if (lane * 8 < full) nx = g[lane];
+                for (u32 base = 0; base < full; base += 256) {
+                    __syncwarp();
+                    stage[lane] = nx;
+                    __syncwarp();
+                    if (base + 256 + lane * 8 < full) nx = g[(base + 256) / 8 + lane];
+                    const u32 m = full - base < 256 ? (full - base) / 8 : 32;
+                    uint4 vn = stage[0];
+#pragma unroll 1
+                    for (u32 q = 0; q < m; q++) {
+                        const uint4 v = vn;
+                        vn = stage[(q + 1) & 31];   // the next eight are on their way while these are coded
+                        const u32 w[4] = {v.x, v.y, v.z, v.w};
+                        const u32 i0 = base + q * 8;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        step(w[k] & 0xFFFFu, 2 * (i + 2 * k) + 1);
-                        step(w[k] >> 16, 2 * (i + 2 * k + 1) + 1);
+                        for (int k = 0; k < 4; k++) {
+                            step(w[k] & 0xFFFFu, 2 * (i0 + 2 * k) + 1);
+                            step(w[k] >> 16, 2 * (i0 + 2 * k + 1) + 1);
+                        }
                     }
                 }
+                i = full;
             }
 #endif
             for (; i < cnt; i++) step(d[i], 2 * i + 1);

@@ -33,6 +33,7 @@ CSC_HDF u32 popc32(u32 m) { return (u32)__popc(m); }
 CSC_HDF void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 CSC_HDF void pf_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }   // read-only arrays only
 CSC_HDF void s_or(u32 *p, u32 m) { atomicOr(p, m); }   // shared-memory word, lanes may collide
+CSC_HDF void s_max(u32 *p, u32 v) { atomicMax(p, v); }
 #else
 #define CSC_LANE 0u
 #define CSC_NLANES 1u
@@ -51,6 +52,7 @@ CSC_HDF u32 popc32(u32 m) { return (u32)__builtin_popcount(m); }
 CSC_HDF void pf_l2(const void *) {}
 CSC_HDF void pf_l1(const void *) {}
 CSC_HDF void s_or(u32 *p, u32 m) { *p |= m; }
+CSC_HDF void s_max(u32 *p, u32 v) { if (v > *p) *p = v; }
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -219,6 +219,19 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         build_chain23_cpu(lz.data(), n, subs, cfg.wnd_size, 3, P3, L3);
         build_chain23_cpu(lz.data(), n, subs, cfg.wnd_size, 2, P2, L2);
         std::vector<u32> D23((n + 31) / 32 + 1, 0);
+        // precomputed table candidates (k_mf_tlist on the device): the same scalar statement, per LZ-parsed sub-block
+        std::vector<TRec> T;
+        if (n <= cfg.wnd_size && !cfg.bounded && !getenv("CSC_HS_NO_TREC")) {
+            T.assign(n + 1, TRec());
+            for (const SubBlock &sb : subs) {
+                if (sb.flags & 1) continue;
+                for (u32 i = 0; i < sb.size; i++) {
+                    const u32 x = sb.x + i;
+                    T[x] = Encoder::tlist_of(x, sb.size - i, cfg.vld_rge, cfg.ht_width, K ? K : 1, cfg.good_len, P2[x], L2[x], P3[x], L3[x],
+                                             P6.data() + (size_t)x * (K ? K : 1), L6.data() + (size_t)x * (K ? K : 1));
+                }
+            }
+        }
         if (g_dump.on) {
             memcpy(g_dump.binfo, binfo.data(), nblk * 4); memcpy(g_dump.bbpb, bbpb.data(), nblk * 4);
             memcpy(g_dump.lz, lz.data(), n); memcpy(g_dump.P6, P6.data(), (size_t)n * K * 4);
@@ -246,7 +259,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         S.tail_dlt = tail_dlt.data(); S.dict_ok = dict_ok.data();
         S.P6 = P6.data(); S.L6 = L6.data(); S.K = K ? K : 1; S.Z2 = Z2.data(); S.Z6 = Z6.data(); S.D6 = D6.data();
         S.P3 = P3.data(); S.L3 = L3.data(); S.P2 = P2.data(); S.L2 = L2.data(); S.D23 = D23.data(); S.blk_nolz = nolz.data();
-        S.flip = flip.data(); S.replan = replan;
+        S.flip = flip.data(); S.replan = replan; S.T = T.empty() ? nullptr : T.data();
         S.ht2 = ht2.data(); S.ht3 = ht3.data(); S.p_lit = p_lit.data(); S.p_delta = p_lit.data() + 65536; S.ap = ap.data();
         S.rc_out = rc.data(); S.rc_cap = rc_cap; S.bc_out = bc.data(); S.bc_cap = bc_cap;
         S.dec = dec.data(); S.dec_cap = (u32)dec.size();
@@ -262,7 +275,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         if (trace_n) *trace_n = tn;
         if (status < 0) return status;
         RcCoder R;   // the range-coder pass over the decision lists (k_rc on the device)
-        R.run(S);
+        R.run(S, nullptr);
         if (status < 0) return status;
         break;
         }
