@@ -168,6 +168,8 @@ struct EncStream {
     const u32 *P3; const u16 *L3;
     const u32 *P2; const u16 *L2;
     u32 *D23;
+    u32 *B6;               // bitmap (with T): HASH6 == 0 or == the previous position's HASH6
+    u32 *E6;               // bitmap (with T): the record holds table candidates (cnt != 0)
     TRec *T;               // [n] precomputed table candidates (k_mf_tlist); null: general path only (wrapped streams)
     const u8 *blk_nolz;    // [nblk] block left out of the 2-/3-byte chains (statically typed BAD/ENTROPY/DLT)
     const u8 *flip;        // [nblk] outcome of the duplicate-block test the static plan assumed (plan.h); may be null

@@ -18,6 +18,9 @@ struct Decoder {
     ModelSmall &M;
     u32 range, code;
     u32 rc_pos, rc_end, rc_blk;      // read cursor, end of current RC block, its index
+    u32 rc_cur, rc_nxt;              // device: the aligned word under the cursor and the one behind it (already loaded)
+    u32 rc_len, n_rc_blk;            // copies of the stream descriptor's fields (registers instead of descriptor loads)
+    const u8 *rcp;
     u32 bc_pos, bc_end, bc_blk;
     u32 bc_bits, bc_val;
     u32 state, ctx;
@@ -27,12 +30,28 @@ struct Decoder {
 
     CSC_HD Decoder(const DecStream &s, ModelSmall &m) : S(s), M(m) {}
 
+    // The RC payloads of a stream are one contiguous, 16-byte aligned and padded buffer: the device reads it a
+    // word at a time and always has the next word loaded before the cursor gets there, so the byte a
+    // renormalisation needs is never an L2 round trip on the decoder's dependency chain.
+    CSC_HD void rc_seek(u32 pos) {
+        rc_pos = pos;
+#if defined(__CUDA_ARCH__)
+        const u32 *w = reinterpret_cast<const u32 *>(rcp) + (pos >> 2);
+        rc_cur = w[0]; rc_nxt = w[1];
+#endif
+    }
     CSC_HD u32 rc_byte() {
-        if (rc_pos >= S.rc_len || rc_blk >= S.n_rc_blk) { if (!err) err = kErrRead; return 0; }
-        u32 b = S.rc[rc_pos++];
+        if (rc_pos >= rc_len || rc_blk >= n_rc_blk) { if (!err) err = kErrRead; return 0; }
+#if defined(__CUDA_ARCH__)
+        const u32 b = (rc_cur >> ((rc_pos & 3) * 8)) & 0xFFu;
+        rc_pos++;
+        if ((rc_pos & 3) == 0) { rc_cur = rc_nxt; rc_nxt = reinterpret_cast<const u32 *>(rcp)[(rc_pos >> 2) + 1]; }
+#else
+        const u32 b = rcp[rc_pos++];
+#endif
         if (rc_pos == rc_end) {   // block exhausted: the reference fetches the next one at once (:15-21)
             rc_blk++;
-            rc_end = rc_blk < S.n_rc_blk ? S.rc_blk_off[rc_blk + 1] : rc_pos;
+            rc_end = rc_blk < n_rc_blk ? S.rc_blk_off[rc_blk + 1] : rc_pos;
         }
         return b;
     }
@@ -48,15 +67,15 @@ struct Decoder {
     // start of a flush segment: position both readers on a fresh block (:336-345, :657-680)
     CSC_HD void open_segment(bool first) {
         if (!first) { rc_blk++; bc_blk++; }
-        if (rc_blk >= S.n_rc_blk || bc_blk >= S.n_bc_blk) { err = -1; return; }
+        if (rc_blk >= n_rc_blk || bc_blk >= S.n_bc_blk) { err = -1; return; }
         rc_pos = S.rc_blk_off[rc_blk]; rc_end = S.rc_blk_off[rc_blk + 1];
         bc_pos = S.bc_blk_off[bc_blk]; bc_end = S.bc_blk_off[bc_blk + 1];
         range = 0xFFFFFFFFu; bc_bits = 0; bc_val = 0;
         // byte 0 is the coder's initial cache byte; code = bytes 1..4
         if (rc_end - rc_pos < 5) { err = -1; return; }
-        code = ((u32)S.rc[rc_pos + 1] << 24) | ((u32)S.rc[rc_pos + 2] << 16) | ((u32)S.rc[rc_pos + 3] << 8) | S.rc[rc_pos + 4];
-        rc_pos += 5;
-        if (rc_pos == rc_end) { rc_blk++; rc_end = rc_blk < S.n_rc_blk ? S.rc_blk_off[rc_blk + 1] : rc_pos; }
+        code = ((u32)rcp[rc_pos + 1] << 24) | ((u32)rcp[rc_pos + 2] << 16) | ((u32)rcp[rc_pos + 3] << 8) | rcp[rc_pos + 4];
+        rc_seek(rc_pos + 5);
+        if (rc_pos == rc_end) { rc_blk++; rc_end = rc_blk < n_rc_blk ? S.rc_blk_off[rc_blk + 1] : rc_pos; }
     }
     // after open_segment rc_blk may already have advanced when a block held exactly 5 bytes;
     // segment switches are relative to the block the segment *ended* in, which is what rc_blk tracks.
@@ -66,13 +85,13 @@ struct Decoder {
             range <<= 8;
             code = (code << 8) + rc_byte();
         }
-        u32 p = pr;
-        u32 bound = (range >> 12) * p;
-        u32 bit;
-        if (code < bound) { range = bound; p += (0xFFFu - p) >> 5; bit = 1; }
-        else { range -= bound; code -= bound; p -= p >> 5; bit = 0; }
-        pr = (u16)p;
-        return bit;
+        const u32 p = pr;
+        const u32 bound = (range >> 12) * p;
+        const bool one = code < bound;
+        range = one ? bound : range - bound;
+        code = one ? code : code - bound;
+        pr = (u16)(one ? p + ((0xFFFu - p) >> 5) : p - (p >> 5));
+        return one ? 1u : 0u;
     }
     CSC_HD u32 direct16(u32 len) {   // coder_decode_direct, csc_dec.cpp:64-87
         while (bc_bits < len) {
@@ -180,9 +199,10 @@ struct Decoder {
     }
 
     // copy len bytes from x - dist (overlap allowed, csc_dec.cpp:516-518)
-    CSC_HD void lz_copy(u32 dist, u32 len) {
+    CSC_HD u32 lz_copy(u32 dist, u32 len) {   // returns the last byte copied (the next literal context)
         u8 *d = S.wnd + x;
         const u8 *s = d - dist;
+        const u32 last = s[dist >= len ? len - 1 : (len - 1) % dist];   // on its way while the copy runs
         if (dist >= len) {
             for (u32 k = CSC_LANE; k < len; k += CSC_NLANES) d[k] = s[k];
         } else {
@@ -191,11 +211,13 @@ struct Decoder {
         }
         w_sync();
         x += len;
+        return last;
     }
 
     // lz_decode (csc_dec.cpp:476-571). Returns decoded size or sets err.
     CSC_HD u32 lz_decode(u32 limit) {
         const u32 wsz = S.wnd_size;
+        const bool lin = S.out_cap <= wsz;   // the stream never wraps its window: ring offsets are the linear positions
         u32 i = 0;
         while (i <= limit && !err) {
             if (dec_bit(M.p_state[state * 3 + 0]) == 0) {
@@ -218,9 +240,10 @@ struct Decoder {
                 state = (state * 4 + 2) & 0x3F;
                 ctx = 0;
                 if (rep[0] == 0 || rep[0] > x || x >= S.out_cap) { err = kErrDecode; break; }
-                S.wnd[x] = S.wnd[x - rep[0]];
+                const u32 b = S.wnd[x - rep[0]];
+                S.wnd[x] = (u8)b;
                 x++; i++;
-                ctx = S.wnd[x - 1];
+                ctx = b;
                 continue;
             } else {
                 u32 idx = 0;
@@ -236,12 +259,10 @@ struct Decoder {
             }
             if (err) break;
             // bounds checks of the reference ring (csc_dec.cpp:508-510,545-547) on the linear history
-            u32 wpos = x % wsz;
-            if (dist == 0 || dist > x || dist >= wsz || len + i > limit || wpos + len > wsz ||
-                ((x - dist) % wsz) + len > wsz || x + len > S.out_cap) { err = kErrDecode; break; }
-            lz_copy(dist, len);
+            if (dist == 0 || dist > x || dist >= wsz || len + i > limit || x + len > S.out_cap) { err = kErrDecode; break; }
+            if (!lin && (x % wsz + len > wsz || (x - dist) % wsz + len > wsz)) { err = kErrDecode; break; }   // (lin: implied by x + len <= out_cap <= wsz)
+            ctx = lz_copy(dist, len);
             i += len;
-            ctx = S.wnd[x - 1];
         }
         return i;
     }
@@ -257,6 +278,8 @@ struct Decoder {
         state = 0; ctx = 0; err = 0; x = 0;
         rep[0] = rep[1] = rep[2] = rep[3] = 0;
         rc_blk = bc_blk = 0;
+        rcp = S.rc; rc_len = S.rc_len; n_rc_blk = S.n_rc_blk;
+        rc_cur = rc_nxt = 0;
         u32 nruns = 0;
         open_segment(true);
         const u32 maxb = S.raw_blocksize;

@@ -23,6 +23,34 @@
 #include "csc_defs.h"
 #include "warp.h"
 #include "plan.h"
+#include "tstage.cuh"
+
+// TMA staging of the candidate records through shared memory (tstage.cuh); 0: plain loads + L1 prefetch
+#ifndef CSC_TMA_STAGE
+#define CSC_TMA_STAGE 0
+#endif
+// A/B switches of the record path (all on in the product build)
+#ifndef CSC_OPT_TREC
+#define CSC_OPT_TREC 1
+#endif
+#ifndef CSC_OPT_LITRUN
+#define CSC_OPT_LITRUN 1
+#endif
+#ifndef CSC_OPT_PAIR
+#define CSC_OPT_PAIR 1
+#endif
+#ifndef CSC_OPT_LITW
+#define CSC_OPT_LITW 32
+#endif
+#ifndef CSC_OPT_FUSED
+#define CSC_OPT_FUSED 1
+#endif
+#ifndef CSC_OPT_BESTOF_OUT
+#define CSC_OPT_BESTOF_OUT 1
+#endif
+#ifndef CSC_OPT_FM_OUT
+#define CSC_OPT_FM_OUT 1
+#endif
 
 namespace cscb {
 
@@ -56,6 +84,9 @@ struct MfCtx {
     u32 *dsum; u32 gs;     // liveness summary (ModelSmall::dsum) and its granule shift
     u32 *dhi;              // ModelSmall::dead_hi
     const TRec *T;         // precomputed table candidates, or null (wrapped stream)
+    TStage *ts;            // this warp's staging ring for the records (device)
+    const u32 *E6;         // bitmap (with T): the record of the position holds table candidates (or overflowed)
+    const u32 *B6;         // bitmap (with T): HASH6 == 0 or equal to the previous position's -- the only positions SlidePos' 6-byte rules act on
     u32 vld, W, K, good;
     u32 wnd;               // window size when the stream wraps, else 0 (no ring arithmetic on the hot path)
     bool tmode;
@@ -81,14 +112,15 @@ struct Encoder {
     bool tmode, want_tables;   // 2-/3-byte tables: false = chains + liveness bits, true = real tables (after a flip)
     bool wrap;                 // the stream is longer than its window: ring semantics apply (csc_lz.cpp:91-92)
     bool tracing;              // debug trace requested (tests)
+    TStage *ts;                // staging ring of this warp (device; null on the host)
     u32 seg_dec0, seg_bc0, seg_bev0;
 
-    CSC_HD Encoder(const EncStream &s, ModelSmall &m) : S(s), M(m) {}
+    CSC_HD Encoder(const EncStream &s, ModelSmall &m, TStage *t = nullptr) : S(s), M(m), ts(t) {}
     CSC_HDF MfCtx mfctx() const {
         MfCtx h;
         h.lz = S.lz; h.P6 = S.P6; h.L6 = S.L6; h.P3 = S.P3; h.L3 = S.L3; h.P2 = S.P2; h.L2 = S.L2; h.Z6 = S.Z6;
         h.D6 = S.D6; h.D23 = S.D23; h.ht2 = S.ht2; h.ht3 = S.ht3; h.cl = M.cl; h.cd = M.cd;
-        h.dsum = M.dsum; h.gs = gs; h.dhi = &M.dead_hi; h.T = wrap ? nullptr : S.T;
+        h.dsum = M.dsum; h.gs = gs; h.dhi = &M.dead_hi; h.T = (wrap || !CSC_OPT_TREC) ? nullptr : S.T; h.B6 = S.B6; h.E6 = S.E6; h.ts = ts;
         h.vld = vld; h.W = W; h.K = K; h.good = good; h.tmode = tmode;
         h.wnd = wrap ? S.cfg.wnd_size : 0;
         return h;
@@ -172,6 +204,13 @@ struct Encoder {
             put_bc((bc_val >> (bc_bits - 8)) & 0xFF, 2 * (dec_n - seg_dec0));   // after dec_n - seg_dec0 decisions of the segment
             bc_bits -= 8;
         }
+    }
+    // raw bits whose block completions carry an explicit time stamp (the caller appends its decisions afterwards);
+    // the decision queue is known to be empty
+    CSC_HDF void raw16(u32 val, u32 len, u32 stamp) {
+        bc_val = (bc_val << len) | val;
+        bc_bits += len;
+        while (bc_bits >= 8) { put_bc((bc_val >> (bc_bits - 8)) & 0xFF, stamp); bc_bits -= 8; }
     }
     CSC_HD void direct(u32 val, u32 len) {     // csc_coder.h:83-88
         if (len <= 16) direct16(val, len);
@@ -351,8 +390,7 @@ struct Encoder {
         }
         state = (state * 4 + 3) & 0x3F;
     }
-    CSC_HDN void encode_match(u32 dist, u32 lencode) {   // csc_model.cpp:301-366
-        trace(1, lencode, dist);
+    CSC_HDN void encode_match_general(u32 dist, u32 lencode) {   // csc_model.cpp:301-366, decision by decision
         dist = w_uni_u32(dist);
         lencode = w_uni_u32(lencode);
         const u32 st = state;
@@ -393,6 +431,55 @@ struct Encoder {
             });
         }
         state = (state * 4 + 1) & 0x3F;
+    }
+    CSC_HDN void encode_match(u32 dist, u32 lencode) {   // csc_model.cpp:301-366
+        trace(1, lencode, dist);
+#if defined(__CUDA_ARCH__) && CSC_OPT_FUSED
+        dist = w_uni_u32(dist);
+        lencode = w_uni_u32(lencode);
+        if (lencode < 143) {
+            const u32 st = state;
+            u32 base, sbits;
+            if (lencode == 0) { base = 0; sbits = 3; }
+            else if (lencode <= 2) { base = 16 * (lencode - 1) + 8; sbits = 4; }
+            else if (lencode <= 5) { base = 32 * (lencode - 3) + 8 + 32; sbits = 5; }
+            else { base = 32 * 3 + 8 + 32; sbits = 5; }
+            const u32 slot = dist_slot(dist);
+            const u32 cs = slot | (1u << sbits);
+            // the whole packet in one go: lane k owns decision k of state(2) | length(nl) | distance slot(sbits) | the four
+            // modelled low bits of the distance; the raw bits in between are stamped with the decision count in front of them
+            const u32 nl = len_ndec(lencode), n1 = 2 + nl + sbits, ne = slot > 2 ? 4u : 0u;
+            const u32 ebits = slot > 2 ? slot - 2 : 1u, elen = dist - (1u << ebits) - 1;
+            if (dec_n + n1 + ne > S.dec_cap) { err = kErrOverflow; return; }
+            const u32 k = CSC_LANE;
+            u32 bit = 1, sl = slot_of(M.p_state[st * 3]) + k;
+            if (k >= n1) {
+                const u32 c = (rev4(elen & 0x0F) | 0x10) << (k - n1);
+                bit = (c >> 3) & 1;
+                sl = slot_of(M.p_matchdist_extra[(ebits - 1) * 16]) + (c >> 4);
+            } else if (k >= 2 + nl) {
+                const u32 c = cs << (k - 2 - nl);
+                bit = (c >> (sbits - 1)) & 1;
+                sl = slot_of(M.p_dist[base]) + (c >> sbits);
+            } else if (k >= 2) sl = len_dec(lencode, k - 2, bit);
+            if (k < n1 + ne) {
+                u16 *pp = reinterpret_cast<u16 *>(&M) + sl;
+                const u32 v = *pp;
+                *pp = (u16)(bit ? v + ((0xFFFu - v) >> 5) : v - (v >> 5));
+                S.dec[dec_n + k] = (DecEntry)(v | (bit << 15));
+            }
+            if (ebits > 4 && ne) {
+                const u32 stamp = 2 * (dec_n + n1 - seg_dec0), rv = elen >> 4, rl = ebits - 4;
+                if (rl <= 16) raw16(rv, rl, stamp);
+                else { raw16(rv >> 16, rl - 16, stamp); raw16(rv & 0xFFFF, 16, stamp); }
+            }
+            dec_n += n1 + ne;
+            w_sync();
+            state = (state * 4 + 1) & 0x3F;
+            return;
+        }
+#endif
+        encode_match_general(dist, lencode);
     }
     CSC_HDN void encode_int(u32 num) {   // csc_model.cpp:389-414
         u32 slot = num ? ilog2(num) : 0;
@@ -477,6 +564,13 @@ struct Encoder {
     // warm the lines the next find_match(y) will need while the coder is busy with a packet
     CSC_HDF static void prefetch_core(const MfCtx &h, u32 y, u32 sb_end) {
         if (y >= sb_end) return;
+        if ((CSC_OPT_TREC && h.T) && !h.tmode) {   // the records of y .. y + 31 (literal-run check, paired probe): eight 128-byte lines
+#if !CSC_TMA_STAGE
+            const u32 q = y + 4 * CSC_LANE;
+            if (CSC_LANE < 8 && q < sb_end) pf_l1(h.T + q);
+#endif
+            return;
+        }
         if (h.W) { pf_l1(h.P6 + (size_t)y * h.K); pf_l1(h.L6 + (size_t)y * h.K); }
         if (h.tmode) {
             u32 w = word_at(h, y, sb_end);
@@ -573,6 +667,21 @@ struct Encoder {
     }
     // the record of x may stand in for the tables: nothing it consulted has been marked dead
     CSC_HDF static bool trec_valid(const MfCtx &h, u32 x, u32 cnt, u32 far) { return cnt != kTOver && x - far >= *h.dhi; }
+    // record of position p; on the device it comes out of the staging ring once stage(h, x) has covered [x, x + 33) (p in that range)
+    CSC_HDF static const TRec *trec_at(const MfCtx &h, u32 p) {
+#if defined(__CUDA_ARCH__) && CSC_TMA_STAGE
+        return ts_rec(h.ts, p);
+#else
+        return h.T + p;
+#endif
+    }
+    CSC_HDF static void stage(const MfCtx &h, u32 x) {
+#if defined(__CUDA_ARCH__) && CSC_TMA_STAGE
+        ts_ensure(h.ts, h.T, x);
+#else
+        (void)h; (void)x;
+#endif
+    }
 
 #if defined(__CUDACC__)
     // ---- lane-parallel find_match (device) ------------------------------------------------------
@@ -598,58 +707,82 @@ struct Encoder {
         u32 e = __shfl_up_sync(0xFFFFFFFFu, v, 1);
         return lane ? e : 0;
     }
-    // find_match from the precomputed record: lanes 0-3 probe the rep distances, lanes 4-7 hold the table
-    // candidates; the length filter is a prefix maximum over those eight lanes.
+    // find_match from the precomputed records, G positions (x, x + 1, ...) at once, eight lanes each: lanes 0-3 of a
+    // group probe the rep distances, lanes 4-7 hold the table candidates; the length filter is a prefix maximum over
+    // the group.  Candidate list g goes to cl / cd [16 g ...); returns the counts, 8 bits per group.  (Two positions
+    // at once is the lazy parser's u1 / u2 pair: nothing changes between the two calls of the reference.)
+    template <int G>
     static __device__ __forceinline__ u32 fm_fast(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3, u32 tcnt) {
         const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
-        if (limit <= 1) return 0;
-        const u8 *cur = h.lz + x;
-        const bool is_rep = lane < 4;
+        const u32 g = lane >> 3, l8 = lane & 7;
+        const bool ing = g < (u32)G;
+        const u32 px = x + g, lim = ing && limit > g ? limit - g : 0;   // (lim <= 1: find_match returns nothing)
+        const u8 *cur = h.lz + px;
+        const bool is_rep = l8 < 4;
         u32 d = 0, L = 0;
         bool usable = false, cmp = false;
-        if (is_rep) {
-            d = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : r3;
-            usable = d < h.vld;
-            if (usable) {
-                const u8 *m = cur - d;
-                cmp = m[1] == cur[1];
-                if (cmp) L = lane_lcp(cur, m, limit < 64 ? limit : 64);
+        if (lim > 1) {
+            if (is_rep) {
+                d = l8 == 0 ? r0 : l8 == 1 ? r1 : l8 == 2 ? r2 : r3;
+                usable = d < h.vld;
+                if (usable) {
+                    const u8 *m = cur - d;
+                    cmp = m[1] == cur[1];
+                    if (cmp) L = lane_lcp(cur, m, lim < 64 ? lim : 64);
+                }
+            } else {
+                const TRec *t = trec_at(h, px);
+                const u32 tc = G == 1 ? tcnt : (g == 0 ? tcnt & 0xFF : tcnt >> 8);
+                if (l8 - 4 < tc) { d = t->d[l8 - 4]; L = t->l[l8 - 4]; usable = true; }
             }
-        } else if (lane < 4 + tcnt) {
-            const TRec *t = h.T + x;
-            d = t->d[lane - 4];
-            L = t->l[lane - 4];
-            usable = true;
         }
-        u32 more = __ballot_sync(FULL, cmp && L == 64 && limit > 64);
+        u32 more = __ballot_sync(FULL, cmp && L == 64 && lim > 64);
         while (more) {   // long rep matches are finished by the whole warp
             const u32 src = (u32)__ffs((int)more) - 1;
             more &= more - 1;
-            const u32 dd = __shfl_sync(FULL, d, src);
-            const u32 ext = 64 + lcp_bytes(cur + 64, cur - dd + 64, limit - 64);
+            const u32 dd = __shfl_sync(FULL, d, src), sp = __shfl_sync(FULL, px, src), sl = __shfl_sync(FULL, lim, src);
+            const u32 ext = 64 + lcp_bytes(h.lz + sp + 64, h.lz + sp - dd + 64, sl - 64);
             if (lane == src) L = ext;
         }
-        u32 v = usable ? L : 0;   // running maximum of the usable lengths in front of each lane (starts at 1)
+        u32 v = usable ? L : 0;   // running maximum of the usable lengths in front of each lane of the group (starts at 1)
 #pragma unroll
-        for (int sft = 1; sft < 8; sft <<= 1) { const u32 t = __shfl_up_sync(FULL, v, sft); if (lane >= (u32)sft) v = max(v, t); }
+        for (int sft = 1; sft < 8; sft <<= 1) { const u32 t = __shfl_up_sync(FULL, v, sft); if (l8 >= (u32)sft) v = max(v, t); }
         const u32 prev = __shfl_up_sync(FULL, v, 1);
-        const u32 run = max(1u, lane ? prev : 0u);
-        bool acc = lane < 8 && usable && L > run;
-        const u32 stopm = __ballot_sync(FULL, acc && L >= h.good);
-        if (stopm && lane > (u32)__ffs((int)stopm) - 1) acc = false;
-        const u32 has11 = __ballot_sync(FULL, lane == 0 && usable && L >= 2) & 1u;
-        const u32 accm = __ballot_sync(FULL, acc);
-        if (has11 && lane == 0) { h.cl[0] = 1; h.cd[0] = 1; }
-        if (acc) { const u32 idx = has11 + (u32)__popc(accm & ((1u << lane) - 1)); h.cl[idx] = L; h.cd[idx] = is_rep ? 1 + lane : 4 + d; }
+        const u32 run = max(1u, l8 ? prev : 0u);
+        bool acc = usable && L > run;
+        const u32 gsh = 8 * g;
+        const u32 stopm = (__ballot_sync(FULL, acc && L >= h.good) >> gsh) & 0xFFu;
+        if (stopm && l8 > (u32)__ffs((int)stopm) - 1) acc = false;
+        const u32 has11 = (__ballot_sync(FULL, l8 == 0 && usable && L >= 2) >> gsh) & 1u;
+        const u32 accm = (__ballot_sync(FULL, acc) >> gsh) & 0xFFu;
+        if (ing) {
+            if (has11 && l8 == 0) { h.cl[16 * g] = 1; h.cd[16 * g] = 1; }
+            if (acc) { const u32 idx = 16 * g + has11 + (u32)__popc(accm & ((1u << l8) - 1)); h.cl[idx] = L; h.cd[idx] = is_rep ? 1 + l8 : 4 + d; }
+        }
+        const u32 cnt = ing ? has11 + (u32)__popc(accm) : 0;
         __syncwarp();
-        return has11 + (u32)__popc(accm);
+        if (G == 1) return __shfl_sync(FULL, cnt, 0);
+        return __shfl_sync(FULL, cnt, 0) | (__shfl_sync(FULL, cnt, 8) << 8);
     }
     static __device__ __forceinline__ u32 fm_lanes(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
-        const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
-        if (h.T && !h.tmode) {
-            const u32 tcnt = h.T[x].cnt, far = h.T[x].far;
-            if (trec_valid(h, x, tcnt, far)) return fm_fast(h, x, limit, r0, r1, r2, r3, tcnt);
+        if ((CSC_OPT_TREC && h.T) && !h.tmode) {
+            stage(h, x);
+            const u32 tcnt = trec_at(h, x)->cnt, far = trec_at(h, x)->far;
+            if (trec_valid(h, x, tcnt, far)) return fm_fast<1>(h, x, limit, r0, r1, r2, r3, tcnt);
         }
+        return fm_tables(h, x, limit, r0, r1, r2, r3);
+    }
+    // the general statement: candidate rows + liveness (out of line: the hot loops only hold the record path)
+#ifndef CSC_OPT_TABLES_OUT
+#define CSC_OPT_TABLES_OUT 1
+#endif
+#if CSC_OPT_TABLES_OUT
+    static __device__ __noinline__
+#else
+    static __device__ __forceinline__
+#endif
+    u32 fm_tables(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
+        const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
         const u8 *cur = h.lz + x;
         const u32 pos = h.vld + x;
         const bool is_rep = lane < 4, is_tab = lane == 4 || lane == 5, is_row = lane >= 8 && lane < 8 + h.K;
@@ -799,7 +932,7 @@ struct Encoder {
             if (ml > minlen) { minlen = ml; push_cand(h, cnt, ml, 1 + i); stop = ml >= h.good; }
         }
         if (stop) dist = 0xFFFFFFFFu;
-        if (h.T && !h.tmode && trec_valid(h, x, h.T[x].cnt, h.T[x].far)) {   // the precomputed table half (csc_defs.h: TRec)
+        if ((CSC_OPT_TREC && h.T) && !h.tmode && trec_valid(h, x, h.T[x].cnt, h.T[x].far)) {   // the precomputed table half (csc_defs.h: TRec)
             const TRec &t = h.T[x];
             if (limit > 1 && !stop)
                 for (u32 i = 0; i < t.cnt; i++)
@@ -877,10 +1010,15 @@ struct Encoder {
         if (u2.len < u1.len && u2.len + 2 >= u1.len && u1.dist > 4 && (u1.dist >> (4 * (u1.len - u2.len))) > u2.dist) return true;
         return false;
     }
-    CSC_HDF static Cand best_of(const MfCtx &h, u32 n) {   // fold of FindMatch, csc_mf.cpp:497-524
+#if CSC_OPT_BESTOF_OUT
+    CSC_HDN
+#else
+    CSC_HDF
+#endif
+    static Cand best_of(const MfCtx &h, u32 n, u32 at = 0) {   // fold of FindMatch, csc_mf.cpp:497-524
         Cand best; best.len = 1; best.dist = 0;
         for (u32 i = 0; i < n; i++) {
-            Cand c; c.len = h.cl[i]; c.dist = h.cd[i];
+            Cand c; c.len = h.cl[at + i]; c.dist = h.cd[at + i];
             if (i == 0 || second_better(best, c)) best = c;
         }
         return best;
@@ -915,6 +1053,19 @@ struct Encoder {
         if (p_uni(h.W != 0)) {
             if (p_uni(i0 > 1)) { sum_mark_range(h, s + 1, s + i0); bits_set_range(h.D6, s + 1, s + i0); }   // never inserted (:145)
             u32 first = s + i0;
+            if ((CSC_OPT_TREC && h.T) && !h.tmode) {
+                // the rules below only act on positions whose HASH6 is 0 or repeats the previous position's: one look at
+                // the precomputed bitmap of those (k_mf_tlist) settles the common case
+                bool any = false;
+                const u32 w0 = first >> 5, w1 = (s + len - 1) >> 5;
+                for (u32 w = w0 + CSC_LANE; w <= w1; w += CSC_NLANES) {
+                    u32 m = h.B6[w];
+                    if (w == w0) m &= 0xFFFFFFFFu << (first & 31);
+                    if (w == w1) m &= 0xFFFFFFFFu >> (31 - ((s + len - 1) & 31));
+                    any = any || m != 0;
+                }
+                if (!w_any(any)) return;
+            }
             if (p_uni(i0 < len && bit_get_ro(h.Z6, first))) {    // h6 == lasth6 (== 0): slot 0 overwritten (:147-156)
                 u32 e = newest_alive6(h, first, first);
                 if (e != kNone) kill6(h, e);
@@ -931,7 +1082,7 @@ struct Encoder {
     // ---------------------------------------------------- packets
     // The parsers hand packets to the model through emit(); a packet is executed on the spot.
     enum : u32 { OP_LIT = 1, OP_MATCH, OP_REP, OP_REP01, OP_INT, OP_BAD, OP_ENTROPY, OP_DELTA, OP_FLUSH, OP_END };
-    CSC_HDN void exec(u32 op, u32 a, u32 b, u32 c) {
+    CSC_HDF void emit(u32 op, u32 a, u32 b, u32 c) {   // `op` is a constant at every call site: this folds to the one call
         if (err) return;
         switch (op) {
             case OP_LIT: encode_literal(a); break;
@@ -948,7 +1099,6 @@ struct Encoder {
             default: break;
         }
     }
-    CSC_HDF void emit(u32 op, u32 a, u32 b, u32 c) { exec(op, a, b, c); }
 
 #if defined(__CUDA_ARCH__)
     // ---- literal runs (device) ---------------------------------------------------------------------------
@@ -959,10 +1109,23 @@ struct Encoder {
     static __device__ __forceinline__ u32 literal_run(const MfCtx &h, u32 x, u32 end, u32 r0, u32 r1, u32 r2, u32 r3) {
         const u32 p = x + CSC_LANE;
         bool hit = true;
-        if (p < end) {
+        if (*h.dhi == 0) {
+            // nothing of this stream has been marked dead so far, so every record is valid and "has table candidates" is
+            // one bit per position: two words of the E6 bitmap instead of 32 records
+            const u32 w0 = h.E6[x >> 5], w1 = h.E6[(x >> 5) + 1];
+            const u32 tab = __funnelshift_r(w0, w1, x & 31);
+            if (p < end) hit = end - p > 1 && ((tab >> CSC_LANE) & 1u);
+            if (p < end && !hit && end - p > 1) {
+                const u32 w = (u32)h.lz[p] | ((u32)h.lz[p + 1] << 8);
+                if (r0 < h.vld) hit |= ((u32)h.lz[p - r0] | ((u32)h.lz[p + 1 - r0] << 8)) == w;
+                if (r1 < h.vld) hit |= ((u32)h.lz[p - r1] | ((u32)h.lz[p + 1 - r1] << 8)) == w;
+                if (r2 < h.vld) hit |= ((u32)h.lz[p - r2] | ((u32)h.lz[p + 1 - r2] << 8)) == w;
+                if (r3 < h.vld) hit |= ((u32)h.lz[p - r3] | ((u32)h.lz[p + 1 - r3] << 8)) == w;
+            }
+        } else if (p < end && CSC_LANE < CSC_OPT_LITW) {
             if (end - p <= 1) hit = false;
             else {
-                const TRec *t = h.T + p;
+                const TRec *t = trec_at(h, p);
                 const u32 tc = t->cnt, far = t->far;
                 hit = tc != 0 || p - far < *h.dhi;
                 if (!hit) {
@@ -1016,39 +1179,58 @@ struct Encoder {
         const MfCtx h = mfctx();   // pointers and constants of the hot loop stay in registers
         const u32 end = x0 + size;
         u32 x = x0;
-        Cand u1;
+        Cand u1, u2;
         u1.len = 1; u1.dist = 0;
-        bool have = false;
+        u2 = u1;
+        bool have = false, have2 = false;   // have2: u2 already holds the look-ahead of x + 1 (device: paired probe)
         while (p_uni(x < end)) {
 #if defined(__CUDA_ARCH__)
-            if (!have && h.T && !h.tmode && !tracing) {   // a run of literals is found and coded in one go
+            if (CSC_OPT_LITRUN && !have && (CSC_OPT_TREC && h.T) && !h.tmode && !tracing) {   // a run of literals is found and coded in one go
+                stage(h, x);
                 const u32 nl = literal_run(h, x, end, rep[0], rep[1], rep[2], rep[3]);
                 if (nl) { emit_literals(x, nl); x += nl; continue; }
             }
 #endif
+#if defined(__CUDA_ARCH__)
+            if (CSC_OPT_PAIR && !have && !tracing && (CSC_OPT_TREC && h.T) && !h.tmode && x + 1 < end) {
+                // u1 at x and the lazy look-ahead u2 at x + 1 in one go, when both records stand in for the tables
+                const u32 c0 = trec_at(h, x)->cnt, f0 = trec_at(h, x)->far, c1 = trec_at(h, x + 1)->cnt, f1 = trec_at(h, x + 1)->far;
+                if (trec_valid(h, x, c0, f0) && trec_valid(h, x + 1, c1, f1)) {
+                    const u32 nn = fm_fast<2>(h, x, end - x, rep[0], rep[1], rep[2], rep[3], c0 | (c1 << 8));
+                    u1 = best_of(h, nn & 0xFF, 0);
+                    u2 = best_of(h, nn >> 8, 16);
+                    have = true; have2 = true;
+                }
+            }
+#endif
+            bool lazy = false;   // u1 was kept after a look-ahead probe at x + 1 (which entered x + 1 into the tables)
             if (p_uni(!have || !(u1.len == 1 || u1.len >= h.good))) {
                 // the one probe site: u1 at x, or the lazy look-ahead u2 at x + 1
-                const u32 px = have ? x + 1 : x;
-                const u32 nc = fm_core(h, px, end - px, rep[0], rep[1], rep[2], rep[3]);
-                if (tracing) trace_cands(px, nc);
-                Cand c = best_of(h, nc);
-                if (p_uni(!have)) { u1 = c; have = true; continue; }
+                Cand c;
+                if (have && have2) { c = u2; have2 = false; }
+                else {
+                    const u32 px = have ? x + 1 : x;
+#if defined(__CUDA_ARCH__) && CSC_OPT_FM_OUT
+                    const u32 nc = find_match(px, end - px, rep[0], rep[1], rep[2], rep[3]);   // (out of line: the paired probe above is the hot one)
+#else
+                    const u32 nc = fm_core(h, px, end - px, rep[0], rep[1], rep[2], rep[3]);
+#endif
+                    if (tracing) trace_cands(px, nc);
+                    c = best_of(h, nc);
+                    if (p_uni(!have)) { u1 = c; have = true; continue; }
+                }
                 if (p_uni(second_better(u1, c))) {
                     emit(OP_LIT, h.lz[x], 0, 0);
                     x++;
                     u1 = c;
-                } else {
-                    prefetch_core(h, x + u1.len, end);
-                    encode_nonlit(u1, h.lz[x + u1.len - 1]);
-                    slide_core(h, x + 1, u1.len - 1, end);
-                    x += u1.len;
-                    have = false;
+                    continue;
                 }
-                continue;
+                lazy = true;
             }
+            have2 = false;
             if (p_uni(u1.dist == 0)) emit(OP_LIT, h.lz[x], 0, 0);
             else { prefetch_core(h, x + u1.len, end); encode_nonlit(u1, h.lz[x + u1.len - 1]); }
-            slide_core(h, x, u1.len, end);
+            slide_core(h, lazy ? x + 1 : x, lazy ? u1.len - 1 : u1.len, end);
             x += u1.len;
             have = false;
         }
@@ -1156,7 +1338,8 @@ struct Encoder {
         LV_FOR(j) { wp.v[LV_AT(j)] = 0; wd.v[LV_AT(j)] = 0; wb.v[LV_AT(j)] = 0; td.v[LV_AT(j)] = 0; tp.v[LV_AT(j)] = 0; }
         while (p_uni(in_round || i < size)) {
 #if defined(__CUDA_ARCH__)
-            if (!in_round && h.T && !h.tmode && !tracing) {   // outside a round a position without candidates is a literal
+            if (CSC_OPT_LITRUN && !in_round && (CSC_OPT_TREC && h.T) && !h.tmode && !tracing) {   // outside a round a position without candidates is a literal
+                stage(h, x);
                 const u32 nl = literal_run(h, x, end, rep[0], rep[1], rep[2], rep[3]);
                 if (nl) { emit_literals(x, nl); i += nl; x += nl; continue; }
             }
@@ -1191,7 +1374,12 @@ struct Encoder {
                 w_sync();
             }
             if (p_uni(!in_round || apcur < aplimit)) {
-                prefetch_core(h, x + 1, end);
+                if ((CSC_OPT_TREC && h.T) && !h.tmode) {
+#if !CSC_TMA_STAGE
+                    if ((x & 3) == 0 && x + 32 < end) pf_l1(h.T + x + 32);   // every position is visited: one line ahead
+#endif
+                }
+                else prefetch_core(h, x + 1, end);
                 const u32 n = fm_core(h, x, end - x, r0, r1, r2, r3);
                 if (tracing) trace_cands(x, n);
                 price_table(n, ns, t0, td, tp, t1d, t1p);
@@ -1578,6 +1766,9 @@ struct Encoder {
         w_sync();
         for (u32 i = CSC_LANE; i < 64; i += CSC_NLANES) M.dsum[i] = 0;
         if (CSC_LANE == 0) M.dead_hi = 0;
+#if defined(__CUDA_ARCH__) && CSC_TMA_STAGE
+        ts_reset(ts);
+#endif
         w_sync();
         dec_n = bc_n = bev_n = 0;
         seg_dec0 = seg_bc0 = seg_bev0 = 0;

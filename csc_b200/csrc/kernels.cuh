@@ -741,30 +741,62 @@ k_mf_extend(const u8 *__restrict__ lz, const BlockDesc *__restrict__ blk, const 
 // tlist_of), 32 bytes per position.  Rows, chains and records are read / written as whole sectors by
 // neighbouring threads.  Sub-blocks the static plan types as not LZ-parsed are skipped (their records are never
 // read: a duplicate-block flip moves the stream to table mode), and so are wrapped streams.
+template <int K>
+__device__ __forceinline__ TRec tlist_row(const EncStream &S, u32 x, u32 limit, u32 &first) {
+    u32 row[K], len[K];
+    u16 lrow[K];
+    RowIO<K>::load(S.P6 + (size_t)x * K, row);
+    if (K == 1) lrow[0] = S.L6[x];
+    else {
+        // lengths are packed two per word, K / 2 words per row
+        const u32 *lp = reinterpret_cast<const u32 *>(S.L6 + (size_t)x * K);
+        if (K == 2) { const u32 w = lp[0]; len[0] = w & 0xFFFF; len[1] = w >> 16; }
+        else {
+#pragma unroll
+            for (int q = 0; q < K / 8; q++) {
+                const uint4 w = reinterpret_cast<const uint4 *>(lp)[q];
+                len[8 * q] = w.x & 0xFFFF; len[8 * q + 1] = w.x >> 16; len[8 * q + 2] = w.y & 0xFFFF; len[8 * q + 3] = w.y >> 16;
+                len[8 * q + 4] = w.z & 0xFFFF; len[8 * q + 5] = w.z >> 16; len[8 * q + 6] = w.w & 0xFFFF; len[8 * q + 7] = w.w >> 16;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) lrow[k] = (u16)len[k];
+    }
+    first = row[0];
+    return Encoder::tlist_of(x, limit, S.cfg.vld_rge, K, K, S.cfg.good_len, S.P2[x], S.L2[x], S.P3[x], S.L3[x], row, lrow);
+}
 __global__ void __launch_bounds__(256)
 k_mf_tlist(const BlockDesc *__restrict__ blk, const EncStream *__restrict__ streams) {
     const BlockDesc bd = blk[blockIdx.x];
     if (!bd.size || (bd.flags & 1)) return;
     const EncStream &S = streams[bd.stream];
     if (!S.T || S.n > S.cfg.wnd_size) return;
-    const u32 vld = S.cfg.vld_rge, W = S.cfg.ht_width, K = S.K, good = S.cfg.good_len;
-    for (u32 i = threadIdx.x; i < bd.size; i += 256) {
+    const u32 K = S.K;
+    if (S.cfg.ht_width != K) return;   // (never: the row depth is the table width)
+    for (u32 i0 = 0; i0 < bd.size; i0 += 256) {
+        const u32 i = i0 + threadIdx.x;
         const u32 x = bd.x + i;
-        u32 row[16];
-        u16 lrow[16];
-        if (K == 8) {
-            const uint4 a = reinterpret_cast<const uint4 *>(S.P6 + (size_t)x * 8)[0], b = reinterpret_cast<const uint4 *>(S.P6 + (size_t)x * 8)[1];
-            const uint4 l = *reinterpret_cast<const uint4 *>(S.L6 + (size_t)x * 8);
-            row[0] = a.x; row[1] = a.y; row[2] = a.z; row[3] = a.w; row[4] = b.x; row[5] = b.y; row[6] = b.z; row[7] = b.w;
-            lrow[0] = (u16)l.x; lrow[1] = (u16)(l.x >> 16); lrow[2] = (u16)l.y; lrow[3] = (u16)(l.y >> 16);
-            lrow[4] = (u16)l.z; lrow[5] = (u16)(l.z >> 16); lrow[6] = (u16)l.w; lrow[7] = (u16)(l.w >> 16);
-        } else {
-            for (u32 k = 0; k < K && k < 16; k++) { row[k] = S.P6[(size_t)x * K + k]; lrow[k] = S.L6[(size_t)x * K + k]; }
+        bool flag = false;   // SlidePos' 6-byte rules (csc_mf.cpp:147-157) can act on this position
+        bool has = false;    // the record holds table candidates
+        if (i < bd.size) {
+            u32 first = kNone;
+            TRec t;
+            if (K == 1) t = tlist_row<1>(S, x, bd.size - i, first);
+            else if (K == 2) t = tlist_row<2>(S, x, bd.size - i, first);
+            else if (K == 8) t = tlist_row<8>(S, x, bd.size - i, first);
+            else t = tlist_row<16>(S, x, bd.size - i, first);
+            uint4 *o = reinterpret_cast<uint4 *>(S.T + x);
+            o[0] = make_uint4(t.d[0], t.d[1], t.d[2], t.d[3]);
+            o[1] = make_uint4((u32)t.l[0] | ((u32)t.l[1] << 16), (u32)t.l[2] | ((u32)t.l[3] << 16), t.far, t.cnt);
+            flag = (first == x - 1 && x) || ((S.Z6[x >> 5] >> (x & 31)) & 1u);
+            has = t.cnt != 0;
         }
-        const TRec t = Encoder::tlist_of(x, bd.size - i, vld, W, K, good, S.P2[x], S.L2[x], S.P3[x], S.L3[x], row, lrow);
-        uint4 *o = reinterpret_cast<uint4 *>(S.T + x);
-        o[0] = make_uint4(t.d[0], t.d[1], t.d[2], t.d[3]);
-        o[1] = make_uint4((u32)t.l[0] | ((u32)t.l[1] << 16), (u32)t.l[2] | ((u32)t.l[3] << 16), t.far, t.cnt);
+        const u32 m = __ballot_sync(0xFFFFFFFFu, flag), me = __ballot_sync(0xFFFFFFFFu, has);
+        if ((threadIdx.x & 31) == 0) {
+            const u32 sh = x & 31;
+            if (m) { atomicOr(&S.B6[x >> 5], m << sh); if (sh) atomicOr(&S.B6[(x >> 5) + 1], m >> (32 - sh)); }
+            if (me) { atomicOr(&S.E6[x >> 5], me << sh); if (sh) atomicOr(&S.E6[(x >> 5) + 1], me >> (32 - sh)); }
+        }
     }
 }
 
@@ -806,8 +838,10 @@ static const int kEncWarps = 4;
 __global__ void __launch_bounds__(kEncWarps * 32, CSC_ENC_MIN_CTAS)
 k_encode(const EncStream *__restrict__ streams, u32 ns, u32 *queue, const u32 *__restrict__ p2bits) {
     __shared__ ModelSmall sm[kEncWarps];
+    __shared__ TStage tsm[kEncWarps];   // candidate records staged by the bulk-copy engine (tstage.cuh)
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (u32 i = lane; i < 512; i += 32) sm[warp].p2bits[i] = p2bits[i];
+    ts_init(&tsm[warp]);
     __syncwarp();
     for (;;) {
         u32 s = 0;
@@ -815,7 +849,7 @@ k_encode(const EncStream *__restrict__ streams, u32 ns, u32 *queue, const u32 *_
         s = __shfl_sync(0xFFFFFFFFu, s, 0);
         if (s >= ns) break;
         EncStream S = streams[s];
-        Encoder E(S, sm[warp]);
+        Encoder E(S, sm[warp], &tsm[warp]);
         E.run();
         __syncwarp();
     }

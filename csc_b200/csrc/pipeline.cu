@@ -86,10 +86,10 @@ struct Ctx {
     AnalyzerTables *d_AT = nullptr;
     DictTables *d_DT = nullptr;
     u32 *d_p2bits = nullptr;
-    DevBuf packdesc, lz, tmp, keys0, keys1, vals0, vals1, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
+    DevBuf packdesc, lz, tmp, mfs, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
         dwnd, dout, doffs, druns, dmeta, doutptr, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
-        flip, replan, subdesc, subscratch, rcev, bcev, dec, T, swnd;
+        flip, replan, subdesc, subscratch, rcev, bcev, dec, B6, E6, swnd;
     PinBuf h_segout, h_status, h_rcev, h_bcev, h_rc, h_bc, h_meta, h_replan;
     Timer tm;
     CSCB200_Stats stats;
@@ -272,13 +272,17 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     // ---- device memory
     int r = 0;
     r |= C.lz.ensure(total); r |= C.tmp.ensure(total);
-    r |= C.keys0.ensure((size_t)npos * 4 + 16); r |= C.keys1.ensure((size_t)npos * 4 + 16);
-    r |= C.vals0.ensure((size_t)npos * 4 + 16); r |= C.vals1.ensure((size_t)npos * 4 + 16);
+    // One scratch area serves three consumers that never overlap in time: the radix sort's key / value ping-pong buffers
+    // (match-finder stage), the candidate records T written by k_mf_tlist after the last sort and read by k_encode, and
+    // the packed RC / BC sub-streams gathered for the download once k_rc is done.
+    const size_t sortq = align_up((size_t)npos * 4 + 16, 256);
+    const size_t mfs_bytes = std::max<size_t>({4 * sortq, total * sizeof(TRec), (size_t)2 * align_up(rctot + 64, 256)});
+    r |= C.mfs.ensure(mfs_bytes);
     r |= C.P6.ensure(total * K * 4); r |= C.L6.ensure(total * K * 2);
     const size_t bmbytes = total / 8 + 64;
     r |= C.Z2.ensure(bmbytes); r |= C.Z6.ensure(bmbytes); r |= C.D6.ensure(bmbytes); r |= C.D23.ensure(bmbytes);
     r |= C.P3.ensure(total * 4); r |= C.P2.ensure(total * 4); r |= C.L3.ensure(total * 2); r |= C.L2.ensure(total * 2);
-    r |= C.T.ensure(total * sizeof(TRec));
+    r |= C.B6.ensure(bmbytes); r |= C.E6.ensure(bmbytes);
     r |= C.nolz.ensure(nblk + 16); r |= C.flip.ensure(nblk + 16); r |= C.replan.ensure((size_t)ns * 8);
     r |= C.subdesc.ensure((size_t)nsub * sizeof(BlockDesc)); r |= C.subscratch.ensure((size_t)nsub * sizeof(SubBlock));
     r |= C.swnd.ensure((size_t)ns * 4);
@@ -297,6 +301,8 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     r |= C.sbits.ensure((size_t)ns * 4); r |= C.sgoff.ensure((size_t)ns * 8); r |= C.sK.ensure((size_t)ns * 4);
     if (r) return kErrCuda;
     if (C.rstiles.ensure((size_t)nrst * sizeof(RsTile)) || C.rsH.ensure((size_t)rsHn * 4 + 64) || C.rsB.ensure((size_t)rsNb * 4 + 64)) return kErrCuda;
+    RsKey *const keys0 = (RsKey *)C.mfs.as<u8>(), *const keys1 = (RsKey *)(C.mfs.as<u8>() + sortq);
+    u32 *const vals0 = (u32 *)(C.mfs.as<u8>() + 2 * sortq), *const vals1 = (u32 *)(C.mfs.as<u8>() + 3 * sortq);
     u32 launches = 1;
     static bool smem_opt_in = false;
     if (!smem_opt_in) {
@@ -305,8 +311,8 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     }
     // sorts (keys0,vals0) by the low `hbits` key bits inside every stream; returns the buffers holding the result
     auto sort_pairs = [&](u32 hbits, RsKey *&kres, u32 *&vres) -> int {
-        RsKey *ka = C.keys0.as<RsKey>(), *kb = C.keys1.as<RsKey>();
-        u32 *va = C.vals0.as<u32>(), *vb = C.vals1.as<u32>();
+        RsKey *ka = keys0, *kb = keys1;
+        u32 *va = vals0, *vb = vals1;
         for (u32 shift = 0; shift < hbits; shift += 8) {
             const u32 bits = std::min<u32>(8, hbits - shift), mask = (1u << bits) - 1;
             rs_hist<<<nrst, kRsThreads, 0, st>>>(ka, C.rstiles.as<RsTile>(), shift, mask, C.rsH.as<u32>());
@@ -337,7 +343,8 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         S.P3 = C.P3.as<u32>() + goff[s]; S.L3 = C.L3.as<u16>() + goff[s];
         S.P2 = C.P2.as<u32>() + goff[s]; S.L2 = C.L2.as<u16>() + goff[s];
         S.D23 = C.D23.as<u32>() + goff[s] / 32; S.blk_nolz = C.nolz.as<u8>();
-        S.T = (J.n > S.cfg.wnd_size || bounded) ? nullptr : C.T.as<TRec>() + goff[s];
+        S.T = (J.n > S.cfg.wnd_size || bounded) ? nullptr : C.mfs.as<TRec>() + goff[s];
+        S.B6 = C.B6.as<u32>() + goff[s] / 32; S.E6 = C.E6.as<u32>() + goff[s] / 32;
         S.flip = C.flip.as<u8>(); S.replan = C.replan.as<u32>() + 2 * (size_t)s;
         S.ht2 = C.ht.as<u32>() + (size_t)s * 81920; S.ht3 = S.ht2 + 16384;
         S.p_lit = C.plit.as<u16>() + (size_t)s * 131072; S.p_delta = S.p_lit + 65536;
@@ -380,6 +387,8 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     CK(cudaMemsetAsync(C.Z6.p, 0, bmbytes, st));
     CK(cudaMemsetAsync(C.D6.p, 0, bmbytes, st));
     CK(cudaMemsetAsync(C.D23.p, 0, bmbytes, st));
+    CK(cudaMemsetAsync(C.B6.p, 0, bmbytes, st));
+    CK(cudaMemsetAsync(C.E6.p, 0, bmbytes, st));
     CK(cudaMemsetAsync(C.P3.p, 0xFF, total * 4, st));
     CK(cudaMemsetAsync(C.P2.p, 0xFF, total * 4, st));
     CK(cudaMemsetAsync(C.ht.p, 0, (size_t)ns * 81920 * 4, st));
@@ -404,7 +413,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     launches += 3;
     // ---- match finder precomputation: 6-byte rows, then the 3-byte and 2-byte chains
     k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), key_shift,
-                                           C.keys0.as<RsKey>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), 6);
+                                           keys0, vals0, C.Z2.as<u32>(), C.Z6.as<u32>(), 6);
     T.mark(st);                                                                   // 4
     RsKey *ksorted = nullptr;
     u32 *vsorted = nullptr;
@@ -415,7 +424,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     if (bounded) {   // two more candidate lists by 8- and 12-byte context, then one distance-ordered row
         for (u32 which = kBtCtxB; which <= kBtCtxC; which += kBtCtxC - kBtCtxB) {
             k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), key_shift,
-                                                   C.keys0.as<RsKey>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
+                                                   keys0, vals0, C.Z2.as<u32>(), C.Z6.as<u32>(), which);
             sort_pairs(key_shift, ksorted, vsorted);
             k_mf_rows<<<nrst, 256, 0, st>>>(ksorted, vsorted, C.rstiles.as<RsTile>(), C.sgoff.as<u64>(), C.sK.as<u32>(), C.P6.as<u32>(),
                                             which == kBtCtxB ? kBtKB : kBtKC, kBtRowK, which == kBtCtxB ? kBtKA : kBtKA + kBtKB);
@@ -435,7 +444,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
         u32 *P = which == 3 ? C.P3.as<u32>() : C.P2.as<u32>();
         u16 *L = which == 3 ? C.L3.as<u16>() : C.L2.as<u16>();
         k_mf_hash<<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sbits.as<u32>(), C.sgoff.as<u64>(), C.swnd.as<u32>(), shift,
-                                               C.keys0.as<RsKey>(), C.vals0.as<u32>(), C.Z2.as<u32>(), C.Z6.as<u32>(), which);
+                                               keys0, vals0, C.Z2.as<u32>(), C.Z6.as<u32>(), which);
         sort_pairs(shift, ksorted, vsorted);
         k_mf_rows<<<nrst, 256, 0, st>>>(ksorted, vsorted, C.rstiles.as<RsTile>(), C.sgoff.as<u64>(), C.sK.as<u32>(), P, 1, 0, 0);
         k_mf_extend<1><<<nsub, kMfThreads, 0, st>>>(C.lz.as<u8>(), C.subdesc.as<BlockDesc>(), C.sgoff.as<u64>(), P, L);
@@ -536,12 +545,13 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     }
     if (any_payload) {   // gather on the device, then two dense downloads
         // the sort buffers are free again: 8 bytes per position each, the sub-streams need < 1.2
-        if (hrc + 16 > C.keys0.cap || hbc + 16 > C.keys1.cap) { if (C.keys0.ensure(hrc + 16) || C.keys1.ensure(hbc + 16)) return kErrCuda; }
+        u8 *const pk_rc = C.mfs.as<u8>(), *const pk_bc = C.mfs.as<u8>() + align_up(rctot + 64, 256);   // (hrc, hbc <= rctot + alignment)
+        if (hrc + 16 > align_up(rctot + 64, 256) || hbc + 16 > align_up(rctot + 64, 256)) return kErrCuda;
         if (C.packdesc.ensure((size_t)ns * sizeof(PackDesc))) return kErrCuda;
         CK(cudaMemcpyAsync(C.packdesc.p, pd.data(), (size_t)ns * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
-        k_pack_results<<<dim3(ns, 4), 256, 0, st>>>(C.rc.as<u8>(), C.bc.as<u8>(), C.keys0.as<u8>(), C.keys1.as<u8>(), C.packdesc.as<PackDesc>());
-        if (hrc) CK(cudaMemcpyAsync(C.h_rc.p, C.keys0.p, hrc, cudaMemcpyDeviceToHost, st));
-        if (hbc) CK(cudaMemcpyAsync(C.h_bc.p, C.keys1.p, hbc, cudaMemcpyDeviceToHost, st));
+        k_pack_results<<<dim3(ns, 4), 256, 0, st>>>(C.rc.as<u8>(), C.bc.as<u8>(), pk_rc, pk_bc, C.packdesc.as<PackDesc>());
+        if (hrc) CK(cudaMemcpyAsync(C.h_rc.p, pk_rc, hrc, cudaMemcpyDeviceToHost, st));
+        if (hbc) CK(cudaMemcpyAsync(C.h_bc.p, pk_bc, hbc, cudaMemcpyDeviceToHost, st));
         launches += 1;
     }
     T.mark(st);                                                                   // 11
@@ -578,7 +588,8 @@ size_t framed_size(const EncJob &J, bool with_props) {
 }
 
 size_t per_stream_bytes() { return 81920 * 4 + 131072 * 2 + (kApLimit + 2) * sizeof(ApUnit) + 140000 * 2 + 4096; }
-size_t per_pos_bytes(u32 K) { return 2 + 24 + 6 * (size_t)K + 12 + 1 + 3 + 9 * sizeof(DecEntry) + sizeof(TRec); }
+// lz + tmp, scratch (sort buffers / records), rows, 2-/3-byte chains, six bitmaps, RC + BC output (n + n/8 each), decisions
+size_t per_pos_bytes(u32 K) { return 2 + sizeof(TRec) + 6 * (size_t)K + 12 + 1 + 3 + 9 * sizeof(DecEntry); }
 
 // ----------------------------------------------------------------------------- decode
 struct DecJob {

@@ -221,6 +221,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         std::vector<u32> D23((n + 31) / 32 + 1, 0);
         // precomputed table candidates (k_mf_tlist on the device): the same scalar statement, per LZ-parsed sub-block
         std::vector<TRec> T;
+        std::vector<u32> B6((n + 31) / 32 + 2, 0);
         if (n <= cfg.wnd_size && !cfg.bounded && !getenv("CSC_HS_NO_TREC")) {
             T.assign(n + 1, TRec());
             for (const SubBlock &sb : subs) {
@@ -229,6 +230,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
                     const u32 x = sb.x + i;
                     T[x] = Encoder::tlist_of(x, sb.size - i, cfg.vld_rge, cfg.ht_width, K ? K : 1, cfg.good_len, P2[x], L2[x], P3[x], L3[x],
                                              P6.data() + (size_t)x * (K ? K : 1), L6.data() + (size_t)x * (K ? K : 1));
+                    if ((K && x && P6[(size_t)x * K] == x - 1) || ((Z6[x >> 5] >> (x & 31)) & 1u)) B6[x >> 5] |= 1u << (x & 31);
                 }
             }
         }
@@ -259,7 +261,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         S.tail_dlt = tail_dlt.data(); S.dict_ok = dict_ok.data();
         S.P6 = P6.data(); S.L6 = L6.data(); S.K = K ? K : 1; S.Z2 = Z2.data(); S.Z6 = Z6.data(); S.D6 = D6.data();
         S.P3 = P3.data(); S.L3 = L3.data(); S.P2 = P2.data(); S.L2 = L2.data(); S.D23 = D23.data(); S.blk_nolz = nolz.data();
-        S.flip = flip.data(); S.replan = replan; S.T = T.empty() ? nullptr : T.data();
+        S.flip = flip.data(); S.replan = replan; S.T = T.empty() ? nullptr : T.data(); S.B6 = B6.data();
         S.ht2 = ht2.data(); S.ht3 = ht3.data(); S.p_lit = p_lit.data(); S.p_delta = p_lit.data() + 65536; S.ap = ap.data();
         S.rc_out = rc.data(); S.rc_cap = rc_cap; S.bc_out = bc.data(); S.bc_cap = bc_cap;
         S.dec = dec.data(); S.dec_cap = (u32)dec.size();

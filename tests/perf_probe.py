@@ -22,6 +22,7 @@ for spec in sys.argv[1:]:
     st = csc_b200.get_stats()
     comp = sum(o.size for o in outs)
     enc = {k[3:]: round(v, 1) for k, v in st.items() if k.startswith("ms_") and v > 0.5}
+    enc["waves"] = st.get("waves")
     t = time.time()
     back = csc_b200.decode_chunks(outs, [c.size for c in chunks])
     dd = time.time() - t
