@@ -115,7 +115,7 @@ struct ModelSmall {
     u16 p_longlen;
     u16 p_rle_flag;
     u32 len_price[32];
-    u32 p2bits[512];      // p_2_bits_ (csc_model.cpp:68-70), host-libm derived
+    const u32 *p2bits;    // p_2_bits_ (csc_model.cpp:68-70), host-libm derived: 512 entries, one copy per CTA (shared memory is L1 the warps need)
     u32 row_e[8];         // scratch: candidate row of the current position (lane-gathered)
     u32 row_l[8];
     u32 cl[kMaxCand];     // scratch: candidate list of the current find_match (len, dist code)

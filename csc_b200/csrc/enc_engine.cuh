@@ -112,6 +112,7 @@ struct Encoder {
     bool tmode, want_tables;   // 2-/3-byte tables: false = chains + liveness bits, true = real tables (after a flip)
     bool wrap;                 // the stream is longer than its window: ring semantics apply (csc_lz.cpp:91-92)
     bool tracing;              // debug trace requested (tests)
+    bool use_rec;              // lazy parser: take the record path for the next sub-block
     TStage *ts;                // staging ring of this warp (device; null on the host)
     u32 seg_dec0, seg_bc0, seg_bev0;
 
@@ -667,7 +668,7 @@ struct Encoder {
     }
     // the record of x may stand in for the tables: nothing it consulted has been marked dead
     CSC_HDF static bool trec_valid(const MfCtx &h, u32 x, u32 cnt, u32 far) { return cnt != kTOver && x - far >= *h.dhi; }
-    // record of position p; on the device it comes out of the staging ring once stage(h, x) has covered [x, x + 33) (p in that range)
+    // record of position p; on the device it comes out of the staging ring once stage(h, x) has covered x and x + 1
     CSC_HDF static const TRec *trec_at(const MfCtx &h, u32 p) {
 #if defined(__CUDA_ARCH__) && CSC_TMA_STAGE
         return ts_rec(h.ts, p);
@@ -764,24 +765,26 @@ struct Encoder {
         if (G == 1) return __shfl_sync(FULL, cnt, 0);
         return __shfl_sync(FULL, cnt, 0) | (__shfl_sync(FULL, cnt, 8) << 8);
     }
+    // find_match on the device.  REC: the caller is on the record path -- the precomputed record answers when it is
+    // valid and the general statement is an out-of-line call (cold there); !REC: the general statement inline and no
+    // record code at all (the table path of the lazy parser, whose hot loop has to stay small).
+    template <bool REC>
     static __device__ __forceinline__ u32 fm_lanes(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
-        if ((CSC_OPT_TREC && h.T) && !h.tmode) {
-            stage(h, x);
-            const u32 tcnt = trec_at(h, x)->cnt, far = trec_at(h, x)->far;
-            if (trec_valid(h, x, tcnt, far)) return fm_fast<1>(h, x, limit, r0, r1, r2, r3, tcnt);
+        if (REC) {
+            if (h.T && !h.tmode) {
+                stage(h, x);
+                const u32 tcnt = trec_at(h, x)->cnt, far = trec_at(h, x)->far;
+                if (trec_valid(h, x, tcnt, far)) return fm_fast<1>(h, x, limit, r0, r1, r2, r3, tcnt);
+            }
+            return fm_tables_out(h, x, limit, r0, r1, r2, r3);
         }
         return fm_tables(h, x, limit, r0, r1, r2, r3);
     }
-    // the general statement: candidate rows + liveness (out of line: the hot loops only hold the record path)
-#ifndef CSC_OPT_TABLES_OUT
-#define CSC_OPT_TABLES_OUT 1
-#endif
-#if CSC_OPT_TABLES_OUT
-    static __device__ __noinline__
-#else
-    static __device__ __forceinline__
-#endif
-    u32 fm_tables(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
+    static __device__ __noinline__ u32 fm_tables_out(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
+        return fm_tables(h, x, limit, r0, r1, r2, r3);
+    }
+    // the general statement: candidate rows + liveness
+    static __device__ __forceinline__ u32 fm_tables(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
         const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
         const u8 *cur = h.lz + x;
         const u32 pos = h.vld + x;
@@ -893,9 +896,10 @@ struct Encoder {
 
     // find_match (csc_mf.cpp:243-495): candidate list (M.cl / M.cd) in reference probe order.  On the device
     // this is fm_lanes; the scalar statement below is what the host simulation runs against the oracle.
+    template <bool REC = true>
     CSC_HDF static u32 fm_core(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
 #if defined(__CUDA_ARCH__)
-        return fm_lanes(h, x, limit, r0, r1, r2, r3);
+        return fm_lanes<REC>(h, x, limit, r0, r1, r2, r3);
 #else
         const u8 *cur = h.lz + x;
         const u32 pos = h.vld + x;
@@ -1029,6 +1033,7 @@ struct Encoder {
     CSC_HDN u32 newest_alive6(u32 x, u32 bound) const { const MfCtx h = mfctx(); return newest_alive6(h, x, bound); }
 
     // SlidePos (csc_mf.cpp:134-206): positions s+1 .. s+len-1 are passed over by a match.
+    template <bool REC = true>
     CSC_HDF static void slide_core(const MfCtx &h, u32 s, u32 len, u32 sb_end) {
         if (p_uni(len <= 1)) return;
         u32 i0 = 1;
@@ -1053,7 +1058,7 @@ struct Encoder {
         if (p_uni(h.W != 0)) {
             if (p_uni(i0 > 1)) { sum_mark_range(h, s + 1, s + i0); bits_set_range(h.D6, s + 1, s + i0); }   // never inserted (:145)
             u32 first = s + i0;
-            if ((CSC_OPT_TREC && h.T) && !h.tmode) {
+            if (REC && (CSC_OPT_TREC && h.T) && !h.tmode) {
                 // the rules below only act on positions whose HASH6 is 0 or repeats the previous position's: one look at
                 // the precomputed bitmap of those (k_mf_tlist) settles the common case
                 bool any = false;
@@ -1125,7 +1130,7 @@ struct Encoder {
         } else if (p < end && CSC_LANE < CSC_OPT_LITW) {
             if (end - p <= 1) hit = false;
             else {
-                const TRec *t = trec_at(h, p);
+                const TRec *t = h.T + p;   // (global: the staging ring only covers the probe positions)
                 const u32 tc = t->cnt, far = t->far;
                 hit = tc != 0 || p - far < *h.dhi;
                 if (!hit) {
@@ -1175,24 +1180,30 @@ struct Encoder {
             rep[0] = u.dist - 4;
         }
     }
-    CSC_HDN void parse_lazy(u32 x0, u32 size) {   // compress_normal(size, true), csc_lz.cpp:156-199
+    // compress_normal(size, true), csc_lz.cpp:156-199.  Two instances on the device, same results: REC reads the precomputed
+    // records (literal runs in one go, u1 / u2 as a paired probe) and wins where literals dominate; !REC walks the candidate
+    // rows, with no record code in its loop, and wins on match-dense data (text).  lz_run picks per sub-block from the
+    // literal share of the sub-block before.  Returns the number of literals coded.
+    template <bool REC>
+    CSC_HDN u32 parse_lazy_t(u32 x0, u32 size) {
         const MfCtx h = mfctx();   // pointers and constants of the hot loop stay in registers
         const u32 end = x0 + size;
         u32 x = x0;
         Cand u1, u2;
         u1.len = 1; u1.dist = 0;
         u2 = u1;
+        u32 nlit = 0;
         bool have = false, have2 = false;   // have2: u2 already holds the look-ahead of x + 1 (device: paired probe)
         while (p_uni(x < end)) {
 #if defined(__CUDA_ARCH__)
-            if (CSC_OPT_LITRUN && !have && (CSC_OPT_TREC && h.T) && !h.tmode && !tracing) {   // a run of literals is found and coded in one go
+            if (REC && CSC_OPT_LITRUN && !have && (CSC_OPT_TREC && h.T) && !h.tmode && !tracing) {   // a run of literals is found and coded in one go
                 stage(h, x);
                 const u32 nl = literal_run(h, x, end, rep[0], rep[1], rep[2], rep[3]);
-                if (nl) { emit_literals(x, nl); x += nl; continue; }
+                if (nl) { emit_literals(x, nl); x += nl; nlit += nl; continue; }
             }
 #endif
 #if defined(__CUDA_ARCH__)
-            if (CSC_OPT_PAIR && !have && !tracing && (CSC_OPT_TREC && h.T) && !h.tmode && x + 1 < end) {
+            if (REC && CSC_OPT_PAIR && !have && !tracing && (CSC_OPT_TREC && h.T) && !h.tmode && x + 1 < end) {
                 // u1 at x and the lazy look-ahead u2 at x + 1 in one go, when both records stand in for the tables
                 const u32 c0 = trec_at(h, x)->cnt, f0 = trec_at(h, x)->far, c1 = trec_at(h, x + 1)->cnt, f1 = trec_at(h, x + 1)->far;
                 if (trec_valid(h, x, c0, f0) && trec_valid(h, x + 1, c1, f1)) {
@@ -1210,17 +1221,14 @@ struct Encoder {
                 if (have && have2) { c = u2; have2 = false; }
                 else {
                     const u32 px = have ? x + 1 : x;
-#if defined(__CUDA_ARCH__) && CSC_OPT_FM_OUT
-                    const u32 nc = find_match(px, end - px, rep[0], rep[1], rep[2], rep[3]);   // (out of line: the paired probe above is the hot one)
-#else
-                    const u32 nc = fm_core(h, px, end - px, rep[0], rep[1], rep[2], rep[3]);
-#endif
+                    const u32 nc = fm_core<REC>(h, px, end - px, rep[0], rep[1], rep[2], rep[3]);
                     if (tracing) trace_cands(px, nc);
                     c = best_of(h, nc);
                     if (p_uni(!have)) { u1 = c; have = true; continue; }
                 }
                 if (p_uni(second_better(u1, c))) {
                     emit(OP_LIT, h.lz[x], 0, 0);
+                    nlit++;
                     x++;
                     u1 = c;
                     continue;
@@ -1228,12 +1236,13 @@ struct Encoder {
                 lazy = true;
             }
             have2 = false;
-            if (p_uni(u1.dist == 0)) emit(OP_LIT, h.lz[x], 0, 0);
+            if (p_uni(u1.dist == 0)) { emit(OP_LIT, h.lz[x], 0, 0); nlit++; }
             else { prefetch_core(h, x + u1.len, end); encode_nonlit(u1, h.lz[x + u1.len - 1]); }
-            slide_core(h, lazy ? x + 1 : x, lazy ? u1.len - 1 : u1.len, end);
+            slide_core<REC>(h, lazy ? x + 1 : x, lazy ? u1.len - 1 : u1.len, end);
             x += u1.len;
             have = false;
         }
+        return nlit;
     }
 
     // ---------------------------------------------------------- optimal parser
@@ -1457,7 +1466,16 @@ struct Encoder {
                 if (to_wrap < sb) sb = to_wrap;
             }
             if (S.cfg.lz_mode == 3) parse_optimal(a + off, sb);
-            else parse_lazy(a + off, sb);
+            else {
+#if defined(__CUDA_ARCH__)
+                // record path when the sub-block before was mostly literals (or the run is typed EXE), else the table path
+                const bool rec = use_rec && S.T && !wrap && !tmode && !tracing;
+                const u32 nl = rec ? parse_lazy_t<true>(a + off, sb) : parse_lazy_t<false>(a + off, sb);
+                use_rec = 3 * nl > sb;
+#else
+                parse_lazy_t<true>(a + off, sb);
+#endif
+            }
             off += sb;
             if (err) return;
         }
@@ -1689,6 +1707,7 @@ struct Encoder {
             lz_run(a, size);
         } else if (type == DT_EXE) {
             emit(OP_INT, DT_EXE, 0, 0);
+            use_rec = true;   // machine code: literal-heavy
             lz_run(a, size);
         } else if (type == DT_ENGTXT) {
             if (S.dict_ok[first_blk]) { emit(OP_INT, DT_ENGTXT, 0, 0); emit(OP_INT, size, 0, 0); }
@@ -1758,7 +1777,7 @@ struct Encoder {
     CSC_HD void init_common() {
         vld = S.cfg.vld_rge; W = S.cfg.ht_width; K = S.K; good = S.cfg.good_len;
         err = 0; tr_n = 0;
-        tmode = false; want_tables = false;
+        tmode = false; want_tables = false; use_rec = false;
         wrap = S.n > S.cfg.wnd_size;
         tracing = S.trace != nullptr;
         gs = 5;

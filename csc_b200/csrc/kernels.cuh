@@ -838,10 +838,20 @@ static const int kEncWarps = 4;
 __global__ void __launch_bounds__(kEncWarps * 32, CSC_ENC_MIN_CTAS)
 k_encode(const EncStream *__restrict__ streams, u32 ns, u32 *queue, const u32 *__restrict__ p2bits) {
     __shared__ ModelSmall sm[kEncWarps];
+#if CSC_TMA_STAGE
     __shared__ TStage tsm[kEncWarps];   // candidate records staged by the bulk-copy engine (tstage.cuh)
+#endif
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u32 i = lane; i < 512; i += 32) sm[warp].p2bits[i] = p2bits[i];
+    __shared__ u32 s_p2bits[512];
+    for (u32 i = threadIdx.x; i < 512; i += kEncWarps * 32) s_p2bits[i] = p2bits[i];
+    if (lane == 0) sm[warp].p2bits = s_p2bits;
+    __syncthreads();
+#if CSC_TMA_STAGE
     ts_init(&tsm[warp]);
+    TStage *const tsw = &tsm[warp];
+#else
+    TStage *const tsw = nullptr;
+#endif
     __syncwarp();
     for (;;) {
         u32 s = 0;
@@ -849,7 +859,7 @@ k_encode(const EncStream *__restrict__ streams, u32 ns, u32 *queue, const u32 *_
         s = __shfl_sync(0xFFFFFFFFu, s, 0);
         if (s >= ns) break;
         EncStream S = streams[s];
-        Encoder E(S, sm[warp], &tsm[warp]);
+        Encoder E(S, sm[warp], tsw);
         E.run();
         __syncwarp();
     }

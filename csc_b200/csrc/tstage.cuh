@@ -1,19 +1,21 @@
 // tstage.cuh -- TMA staging of the precomputed candidate records (TRec) for the serial warp.
 //
 // The parser of a stream walks its positions front to back and reads the 32-byte TRec of the positions it
-// stops at plus a 32-position look-ahead (literal-run check, paired probe).  The records of a stream are one
-// dense array, so they are brought into shared memory by the bulk-copy engine (cp.async.bulk global ->
-// shared, completion on an mbarrier) 64 records = 2 KiB at a time, one chunk ahead of the chunk being parsed:
-// the serial warp then reads them with shared-memory latency instead of waiting on L1 / L2 misses, and issues
-// no load instructions for them at all.  Ring of two chunks per warp: record p lives in slot p & 127.
+// stops at and of the position behind it (paired probe).  The records of a stream are one dense array, so they
+// are brought into shared memory by the bulk-copy engine (cp.async.bulk global -> shared, completion on an
+// mbarrier) 16 records = 512 bytes at a time, one chunk ahead of the chunk being parsed: the serial warp then
+// reads them with shared-memory latency and issues no load instructions for them.  Ring of two chunks per
+// warp: record p lives in slot p & 31.  The ring is kept this small on purpose: every kilobyte of shared
+// memory per warp is 20 KB of L1 the SM's resident streams lose, and k_encode lives on its L1 hit rate (a
+// 128-record ring measured 20 % slower end to end, profiles/r02_ab_tma.log).
 #pragma once
 #include "csc_defs.h"
 
 namespace cscb {
 
-static const u32 kTsChunk = 64;                       // records per bulk copy
+static const u32 kTsChunk = 16;                       // records per bulk copy (512 bytes)
 static const u32 kTsRing = 2 * kTsChunk;              // records per warp
-static const u32 kTsBytes = kTsChunk * sizeof(TRec);  // 2048
+static const u32 kTsBytes = kTsChunk * sizeof(TRec);
 
 struct alignas(128) TStage {
     TRec ring[kTsRing];
@@ -70,7 +72,7 @@ __device__ __forceinline__ void ts_wait(TStage *ts, u32 half) {
     if ((threadIdx.x & 31u) == 0) { ts->pend &= ~(1u << half); ts->phase ^= 1u << half; }
     __syncwarp();
 }
-// make the records of positions [x, x + 33) readable from the ring
+// make the records of positions x and x + 1 (the paired probe) readable from the ring
 __device__ __forceinline__ void ts_ensure(TStage *ts, const TRec *T, u32 x) {
     const u32 c = x / kTsChunk, lo = ts->lo;
     if (c != lo) {
@@ -80,7 +82,7 @@ __device__ __forceinline__ void ts_ensure(TStage *ts, const TRec *T, u32 x) {
         __syncwarp();
     }
     ts_wait(ts, c & 1u);
-    if ((x & (kTsChunk - 1)) + 33 > kTsChunk) ts_wait(ts, (c + 1) & 1u);
+    if ((x & (kTsChunk - 1)) == kTsChunk - 1) ts_wait(ts, (c + 1) & 1u);
 }
 __device__ __forceinline__ const TRec *ts_rec(const TStage *ts, u32 p) { return &ts->ring[p & (kTsRing - 1)]; }
 #endif

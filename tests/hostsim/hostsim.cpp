@@ -268,7 +268,9 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         S.rc_ev = rc_ev.data(); S.bc_ev = bc_ev.data(); S.ev_cap = (u32)rc_ev.size(); S.segout = so.data(); S.status = &status;
         S.trace = trace; S.trace_cap = (u32)trace_cap; S.trace_n = &tn;
         ModelSmall *M = new ModelSmall;
-        build_p2bits(M->p2bits);
+        static u32 p2bits_tab[512];
+        build_p2bits(p2bits_tab);
+        M->p2bits = p2bits_tab;
         Encoder *E = new Encoder(S, *M);
         E->run();
         delete E;
