@@ -21,7 +21,7 @@ EXPORTS = ["CSCEncProps_Init", "CSCEnc_WriteProperties", "CSCEnc_EstMemUsage", "
            "CSCEnc_Encode", "CSCEnc_Encode_Flush", "CSCDec_ReadProperties", "CSCDec_Create", "CSCDec_Destroy",
            "CSCDec_Decode", "CSCB200_EncodeBound", "CSCB200_EncodeChunks", "CSCB200_DecodeChunks",
            "CSCB200_EncodeChunksDevice", "CSCB200_SetDevice", "CSCB200_SetDevices", "CSCB200_DeviceCount", "CSCB200_Trim", "CSCB200_ChunkRange",
-           "CSCB200_GetStats", "CSCB200_Available"]
+           "CSCB200_GetStats", "CSCB200_Available", "CSCB200_EncodeChunksAdler", "CSCB200_DecodeChunksAdler", "CSCB200_Adler32"]
 
 
 class CSCProps(C.Structure):   # csc_common.h:19-63 (ABI)
@@ -83,6 +83,10 @@ def lib():
         l.CSCB200_EncodeChunksDevice.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                                  C.c_void_p]
         l.CSCB200_DecodeChunks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.CSCB200_EncodeChunksAdler.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.CSCB200_DecodeChunksAdler.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.CSCB200_Adler32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.CSCB200_SetDevice.argtypes = [C.c_int]
         l.CSCB200_GetStats.argtypes = [C.POINTER(Stats)]
         _lib = l
@@ -191,6 +195,54 @@ def decode_chunks_raw(in_ptrs, in_sizes, out_ptrs, out_caps):
     if r < 0:
         raise RuntimeError(f"CSCB200_DecodeChunks failed: {r}")
     return [int(v) for v in on]
+
+
+def adler32(bufs, init=None):
+    """csarc's checksum (archiver/csa_adler32.cpp) of every buffer, on the GPU; init: running values to continue from"""
+    arrs = [_u8(b) for b in bufs]
+    n = len(arrs)
+    ip = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    isz = (C.c_size_t * n)(*[a.size for a in arrs])
+    ini = (C.c_uint32 * n)(*init) if init is not None else None
+    out = (C.c_uint32 * n)()
+    r = lib().CSCB200_Adler32(n, ip, isz, ini, out)
+    if r < 0:
+        raise RuntimeError(f"CSCB200_Adler32 failed: {r}")
+    return [int(v) for v in out]
+
+
+def encode_chunks_adler(chunks, dict_size: int, level: int, flt_mask: int = 7, with_props: bool = True):
+    """encode_chunks plus the Adler-32 of every raw chunk (taken from its copy in HBM)"""
+    ins = [_u8(c) for c in chunks]
+    n = len(ins)
+    outs = [np.empty(encode_bound(c.size), dtype=np.uint8) for c in ins]
+    ip = (C.c_void_p * n)(*[c.ctypes.data for c in ins])
+    isz = (C.c_size_t * n)(*[c.size for c in ins])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    ocap = (C.c_size_t * n)(*[o.size for o in outs])
+    on = (C.c_size_t * n)()
+    ad = (C.c_uint32 * n)()
+    r = lib().CSCB200_EncodeChunksAdler(n, ip, isz, dict_size, level, flt_mask, int(with_props), op, ocap, on, ad)
+    if r < 0:
+        raise RuntimeError(f"CSCB200_EncodeChunksAdler failed: {r}")
+    return [o[:int(k)] for o, k in zip(outs, on)], [int(v) for v in ad]
+
+
+def decode_chunks_adler(streams, raw_sizes):
+    """decode_chunks plus the Adler-32 of every decoded chunk (taken on the device before the download)"""
+    ins = [_u8(c) for c in streams]
+    n = len(ins)
+    outs = [np.empty(int(k) + 64, dtype=np.uint8) for k in raw_sizes]
+    ip = (C.c_void_p * n)(*[c.ctypes.data for c in ins])
+    isz = (C.c_size_t * n)(*[c.size for c in ins])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    ocap = (C.c_size_t * n)(*[int(k) for k in raw_sizes])
+    on = (C.c_size_t * n)()
+    ad = (C.c_uint32 * n)()
+    r = lib().CSCB200_DecodeChunksAdler(n, ip, isz, op, ocap, on, ad)
+    if r < 0:
+        raise RuntimeError(f"CSCB200_DecodeChunksAdler failed: {r}")
+    return [o[:int(k)] for o, k in zip(outs, on)], [int(v) for v in ad]
 
 
 def encode_chunks(chunks, dict_size: int, level: int, flt_mask: int = 7, with_props: bool = True):

@@ -9,6 +9,7 @@
 //   k_mf_extend    forward match length of every (position, candidate) pair, capped at the
 //                  sub-block end                               (csc_mf.cpp:470, 8 B words)
 //   k_mf_tlist     thread per position: table candidates of find_match under the all-alive assumption (TRec)
+//   k_adler32_*    Adler-32 of many buffers (csarc's checksum): CTA per 64 KiB tile + in-order combine
 //   k_encode       one stream per warp: enc_engine.cuh (parser + adaptive model -> decision lists)
 //   k_rc           one stream per warp, warp-uniform: rc_engine.cuh (range-coder recurrence over the decision lists)
 //   k_decode       one stream per warp: dec_engine.cuh
@@ -821,6 +822,63 @@ k_pack_results(const u8 *__restrict__ rc, const u8 *__restrict__ bc, u8 *__restr
         const u32 nv = (d.bc_n + 15) / 16;
         for (u32 i = part * 256 + threadIdx.x; i < nv; i += parts * 256) o[i] = s[i];
     }
+}
+
+// ------------------------------------------------------------------ Adler-32 (csarc's file checksum)
+// adler32() of the archiver (csa_adler32.cpp:63-128, zlib's) over many buffers at once.  A buffer is cut into
+// 64 KiB tiles; a CTA reduces one tile to (A, B) = (sum of bytes, sum of (len - offset) * byte), both mod 65521,
+// with coalesced 16-byte loads; k_adler32_combine then folds the tiles of a buffer in order:
+// b += len * a + B_tile, a += A_tile (the running `a` carries the initial value 1).
+static const u32 kAdlerTile = 65536, kAdlerBase = 65521;
+struct AdlerTile { u64 off; u32 len; u32 buf; };   // byte offset inside the batch buffer, bytes, owning buffer
+__global__ void __launch_bounds__(256)
+k_adler32_tiles(const u8 *__restrict__ base, const AdlerTile *__restrict__ tiles, u32 *__restrict__ partA, u32 *__restrict__ partB) {
+    __shared__ u64 sa[8], sb[8];
+    const AdlerTile t = tiles[blockIdx.x];
+    const u8 *p = base + t.off;
+    u64 a = 0, w = 0;   // sum of bytes, sum of offset * byte
+    const u32 mis = (u32)((uintptr_t)p & 15);
+    const u32 head = mis ? min(16 - mis, t.len) : 0;
+    if (threadIdx.x < head) { const u32 b = p[threadIdx.x]; a += b; w += (u64)threadIdx.x * b; }
+    const u32 nv = (t.len - head) / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(p + head);
+    for (u32 i = threadIdx.x; i < nv; i += 256) {
+        const uint4 q = v[i];
+        const u32 o = head + i * 16;
+        const u32 ws[4] = {q.x, q.y, q.z, q.w};
+        u32 s = 0, sw = 0;   // bytes of this vector, sum of (index in vector) * byte
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const u32 b = (ws[k] >> (8 * j)) & 0xFF; s += b; sw += (4 * k + j) * b; }
+        a += s;
+        w += (u64)o * s + sw;
+    }
+    const u32 tail0 = head + nv * 16;
+    if (tail0 + threadIdx.x < t.len) { const u32 b = p[tail0 + threadIdx.x]; a += b; w += (u64)(tail0 + threadIdx.x) * b; }
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, sft); w += __shfl_xor_sync(0xFFFFFFFFu, w, sft); }
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = w; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 A = 0, W = 0;
+        for (int k = 0; k < 8; k++) { A += sa[k]; W += sb[k]; }
+        // B_tile = sum (len - offset) * byte = len * A - W   (A <= 2^24, W <= 2^40: no overflow)
+        partA[blockIdx.x] = (u32)(A % kAdlerBase);
+        partB[blockIdx.x] = (u32)(((u64)t.len * A - W) % kAdlerBase);
+    }
+}
+__global__ void k_adler32_combine(const AdlerTile *__restrict__ tiles, const u32 *__restrict__ partA, const u32 *__restrict__ partB,
+                                  const u32 *__restrict__ first_tile, u32 nbuf, const u32 *__restrict__ init, u32 *__restrict__ out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbuf) return;
+    const u32 v0 = init ? init[i] : 1u;
+    u64 a = v0 & 0xFFFF, b = (v0 >> 16) & 0xFFFF;
+    for (u32 t = first_tile[i]; t < first_tile[i + 1]; t++) {
+        b = (b + (u64)(tiles[t].len % kAdlerBase) * a + partB[t]) % kAdlerBase;
+        a = (a + partA[t]) % kAdlerBase;
+    }
+    out[i] = (u32)a | ((u32)b << 16);
 }
 
 // ------------------------------------------------------------------ fill helper

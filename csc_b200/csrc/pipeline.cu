@@ -89,8 +89,8 @@ struct Ctx {
     DevBuf packdesc, lz, tmp, mfs, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
         dwnd, dout, doffs, druns, dmeta, doutptr, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
-        flip, replan, subdesc, subscratch, rcev, bcev, dec, B6, E6, swnd;
-    PinBuf h_segout, h_status, h_rcev, h_bcev, h_rc, h_bc, h_meta, h_replan;
+        flip, replan, subdesc, subscratch, rcev, bcev, dec, B6, E6, adl, swnd;
+    PinBuf h_segout, h_status, h_rcev, h_bcev, h_rc, h_bc, h_meta, h_adler, h_replan;
     Timer tm;
     CSCB200_Stats stats;
 };
@@ -183,12 +183,44 @@ struct EncJob {
     std::vector<SegOut> so;
     const u8 *rc, *bc;
     const u32 *rc_ev, *bc_ev;   // block-completion time stamps (SegOut::rev_off / bev_off index these)
+    u32 adler = 1;              // Adler-32 of the raw input (when the wave is asked for it)
 };
+
+// ----------------------------------------------------------------------------- Adler-32
+// adler32() (archiver/csa_adler32.cpp:63-128) of n byte ranges of one device buffer, results into pinned host memory
+// (valid after the next synchronisation of C.st).  init == nullptr: every checksum starts at 1.
+int adler_ranges(Ctx &C, const u8 *d_base, const std::vector<u64> &off, const std::vector<u64> &len, const u32 *init, u32 **h_out) {
+    const u32 n = (u32)off.size();
+    std::vector<AdlerTile> tiles;
+    std::vector<u32> first(n + 1);
+    for (u32 i = 0; i < n; i++) {
+        first[i] = (u32)tiles.size();
+        for (u64 o = 0; o < len[i]; o += kAdlerTile) tiles.push_back({off[i] + o, (u32)std::min<u64>(kAdlerTile, len[i] - o), i});
+    }
+    first[n] = (u32)tiles.size();
+    const size_t nt = tiles.size();
+    // layout of C.adl: tiles | partA | partB | first | init | out
+    const size_t o_pa = align_up(nt * sizeof(AdlerTile) + 16, 256), o_pb = o_pa + align_up(nt * 4 + 16, 256), o_first = o_pb + align_up(nt * 4 + 16, 256);
+    const size_t o_init = o_first + align_up((size_t)(n + 1) * 4, 256), o_out = o_init + align_up((size_t)n * 4 + 16, 256);
+    if (C.adl.ensure(o_out + (size_t)n * 4 + 256) || C.h_adler.ensure((size_t)n * 4 + 16)) return kErrCuda;
+    u8 *b = C.adl.as<u8>();
+    cudaStream_t st = C.st;
+    if (nt) CK(cudaMemcpyAsync(b, tiles.data(), nt * sizeof(AdlerTile), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_first, first.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (init) CK(cudaMemcpyAsync(b + o_init, init, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (nt) k_adler32_tiles<<<(u32)nt, 256, 0, st>>>(d_base, (const AdlerTile *)b, (u32 *)(b + o_pa), (u32 *)(b + o_pb));
+    k_adler32_combine<<<(n + 127) / 128, 128, 0, st>>>((const AdlerTile *)b, (const u32 *)(b + o_pa), (const u32 *)(b + o_pb), (const u32 *)(b + o_first), n,
+                                                      init ? (const u32 *)(b + o_init) : nullptr, (u32 *)(b + o_out));
+    CK(cudaMemcpyAsync(C.h_adler.p, b + o_out, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    *h_out = C.h_adler.as<u32>();
+    return 0;
+}
 
 // ----------------------------------------------------------------------------- encode
 // Runs the whole device pipeline for a set of streams that fits in HBM at once and leaves,
 // per job, the RC/BC sub-streams + block events in pinned host memory.
-int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
+int encode_wave(Ctx &C, std::vector<EncJob *> &jobs, bool want_adler = false) {
     const u32 ns = (u32)jobs.size();
     if (!ns) return 0;
     cudaStream_t st = C.st;
@@ -398,6 +430,14 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     CK(cudaMemsetAsync(C.taildlt.p, 0, (size_t)nseg * 5 * 4, st));
     CK(cudaMemsetAsync(C.segout.p, 0, (size_t)nseg * sizeof(SegOut), st));
     k_fill_u16<<<592, 256, 0, st>>>(C.plit.as<u16>(), (u64)ns * 131072, 2048);
+    u32 *h_adl = nullptr;
+    if (want_adler) {   // checksum of the raw chunks while they sit in HBM, before the filters rewrite them in place
+        std::vector<u64> ao(goff.begin(), goff.end()), al(ns);
+        for (u32 s = 0; s < ns; s++) al[s] = jobs[s]->n;
+        int ar = adler_ranges(C, C.lz.as<u8>(), ao, al, nullptr, &h_adl);
+        if (ar < 0) return ar;
+        launches += 2;
+    }
     T.mark(st);                                                                   // 1
     // ---- analyzer, static plan, filters
     k_analyze<<<(nblk + kAnWarps - 1) / kAnWarps, kAnWarps * 32, 0, st>>>(C.lz.as<u8>(), C.blkdesc.as<BlockDesc>(), nblk, C.d_AT,
@@ -501,6 +541,7 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs) {
     CK(cudaStreamSynchronize(st));
     const SegOut *hso = C.h_segout.as<SegOut>();
     const i32 *hst = C.h_status.as<i32>();
+    if (h_adl) for (u32 s = 0; s < ns; s++) jobs[s]->adler = h_adl[s];
     std::vector<u32> rcn(ns, 0), bcn(ns, 0), hrcoff(ns), hbcoff(ns);
     size_t hrc = 0, hbc = 0;
     int ret = 0;
@@ -601,9 +642,10 @@ struct DecJob {
     DecInput di;
     bool predeframed = false;      // di was filled block by block by the caller (handle API)
     std::vector<DecRun> runs;      // filled when want_runs
+    u32 adler = 1;                 // Adler-32 of the decoded bytes (when the wave is asked for it)
 };
 
-int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
+int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs, bool want_adler = false) {
     const u32 ns = (u32)jobs.size();
     if (!ns) return 0;
     cudaStream_t st = C.st;
@@ -706,8 +748,16 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs) {
                 CK(cudaMemcpyAsync(J.runs.data(), C.druns.as<DecRun>() + runoff[s], J.runs.size() * sizeof(DecRun), cudaMemcpyDeviceToHost, st));
         }
     }
+    u32 *h_adl = nullptr;
+    if (want_adler) {   // checksum of the decoded chunks on the device, next to their download
+        std::vector<u64> ao(ns), al(ns);
+        for (u32 s = 0; s < ns; s++) { ao[s] = woff[s]; al[s] = jobs[s]->status < 0 ? 0 : jobs[s]->out_size; }
+        int ar = adler_ranges(C, C.dout.as<u8>(), ao, al, nullptr, &h_adl);
+        if (ar < 0) return ar;
+    }
     T.mark(st);                                                                   // 4
     CK(cudaStreamSynchronize(st));
+    if (h_adl) for (u32 s = 0; s < ns; s++) jobs[s]->adler = h_adl[s];
     CSCB200_Stats &S = C.stats;
     S.ms_h2d += T.ms(0, 1); S.ms_decode += T.ms(1, 2); S.ms_unfilter += T.ms(2, 3); S.ms_d2h += T.ms(3, 4);
     S.ms_total_gpu += T.ms(0, 4); S.ms_frame += ms_deframe;
@@ -810,7 +860,7 @@ void chunk_range(int n, int k, int g, int &lo, int &hi) {
 
 // ----------------------------------------------------------------------------- batched encode on one device
 int encode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
-                     int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size, bool device) {
+                     int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size, bool device, uint32_t *adler = nullptr) {
     if (n <= 0) return 0;
     std::vector<EncJob> jobs(n);
     for (int i = 0; i < n; i++) {
@@ -844,8 +894,9 @@ int encode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_s
             at++;
         }
         std::stable_sort(wave.begin(), wave.end(), [](const EncJob *a, const EncJob *b) { return a->n > b->n; });
-        int r = encode_wave(C, wave);
+        int r = encode_wave(C, wave, adler != nullptr);
         if (r < 0) { ret = r; break; }
+        if (adler) for (EncJob *J : wave) adler[J - jobs.data()] = J->adler;
         auto t0 = std::chrono::steady_clock::now();
         // host framing (MemIO replay) of the wave's streams: independent per stream, so spread over host threads
         std::atomic<size_t> next{0}, bytes_out{0};
@@ -884,6 +935,7 @@ int encode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_s
     if (ret < 0) return ret;
     for (int i = 0; i < n; i++) {
         if (jobs[i].n) continue;   // empty chunk: header + EOF segment only
+        if (adler) adler[i] = 1;
         if (device) { out_size[i] = (with_props ? CSC_PROP_SIZE : 0) + 17; continue; }
         MemSink sink{out[i], out_cap[i], 0, false};
         if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&jobs[i].props, hdr); sink(hdr, CSC_PROP_SIZE); }
@@ -896,7 +948,7 @@ int encode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_s
 }
 
 int decode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out, const size_t *out_cap,
-                     size_t *out_size) {
+                     size_t *out_size, uint32_t *adler = nullptr) {
     if (n <= 0) return 0;
     std::vector<DecJob> jobs(n);
     for (int i = 0; i < n; i++) {
@@ -917,10 +969,10 @@ int decode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_s
             wave.push_back(&jobs[at]);
             at++;
         }
-        int r = decode_wave(C, wave, false);
+        int r = decode_wave(C, wave, false, adler != nullptr);
         if (r < 0) { ret = r; break; }
     }
-    for (int i = 0; i < n; i++) { out_size[i] = jobs[i].out_size; C.stats.bytes_out += jobs[i].out_size; }
+    for (int i = 0; i < n; i++) { out_size[i] = jobs[i].out_size; C.stats.bytes_out += jobs[i].out_size; if (adler) adler[i] = jobs[i].adler; }
     return ret;
 }
 
@@ -1027,6 +1079,46 @@ int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
                          size_t *out_size) {
     return fan_out(n, true, [&](Ctx &C, int lo, int hi) {
         return decode_chunks_on(C, hi - lo, in + lo, in_size + lo, out + lo, out_cap + lo, out_size + lo);
+    });
+}
+
+// The same two calls with csarc's per-file checksum as a by-product: adler32() (archiver/csa_adler32.cpp:63-128) of every
+// raw chunk is taken from its copy in HBM on the way in / of every decoded chunk before it is downloaded, instead of a
+// separate pass over the bytes on a host thread (csa_io.h:250, :342).
+int CSCB200_EncodeChunksAdler(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level, int flt_mask,
+                              int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size, uint32_t *adler_in) {
+    return fan_out(n, true, [&](Ctx &C, int lo, int hi) {
+        return encode_chunks_on(C, hi - lo, in + lo, in_size + lo, dict_size, level, flt_mask, with_props, out + lo, out_cap + lo, out_size + lo, false,
+                                adler_in ? adler_in + lo : nullptr);
+    });
+}
+int CSCB200_DecodeChunksAdler(int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out, const size_t *out_cap,
+                              size_t *out_size, uint32_t *adler_out) {
+    return fan_out(n, true, [&](Ctx &C, int lo, int hi) {
+        return decode_chunks_on(C, hi - lo, in + lo, in_size + lo, out + lo, out_cap + lo, out_size + lo, adler_out ? adler_out + lo : nullptr);
+    });
+}
+// adler32(init[i], buf[i], size[i]) for n host buffers (init == NULL: 1), in waves that fit the device
+int CSCB200_Adler32(int n, const uint8_t *const *buf, const size_t *size, const uint32_t *init, uint32_t *out) {
+    if (n <= 0) return 0;
+    return fan_out(n, true, [&](Ctx &C, int lo, int hi) {
+        const size_t budget = mem_budget(C) / 2;
+        int at = lo;
+        while (at < hi) {
+            std::vector<u64> off, len;
+            size_t tot = 0;
+            int first = at;
+            while (at < hi && (off.empty() || tot + size[at] + 256 <= budget)) { off.push_back(tot); len.push_back(size[at]); tot = align_up(tot + size[at], 256); at++; }
+            if (C.lz.ensure(tot + 256)) return (int)kErrCuda;
+            for (int i = first; i < at; i++)
+                if (size[i]) CK(cudaMemcpyAsync(C.lz.as<u8>() + off[i - first], buf[i], size[i], cudaMemcpyHostToDevice, C.st));
+            u32 *h = nullptr;
+            int r = adler_ranges(C, C.lz.as<u8>(), off, len, init ? init + first : nullptr, &h);
+            if (r < 0) return r;
+            CK(cudaStreamSynchronize(C.st));
+            for (int i = first; i < at; i++) out[i] = h[i - first];
+        }
+        return 0;
     });
 }
 

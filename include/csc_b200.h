@@ -40,6 +40,18 @@ int CSCB200_DecodeChunks(int n, const uint8_t *const *in, const size_t *in_size,
 int CSCB200_EncodeChunksDevice(int n, const uint8_t *const *d_in, const size_t *in_size, uint32_t dict_size, int level,
                                int flt_mask, int with_props, size_t *out_size);
 
+/* csarc keeps an Adler-32 per file (archiver/csa_adler32.cpp:63-128, taken over the bytes it reads, csa_io.h:250, and
+ * over the bytes it writes back, csa_io.h:342).  These variants return it as a by-product of the pass the data makes
+ * through HBM anyway: adler_in[i] = adler32(1, in[i], in_size[i]) of the raw chunk, adler_out[i] = adler32(1, ...) of
+ * the decoded chunk.  CSCB200_Adler32 is the stand-alone form, adler32(init[i], buf[i], size[i]) (init NULL: 1);
+ * checksums of consecutive pieces of a file chain through init exactly like the reference's running value. */
+int CSCB200_EncodeChunksAdler(int n, const uint8_t *const *in, const size_t *in_size, uint32_t dict_size, int level,
+                              int flt_mask, int with_props, uint8_t *const *out, const size_t *out_cap, size_t *out_size,
+                              uint32_t *adler_in);
+int CSCB200_DecodeChunksAdler(int n, const uint8_t *const *in, const size_t *in_size, uint8_t *const *out,
+                              const size_t *out_cap, size_t *out_size, uint32_t *adler_out);
+int CSCB200_Adler32(int n, const uint8_t *const *buf, const size_t *size, const uint32_t *init, uint32_t *out);
+
 /* GPU selection.  Every call runs on a device context leased from a per-GPU pool for the duration of the call, so
  * handles and batched calls may be used from any number of threads (csarc: one handle per worker thread).
  *   CSCB200_SetDevice(d)      this thread's calls run on GPU d (-1: the thread's current CUDA device, the default)

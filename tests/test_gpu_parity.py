@@ -452,3 +452,32 @@ def test_decoder_stops_at_the_end_of_its_stream(gpu_lib, ref):
     l.CSCDec_Destroy(h)
     assert not st["over"] and st["off"] == s.size
     assert same(np.frombuffer(bytes(out), dtype=np.uint8), d)
+
+
+def test_adler32_matches_zlib(gpu_lib, ref):
+    """csarc's file checksum (archiver/csa_adler32.cpp:63-128 is zlib's adler32) on the GPU: stand-alone, chained through
+    `init` like the reference's running value (csa_io.h:250), and as a by-product of the batched encode / decode calls"""
+    import zlib
+    from csc_b200 import api
+    rng = np.random.default_rng(5)
+    bufs = [np.zeros(0, np.uint8), np.array([7], np.uint8), np.full(100000, 255, np.uint8), synth.text(300007, 3), synth.exe(65536, 4),
+            synth.random_bytes(65537, 5), synth.mixed((3 << 20) + 11, 6), rng.integers(0, 256, 15, dtype=np.uint8)]
+    got = api.adler32(bufs)
+    assert got == [zlib.adler32(b.tobytes()) & 0xFFFFFFFF for b in bufs]
+    # chaining: the checksum of a file read in pieces
+    whole = synth.mixed(1 << 20, 8)
+    cuts = [0, 1, 4097, 70000, 500001, whole.size]
+    run = 1
+    for a, b in zip(cuts, cuts[1:]):
+        run = api.adler32([whole[a:b]], init=[run])[0]
+    assert run == zlib.adler32(whole.tobytes()) & 0xFFFFFFFF
+    # by-product of encode / decode
+    chunks = api.split_chunks(synth.mixed(2 << 20, 9), 300000) + [np.zeros(0, np.uint8)]
+    outs, ad_in = api.encode_chunks_adler(chunks, 1 << 20, 1)
+    assert ad_in == [zlib.adler32(c.tobytes()) & 0xFFFFFFFF for c in chunks]
+    for c, o in zip(chunks, outs):
+        e = ref.encode(c, min(1 << 20, c.size) if c.size else 1 << 20, 1) if c.size else None
+        assert e is None or (e.size == o.size and (e == o).all())
+    back, ad_out = api.decode_chunks_adler(outs, [c.size for c in chunks])
+    assert all(b.size == c.size and (b == c).all() for b, c in zip(back, chunks))
+    assert ad_out == ad_in
