@@ -39,6 +39,9 @@
 #ifndef CSC_OPT_PAIR
 #define CSC_OPT_PAIR 1
 #endif
+#ifndef CSC_OPT_PAIR_TAB
+#define CSC_OPT_PAIR_TAB 0   // measured slower (text -m2 354 -> 406 ms per GiB): the table path lives on a small hot loop
+#endif
 #ifndef CSC_OPT_LITW
 #define CSC_OPT_LITW 32
 #endif
@@ -113,6 +116,7 @@ struct Encoder {
     bool wrap;                 // the stream is longer than its window: ring semantics apply (csc_lz.cpp:91-92)
     bool tracing;              // debug trace requested (tests)
     bool use_rec;              // lazy parser: take the record path for the next sub-block
+    bool run_text;             // the run being parsed is typed ENGTXT: no records were built for it (k_mf_tlist), table path only
     TStage *ts;                // staging ring of this warp (device; null on the host)
     u32 seg_dec0, seg_bc0, seg_bev0;
 
@@ -894,6 +898,89 @@ struct Encoder {
     }
 #endif
 
+#if defined(__CUDACC__)
+    // The general statement for TWO positions at once, x in lanes 0-15 and x + 1 in lanes 16-31 (chain mode, no window
+    // wrap, rows of at most 8 entries): the lazy parser's u1 / u2 pair, which the reference computes back to back with
+    // nothing in between that the second call could see (find_match(x) only enters x, which the rows of x + 1 already
+    // hold as alive).  List g goes to cl / cd [16 g ...); returns the two counts, or kNone when one of the positions
+    // needs the walk behind a short bucket (then the caller probes one position at a time).
+    static __device__ __forceinline__ u32 fm_tables2(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
+        const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
+        const u32 g = lane >> 4, l = lane & 15, gb = 16 * g;
+        const u32 px = x + g, lim = limit > g ? limit - g : 0;
+        const u8 *cur = h.lz + px;
+        const u32 pos = h.vld + px;
+        const bool is_rep = l < 4, is_tab = l == 4 || l == 5, is_row = l >= 8 && l < 8 + h.K;
+        u32 d = 0, L = 0;
+        bool cand = false, need_cmp = false;
+        if (is_rep) {
+            d = l == 0 ? r0 : l == 1 ? r1 : l == 2 ? r2 : r3;
+            cand = d < h.vld;
+            need_cmp = cand;
+        } else if (is_tab) {
+            const bool three = l == 5;
+            const u32 *P = three ? h.P3 : h.P2;
+            u32 e = P[px];
+            L = three ? h.L3[px] : h.L2[px];
+            if (e != kNone && dead23(h, e)) { e = alive23(h, P, e); need_cmp = true; }
+            d = (e == kNone) ? pos : px - e;
+            cand = true;
+        } else if (is_row) {
+            const size_t at = (size_t)px * h.K + (l - 8);
+            const u32 e = h.P6[at];
+            L = h.L6[at];
+            cand = e != kNone && !dead6(h, e);
+            d = e != kNone ? px - e : 0;
+        }
+        const u32 validrow = (__ballot_sync(FULL, is_row && d != 0) >> (gb + 8)) & 0xFFu;
+        const u32 alivem = (__ballot_sync(FULL, is_row && cand) >> gb) & 0xFFFFu;
+        const bool live = lim > 1;   // (limit <= 1: find_match returns nothing)
+        const u32 lt = (1u << l) - 1;
+        const bool cons = is_row && cand && (u32)__popc(alivem & lt) < h.W;
+        const u32 dm = (is_tab || cons) ? d : 0;
+        const u32 d2v = __shfl_sync(FULL, d, gb + 4), d3v = __shfl_sync(FULL, d, gb + 5);
+        const bool entered = dm > (l == 4 ? 0u : l == 5 ? d2v : max(d2v, d3v));
+        bool usable;
+        if (is_rep) usable = cand;
+        else if (l == 4) usable = entered && d < h.vld && px != d && px >= d;
+        else if (l == 5) usable = entered && d < h.vld && px >= d;
+        else usable = cons && entered && d < h.vld;
+        usable = usable && live;
+        if (need_cmp && usable) {
+            const u8 *m = cur - d;
+            L = 0;
+            if (m[1] == cur[1]) L = lane_lcp(cur, m, lim < 64 ? lim : 64);
+        }
+        u32 more = __ballot_sync(FULL, need_cmp && usable && L == 64 && lim > 64);
+        while (more) {   // long matches are finished by the whole warp
+            const u32 src = (u32)__ffs((int)more) - 1;
+            more &= more - 1;
+            const u32 dd = __shfl_sync(FULL, d, src), sp = __shfl_sync(FULL, px, src), sl = __shfl_sync(FULL, lim, src);
+            const u32 ext = 64 + lcp_bytes(h.lz + sp + 64, h.lz + sp - dd + 64, sl - 64);
+            if (lane == src) L = ext;
+        }
+        const u32 lu = usable ? L : 0;
+        u32 v = lu;   // running maximum of the usable lengths in front of each lane of its group (starts at 1)
+#pragma unroll
+        for (int sft = 1; sft < 16; sft <<= 1) { const u32 t = __shfl_up_sync(FULL, v, sft); if (l >= (u32)sft) v = max(v, t); }
+        const u32 prev = __shfl_up_sync(FULL, v, 1);
+        const u32 run = max(1u, l ? prev : 0u);
+        bool acc = usable && L > run && !(!is_rep && L <= 6 && d >= mf_bound(L));
+        const u32 stopm = (__ballot_sync(FULL, acc && L >= h.good) >> gb) & 0xFFFFu;
+        if (stopm && l > (u32)__ffs((int)stopm) - 1) acc = false;
+        const u32 has11 = (__ballot_sync(FULL, l == 0 && usable && L >= 2) >> gb) & 1u;
+        const u32 accm = (__ballot_sync(FULL, acc) >> gb) & 0xFFFFu;
+        const u32 full = (1u << h.K) - 1;
+        const bool walk = live && h.W && !stopm && validrow == full && (u32)__popc(alivem) < h.W;
+        if (__any_sync(FULL, walk)) return kNone;
+        if (has11 && l == 0) { h.cl[gb] = 1; h.cd[gb] = 1; }
+        if (acc) { const u32 idx = gb + has11 + (u32)__popc(accm & lt); h.cl[idx] = L; h.cd[idx] = is_rep ? 1 + l : 4 + d; }
+        const u32 cnt = has11 + (u32)__popc(accm);
+        __syncwarp();
+        return __shfl_sync(FULL, cnt, 0) | (__shfl_sync(FULL, cnt, 16) << 8);
+    }
+#endif
+
     // find_match (csc_mf.cpp:243-495): candidate list (M.cl / M.cd) in reference probe order.  On the device
     // this is fm_lanes; the scalar statement below is what the host simulation runs against the oracle.
     template <bool REC = true>
@@ -1214,6 +1301,17 @@ struct Encoder {
                 }
             }
 #endif
+#if defined(__CUDA_ARCH__)
+            if (!REC && CSC_OPT_PAIR_TAB && !have && !tracing && !h.tmode && !h.wnd && h.K <= 8 && x + 1 < end) {
+                // table path: the rows of x and x + 1 through the general statement side by side
+                const u32 nn = fm_tables2(h, x, end - x, rep[0], rep[1], rep[2], rep[3]);
+                if (nn != kNone) {
+                    u1 = best_of(h, nn & 0xFF, 0);
+                    u2 = best_of(h, nn >> 8, 16);
+                    have = true; have2 = true;
+                }
+            }
+#endif
             bool lazy = false;   // u1 was kept after a look-ahead probe at x + 1 (which entered x + 1 into the tables)
             if (p_uni(!have || !(u1.len == 1 || u1.len >= h.good))) {
                 // the one probe site: u1 at x, or the lazy look-ahead u2 at x + 1
@@ -1469,7 +1567,7 @@ struct Encoder {
             else {
 #if defined(__CUDA_ARCH__)
                 // record path when the sub-block before was mostly literals (or the run is typed EXE), else the table path
-                const bool rec = use_rec && S.T && !wrap && !tmode && !tracing;
+                const bool rec = use_rec && !run_text && S.T && !wrap && !tmode && !tracing;
                 const u32 nl = rec ? parse_lazy_t<true>(a + off, sb) : parse_lazy_t<false>(a + off, sb);
                 use_rec = 3 * nl > sb;
 #else
@@ -1702,6 +1800,7 @@ struct Encoder {
     CSC_HDN void compress_run(u32 a, u32 size, u32 type, u32 first_blk) {   // compress_block, csc_encoder_main.cpp:35-83
         if (!size) return;
         if (want_tables && !tmode && type < DT_NO_LZ) enter_table_mode(a);
+        run_text = type == DT_ENGTXT;
         if (type == DT_NORMAL || type == DT_FAST) {
             emit(OP_INT, DT_NORMAL, 0, 0);
             lz_run(a, size);
@@ -1777,7 +1876,7 @@ struct Encoder {
     CSC_HD void init_common() {
         vld = S.cfg.vld_rge; W = S.cfg.ht_width; K = S.K; good = S.cfg.good_len;
         err = 0; tr_n = 0;
-        tmode = false; want_tables = false; use_rec = false;
+        tmode = false; want_tables = false; use_rec = false; run_text = false;
         wrap = S.n > S.cfg.wnd_size;
         tracing = S.trace != nullptr;
         gs = 5;

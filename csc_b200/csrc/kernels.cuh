@@ -772,6 +772,7 @@ k_mf_tlist(const BlockDesc *__restrict__ blk, const EncStream *__restrict__ stre
     if (!bd.size || (bd.flags & 1)) return;
     const EncStream &S = streams[bd.stream];
     if (!S.T || S.n > S.cfg.wnd_size) return;
+    if ((bd.flags & 2) && S.cfg.lz_mode == 2) return;   // the lazy parser stays on its table path in text runs (enc_engine.cuh: lz_run)
     const u32 K = S.K;
     if (S.cfg.ht_width != K) return;   // (never: the row depth is the table width)
     for (u32 i0 = 0; i0 < bd.size; i0 += 256) {

@@ -95,6 +95,12 @@ struct Ctx {
     CSCB200_Stats stats;
 };
 
+// frees every cached device buffer of a context (the buffers only ever grow one by one; a wave whose mix of sizes
+// differs from the last one's -- another level, another kind of call -- may need the room they hold)
+void ctx_release_device(Ctx &C) {
+    for (DevBuf *b = &C.packdesc; b != &C.swnd + 1; b++) { if (b->p) cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+}
+
 // Device contexts (stream, cached device / pinned buffers) are pooled per GPU and leased for the duration of one
 // API call: concurrent callers (csarc runs up to 8 worker threads, archiver/csarc.cpp:338-352) each get their own
 // context, sequential callers reuse one, and nothing is tied to the life of a thread.
@@ -302,16 +308,18 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs, bool want_adler = false) {
     total += 256;
     C.stats.mf_positions += npos;
     // ---- device memory
+    size_t sortq = 0;
+    const size_t bmbytes = total / 8 + 64;
+    auto alloc_all = [&]() -> int {
     int r = 0;
     r |= C.lz.ensure(total); r |= C.tmp.ensure(total);
     // One scratch area serves three consumers that never overlap in time: the radix sort's key / value ping-pong buffers
     // (match-finder stage), the candidate records T written by k_mf_tlist after the last sort and read by k_encode, and
     // the packed RC / BC sub-streams gathered for the download once k_rc is done.
-    const size_t sortq = align_up((size_t)npos * 4 + 16, 256);
+    sortq = align_up((size_t)npos * 4 + 16, 256);
     const size_t mfs_bytes = std::max<size_t>({4 * sortq, total * sizeof(TRec), (size_t)2 * align_up(rctot + 64, 256)});
     r |= C.mfs.ensure(mfs_bytes);
     r |= C.P6.ensure(total * K * 4); r |= C.L6.ensure(total * K * 2);
-    const size_t bmbytes = total / 8 + 64;
     r |= C.Z2.ensure(bmbytes); r |= C.Z6.ensure(bmbytes); r |= C.D6.ensure(bmbytes); r |= C.D23.ensure(bmbytes);
     r |= C.P3.ensure(total * 4); r |= C.P2.ensure(total * 4); r |= C.L3.ensure(total * 2); r |= C.L2.ensure(total * 2);
     r |= C.B6.ensure(bmbytes); r |= C.E6.ensure(bmbytes);
@@ -331,8 +339,14 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs, bool want_adler = false) {
     r |= C.counters.ensure(64); r |= C.streams.ensure((size_t)ns * sizeof(EncStream));
     r |= C.segsize.ensure((size_t)nseg * 4); r |= C.segblk0.ensure((size_t)nseg * 4);
     r |= C.sbits.ensure((size_t)ns * 4); r |= C.sgoff.ensure((size_t)ns * 8); r |= C.sK.ensure((size_t)ns * 4);
-    if (r) return kErrCuda;
-    if (C.rstiles.ensure((size_t)nrst * sizeof(RsTile)) || C.rsH.ensure((size_t)rsHn * 4 + 64) || C.rsB.ensure((size_t)rsNb * 4 + 64)) return kErrCuda;
+    r |= (C.rstiles.ensure((size_t)nrst * sizeof(RsTile)) || C.rsH.ensure((size_t)rsHn * 4 + 64) || C.rsB.ensure((size_t)rsNb * 4 + 64)) ? 1 : 0;
+    return r;
+    };
+    if (alloc_all()) {   // make room: drop what the context cached for earlier waves and try once more
+        CK(cudaStreamSynchronize(st));
+        ctx_release_device(C);
+        if (alloc_all()) return kErrCuda;
+    }
     RsKey *const keys0 = (RsKey *)C.mfs.as<u8>(), *const keys1 = (RsKey *)(C.mfs.as<u8>() + sortq);
     u32 *const vals0 = (u32 *)(C.mfs.as<u8>() + 2 * sortq), *const vals1 = (u32 *)(C.mfs.as<u8>() + 3 * sortq);
     u32 launches = 1;
@@ -677,12 +691,19 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs, bool want_a
         runoff[s] = runtot; runtot += runcap[s];
     }
     double ms_deframe = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    auto alloc_all = [&]() -> int {
     int r = 0;
     r |= C.dwnd.ensure(wtot + 256); r |= C.dout.ensure(wtot + 256); r |= C.rc.ensure(rctot + 64);
     r |= C.doffs.ensure(offtot * 4 + 16); r |= C.druns.ensure(runtot * sizeof(DecRun));
     r |= C.plit.ensure((size_t)ns * 131072 * 2); r |= C.dmeta.ensure((size_t)ns * 16);
     r |= C.streams.ensure((size_t)ns * sizeof(DecStream)); r |= C.counters.ensure(64); r |= C.doutptr.ensure((size_t)ns * 8);
-    if (r) return kErrCuda;
+    return r;
+    };
+    if (alloc_all()) {   // make room: drop what the context cached for earlier waves and try once more
+        CK(cudaStreamSynchronize(st));
+        ctx_release_device(C);
+        if (alloc_all()) return kErrCuda;
+    }
     std::vector<DecStream> ds(ns);
     std::vector<u8 *> outp(ns);
     std::vector<u32> offs(offtot);
@@ -724,7 +745,7 @@ int decode_wave(Ctx &C, std::vector<DecJob *> &jobs, bool want_runs, bool want_a
     T.mark(st);                                                                   // 1
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, C.dev);
-    u32 grid = std::min<u32>((ns + kDecWarps - 1) / kDecWarps, (u32)nsm * 8);
+    u32 grid = std::min<u32>((ns + kDecWarps - 1) / kDecWarps, (u32)nsm * 16);   // up to 64 resident warps per SM pull streams from the queue
     k_decode<<<grid, kDecWarps * 32, 0, st>>>(C.streams.as<DecStream>(), ns, C.counters.as<u32>() + 1);
     T.mark(st);                                                                   // 2
     CK(cudaMemcpyAsync(C.dout.p, C.dwnd.p, wtot, cudaMemcpyDeviceToDevice, st));

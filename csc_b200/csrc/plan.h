@@ -16,7 +16,7 @@ struct FilterRun { u32 kind; u32 off; u32 size; u32 first_blk; };   // kind: DT_
 
 // One sub-block of the window copy (csc_lz.cpp:63-67): at most 8 KiB, never across a run end or the
 // window end.  These are the units the match-finder kernels hash / extend over.
-struct SubBlock { u32 x; u32 size; u32 flags; };   // x relative to the stream; flags bit 0: left out of the 2-/3-byte chains
+struct SubBlock { u32 x; u32 size; u32 flags; };   // x relative to the stream; flags bit 0: left out of the 2-/3-byte chains, bit 1: text run
 
 // Type of one block BEFORE the duplicate-block test (csc_encoder_main.cpp:98-121): analyzer type, DT_SKIP
 // inheritance, disabled filters, delta-bpb veto.  `last` is the final type of the previous block of the
@@ -74,7 +74,7 @@ CSC_HD u32 plan_segment(const u32 *binfo, const u32 *bbpb, const u32 *seg_tail_d
                     runs[nruns].kind = last; runs[nruns].off = seg_x + run_begin; runs[nruns].size = run_size;
                     runs[nruns].first_blk = run_blk; nruns++;
                 }
-                const u32 fl = last >= DT_NO_LZ ? 1u : 0u;
+                const u32 fl = (last >= DT_NO_LZ ? 1u : 0u) | (last == DT_ENGTXT ? 2u : 0u);
                 for (u32 off = 0; off < run_size;) {   // LZ::EncodeNormal's copy loop
                     const u32 x = seg_x + run_begin + off;
                     u32 sb = run_size - off < kBlock ? run_size - off : kBlock;
