@@ -769,6 +769,32 @@ struct Encoder {
         if (G == 1) return __shfl_sync(FULL, cnt, 0);
         return __shfl_sync(FULL, cnt, 0) | (__shfl_sync(FULL, cnt, 8) << 8);
     }
+    // the walk behind a row whose first W entries are not all alive (csc_mf.cpp:453-485 keeps going down the bucket)
+    static __device__ __noinline__ u32 fm_walk(const MfCtx &h, u32 x, u32 limit, u32 dm, u32 lu, u32 found, u32 src, u32 cnt) {
+        const u32 FULL = 0xFFFFFFFFu;
+        const u8 *cur = h.lz + x;
+        u32 dist = dm, minlen = lu;
+#pragma unroll
+        for (int sft = 16; sft; sft >>= 1) { dist = max(dist, __shfl_xor_sync(FULL, dist, sft)); minlen = max(minlen, __shfl_xor_sync(FULL, minlen, sft)); }
+        minlen = max(minlen, 1u);
+        u32 kk = 0;
+        const u32 c1 = cur[1];
+        while (found < h.W) {
+            u32 e = h.P6[(size_t)src * h.K + kk];
+            if (e == kNone) break;
+            if (++kk == h.K) { src = e; kk = 0; }
+            if (dead6(h, e)) continue;
+            found++;
+            u32 dd = x - e;
+            if (dd <= dist) continue;
+            dist = dd;
+            if (dist >= h.vld) continue;
+            const u32 cl = climit_of(h, x, dd, limit);
+            if (minlen >= cl) continue;
+            if (probe(h, cur, dd, cl, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
+        }
+        return cnt;
+    }
     // find_match on the device.  REC: the caller is on the record path -- the precomputed record answers when it is
     // valid and the general statement is an out-of-line call (cold there); !REC: the general statement inline and no
     // record code at all (the table path of the lazy parser, whose hot loop has to stay small).
@@ -782,12 +808,15 @@ struct Encoder {
             }
             return fm_tables_out(h, x, limit, r0, r1, r2, r3);
         }
-        return fm_tables(h, x, limit, r0, r1, r2, r3);
+        if (h.tmode) return fm_tables_out(h, x, limit, r0, r1, r2, r3);   // (after a duplicate-block flip: rare)
+        return fm_tables<false>(h, x, limit, r0, r1, r2, r3);
     }
     static __device__ __noinline__ u32 fm_tables_out(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
-        return fm_tables(h, x, limit, r0, r1, r2, r3);
+        return fm_tables<true>(h, x, limit, r0, r1, r2, r3);
     }
-    // the general statement: candidate rows + liveness
+    // the general statement: candidate rows + liveness.  GEN: with the table-mode branches; !GEN: chain mode only (the
+    // instance inlined into the lazy parser's table path, kept as small as it gets: its loop has to stay in the instruction cache)
+    template <bool GEN>
     static __device__ __forceinline__ u32 fm_tables(const MfCtx &h, u32 x, u32 limit, u32 r0, u32 r1, u32 r2, u32 r3) {
         const u32 lane = CSC_LANE, FULL = 0xFFFFFFFFu;
         const u8 *cur = h.lz + x;
@@ -801,7 +830,7 @@ struct Encoder {
             need_cmp = cand;
         } else if (is_tab) {
             const bool three = lane == 5;
-            if (!h.tmode) {
+            if (!GEN || !h.tmode) {
                 const u32 *P = three ? h.P3 : h.P2;
                 u32 e = P[x];
                 L = three ? h.L3[x] : h.L2[x];
@@ -871,29 +900,8 @@ struct Encoder {
         __syncwarp();
         // a dead entry inside a full row leaves the bucket short: keep walking the chain behind the row (rare)
         const u32 full = (1u << h.K) - 1;
-        if (h.W && !stopm && validrow == full && (u32)__popc(alivem) < h.W) {
-            u32 dist = dm, minlen = lu;
-#pragma unroll
-            for (int sft = 16; sft; sft >>= 1) { dist = max(dist, __shfl_xor_sync(FULL, dist, sft)); minlen = max(minlen, __shfl_xor_sync(FULL, minlen, sft)); }
-            minlen = max(minlen, 1u);
-            u32 found = (u32)__popc(alivem);
-            u32 src = __shfl_sync(FULL, x - d, 8 + h.K - 1), kk = 0;
-            const u32 c1 = cur[1];
-            while (found < h.W) {
-                u32 e = h.P6[(size_t)src * h.K + kk];
-                if (e == kNone) break;
-                if (++kk == h.K) { src = e; kk = 0; }
-                if (dead6(h, e)) continue;
-                found++;
-                u32 dd = x - e;
-                if (dd <= dist) continue;
-                dist = dd;
-                if (dist >= h.vld) continue;
-                const u32 cl = climit_of(h, x, dd, limit);
-                if (minlen >= cl) continue;
-                if (probe(h, cur, dd, cl, (cur - dd)[1], c1, 4 + dd, true, minlen, cnt)) break;
-            }
-        }
+        if (h.W && !stopm && validrow == full && (u32)__popc(alivem) < h.W)
+            cnt = fm_walk(h, x, limit, dm, lu, (u32)__popc(alivem), __shfl_sync(FULL, x - d, 8 + h.K - 1), cnt);
         return cnt;
     }
 #endif
@@ -1120,8 +1128,7 @@ struct Encoder {
     CSC_HDN u32 newest_alive6(u32 x, u32 bound) const { const MfCtx h = mfctx(); return newest_alive6(h, x, bound); }
 
     // SlidePos (csc_mf.cpp:134-206): positions s+1 .. s+len-1 are passed over by a match.
-    template <bool REC = true>
-    CSC_HDF static void slide_core(const MfCtx &h, u32 s, u32 len, u32 sb_end) {
+    CSC_HDN static void slide_general(const MfCtx &h, u32 s, u32 len, u32 sb_end) {
         if (p_uni(len <= 1)) return;
         u32 i0 = 1;
         while (p_uni(i0 + 128 < len)) i0 += 4;
@@ -1145,19 +1152,6 @@ struct Encoder {
         if (p_uni(h.W != 0)) {
             if (p_uni(i0 > 1)) { sum_mark_range(h, s + 1, s + i0); bits_set_range(h.D6, s + 1, s + i0); }   // never inserted (:145)
             u32 first = s + i0;
-            if (REC && (CSC_OPT_TREC && h.T) && !h.tmode) {
-                // the rules below only act on positions whose HASH6 is 0 or repeats the previous position's: one look at
-                // the precomputed bitmap of those (k_mf_tlist) settles the common case
-                bool any = false;
-                const u32 w0 = first >> 5, w1 = (s + len - 1) >> 5;
-                for (u32 w = w0 + CSC_LANE; w <= w1; w += CSC_NLANES) {
-                    u32 m = h.B6[w];
-                    if (w == w0) m &= 0xFFFFFFFFu << (first & 31);
-                    if (w == w1) m &= 0xFFFFFFFFu >> (31 - ((s + len - 1) & 31));
-                    any = any || m != 0;
-                }
-                if (!w_any(any)) return;
-            }
             if (p_uni(i0 < len && bit_get_ro(h.Z6, first))) {    // h6 == lasth6 (== 0): slot 0 overwritten (:147-156)
                 u32 e = newest_alive6(h, first, first);
                 if (e != kNone) kill6(h, e);
@@ -1169,6 +1163,42 @@ struct Encoder {
             }
             w_sync();
         }
+    }
+
+    // the common case on the device (chain mode, no skip zone: matches of at most 129 bytes) only has the two 6-byte rules
+    // to look at; everything else is the out-of-line statement above
+    template <bool REC = true>
+    CSC_HDF static void slide_core(const MfCtx &h, u32 s, u32 len, u32 sb_end) {
+        if (p_uni(len <= 1)) return;
+#if defined(__CUDA_ARCH__)
+        if (h.tmode || len > 129 || !h.W) { slide_general(h, s, len, sb_end); return; }
+        const u32 first = s + 1;
+        if (REC && (CSC_OPT_TREC && h.T)) {
+            // the rules only act on positions whose HASH6 is 0 or repeats the previous position's: one look at the
+            // precomputed bitmap of those (k_mf_tlist) settles the common case
+            bool any = false;
+            const u32 w0 = first >> 5, w1 = (s + len - 1) >> 5;
+            for (u32 w = w0 + CSC_LANE; w <= w1; w += CSC_NLANES) {
+                u32 m = h.B6[w];
+                if (w == w0) m &= 0xFFFFFFFFu << (first & 31);
+                if (w == w1) m &= 0xFFFFFFFFu >> (31 - ((s + len - 1) & 31));
+                any = any || m != 0;
+            }
+            if (!w_any(any)) return;
+        }
+        if (p_uni(bit_get_ro(h.Z6, first))) {    // h6 == lasth6 (== 0): slot 0 overwritten (:147-156)
+            u32 e = newest_alive6(h, first, first);
+            if (e != kNone) kill6(h, e);
+        }
+#pragma unroll 1
+        for (u32 i = 2 + CSC_LANE; i < len; i += CSC_NLANES) {
+            u32 q = s + i;
+            if (h.P6[(size_t)q * h.K] == q - 1) kill6(h, q - 1);   // same hash as the previous slid position
+        }
+        w_sync();
+#else
+        slide_general(h, s, len, sb_end);
+#endif
     }
 
     // ---------------------------------------------------- packets
