@@ -17,6 +17,11 @@ namespace {
 struct In { ISeqInStream is; const uint8_t *p; size_t n, at; };
 struct Out { ISeqOutStream os; uint8_t *p; size_t cap, at; bool over; };
 int rd(void *o, void *b, size_t *sz) { In *m = (In *)o; size_t k = std::min(*sz, m->n - m->at); memcpy(b, m->p + m->at, k); m->at += k; *sz = k; return 0; }
+// zero-filling allocator: the one byte per flush segment that Coder::Flush skips instead of storing is then the
+// deterministic 0 the product emulates, not whatever malloc left there
+void *zalloc(void *, size_t size) { return calloc(1, size ? size : 1); }
+void zfree(void *, void *p) { free(p); }
+ISzAlloc g_zero = {zalloc, zfree};
 size_t wr(void *o, const void *b, size_t sz) { Out *m = (Out *)o; if (m->at + sz > m->cap) { m->over = true; return 0; } memcpy(m->p + m->at, b, sz); m->at += sz; return sz; }
 }
 
@@ -32,7 +37,7 @@ int CSCB200_EncodeChunksAdler(int n, const uint8_t *const *in, const size_t *in_
         In mi; mi.is.Read = rd; mi.p = in[i]; mi.n = in_size[i]; mi.at = 0;
         Out mo; mo.os.Write = wr; mo.p = out[i]; mo.cap = out_cap[i]; mo.at = 0; mo.over = false;
         if (with_props) { if (out_cap[i] < CSC_PROP_SIZE) return -90; CSCEnc_WriteProperties(&p, out[i], 0); mo.at = CSC_PROP_SIZE; }
-        CSCEncHandle h = CSCEnc_Create(&p, (ISeqOutStream *)&mo, NULL);
+        CSCEncHandle h = CSCEnc_Create(&p, (ISeqOutStream *)&mo, &g_zero);
         if (!h) return -1;
         int r = CSCEnc_Encode(h, (ISeqInStream *)&mi, NULL);
         if (r >= 0) r = CSCEnc_Encode_Flush(h);
@@ -51,7 +56,7 @@ int CSCB200_DecodeChunksAdler(int n, const uint8_t *const *in, const size_t *in_
         CSCDec_ReadProperties(&p, (uint8_t *)in[i]);
         In mi; mi.is.Read = rd; mi.p = in[i]; mi.n = in_size[i]; mi.at = CSC_PROP_SIZE;
         Out mo; mo.os.Write = wr; mo.p = out[i]; mo.cap = out_cap[i]; mo.at = 0; mo.over = false;
-        CSCDecHandle h = CSCDec_Create(&p, (ISeqInStream *)&mi, NULL);
+        CSCDecHandle h = CSCDec_Create(&p, (ISeqInStream *)&mi, &g_zero);
         if (!h) return -1;
         int r = CSCDec_Decode(h, (ISeqOutStream *)&mo, NULL);
         CSCDec_Destroy(h);

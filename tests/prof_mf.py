@@ -1,4 +1,6 @@
-"""ncu driver for the match-finder / analyzer kernels: one encode pass over N MiB (default 256) of text."""
+"""ncu driver for the parallel kernels: one encode pass over N MiB (default 256) of text (match-finder / analyzer / sort kernels),
+a second one over 64 MiB of the mixed corpus at -m3 (k_mf_tlist, filters on machine code), then Adler-32 and a decode.
+usage: python tests/prof_mf.py [total MiB] [level]"""
 import os
 import sys
 
@@ -18,3 +20,9 @@ d = torch.from_numpy(data).cuda()
 n = total // chunk
 out = api.encode_chunks_device([d.data_ptr() + i * chunk for i in range(n)], [chunk] * n, 64 << 20, level)
 print("ratio", sum(out) / total, {k: round(v, 2) for k, v in csc_b200.get_stats().items() if k.startswith("ms_") and v})
+
+mixed = synth.tiled("mixed", 64 << 20, tile=32 << 20)
+chunks = api.split_chunks(mixed, chunk)
+outs, sums = api.encode_chunks_adler(chunks, 64 << 20, 3)
+back, sums2 = api.decode_chunks_adler(outs, [c.size for c in chunks])
+print("mixed -m3 ratio", sum(o.size for o in outs) / mixed.size, "adler ok", sums == sums2, "roundtrip", all((b == c).all() for b, c in zip(back, chunks)))

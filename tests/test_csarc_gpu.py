@@ -83,7 +83,14 @@ def test_csarc_gpu_on_the_gpu(gpu_lib, ref, tmp_path):
     _run(tmp_path, tool, "a", "-m1", "-c256k", "-f", "gpu.csa", "src")
     _run(tmp_path, shim, "a", "-m1", "-c256k", "-f", "cpu.csa", "src")
     a, b = np.fromfile(tmp_path / "gpu.csa", dtype=np.uint8), np.fromfile(tmp_path / "cpu.csa", dtype=np.uint8)
-    assert a.size == b.size and bool((a == b).all()), "archive written on the GPU differs from the one written with libcsc"
+    if not (a.size == b.size and bool((a == b).all())):
+        n = min(a.size, b.size)
+        diff = np.flatnonzero(a[:n] != b[:n])
+        lg = _run(tmp_path, stock, "l", "-v", "gpu.csa").stdout.splitlines()
+        lc = _run(tmp_path, stock, "l", "-v", "cpu.csa").stdout.splitlines()
+        bad = [(x, y) for x, y in zip(lg, lc) if x != y][:6]
+        raise AssertionError(f"archive written on the GPU differs from the one written with libcsc: sizes {a.size} / {b.size}, "
+                             f"{diff.size} differing bytes, first at {diff[:8].tolist()}, listing differences {bad}")
     _run(tmp_path, stock, "t", "gpu.csa")
     _run(tmp_path, tool, "t", "gpu.csa")
     _run(tmp_path, tool, "x", "-oo1", "gpu.csa")

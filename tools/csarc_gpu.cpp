@@ -113,6 +113,13 @@ struct MemOut { ISeqOutStream os; vector<char> *v; };
 int mem_read(void *o, void *buf, size_t *size) { MemIn *m = (MemIn *)o; size_t k = std::min(*size, m->n - m->at); memcpy(buf, m->p + m->at, k); m->at += k; *size = k; return 0; }
 size_t mem_write(void *o, const void *buf, size_t size) { MemOut *m = (MemOut *)o; m->v->insert(m->v->end(), (const char *)buf, (const char *)buf + size); return size; }
 
+// The index stream is written through the handle API.  A zero-filling allocator makes the one byte per flush segment that
+// libcsc's Coder::Flush skips instead of storing (it keeps whatever the buffer held) deterministic on the reference library;
+// the GPU library always behaves like that.
+void *zero_alloc(void *, size_t size) { return calloc(1, size ? size : 1); }
+void zero_free(void *, void *p) { free(p); }
+ISzAlloc g_zero_alloc = {zero_alloc, zero_free};
+
 int64_t decimal_time(time_t t) {   // csa_common.cpp: YYYYMMDDHHMMSS (UTC)
     struct tm *g = gmtime(&t);
     if (!g) return 0;
@@ -258,7 +265,7 @@ int cmd_add(const string &arc, const vector<string> &paths, int level, uint64_t 
         uint8_t props[CSC_PROP_SIZE];
         CSCEnc_WriteProperties(&p, props, 0);
         cidx.insert(cidx.end(), (char *)props, (char *)props + CSC_PROP_SIZE);
-        CSCEncHandle h = CSCEnc_Create(&p, (ISeqOutStream *)&mo, NULL);
+        CSCEncHandle h = CSCEnc_Create(&p, (ISeqOutStream *)&mo, &g_zero_alloc);
         if (!h || CSCEnc_Encode(h, (ISeqInStream *)&mi, NULL) < 0 || CSCEnc_Encode_Flush(h) < 0) { fprintf(stderr, "index compression failed\n"); fclose(out); return 1; }
         CSCEnc_Destroy(h);
     }
