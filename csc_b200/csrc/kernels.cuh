@@ -10,6 +10,7 @@
 //                  sub-block end                               (csc_mf.cpp:470, 8 B words)
 //   k_mf_tlist     thread per position: table candidates of find_match under the all-alive assumption (TRec)
 //   k_adler32_*    Adler-32 of many buffers (csarc's checksum): CTA per 64 KiB tile + in-order combine
+//   k_frame        one warp per stream: MemIO framing of the finished sub-streams (frame.cuh)
 //   k_encode       one stream per warp: enc_engine.cuh (parser + adaptive model -> decision lists)
 //   k_rc           one stream per warp, warp-uniform: rc_engine.cuh (range-coder recurrence over the decision lists)
 //   k_decode       one stream per warp: dec_engine.cuh
@@ -25,6 +26,7 @@
 #include "plan.h"
 #include "enc_engine.cuh"
 #include "rc_engine.cuh"
+#include "frame.cuh"
 #include "dec_engine.cuh"
 #include "radix_sort.cuh"
 
@@ -880,6 +882,19 @@ __global__ void k_adler32_combine(const AdlerTile *__restrict__ tiles, const u32
         a = (a + partA[t]) % kAdlerBase;
     }
     out[i] = (u32)a | ((u32)b << 16);
+}
+
+// ------------------------------------------------------------------ framing (csc_memio.cpp:83-108) on the device
+// frame.cuh: the finished libcsc stream of every chunk, so that the download is final bytes and the host only copies.
+__global__ void k_frame_sizes(const FrameStream *__restrict__ fs, u32 ns, u32 *__restrict__ sizes) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ns) sizes[i] = frame_size(fs[i]);
+}
+__global__ void __launch_bounds__(128)
+k_frame(const FrameStream *__restrict__ fs, u32 ns, const u64 *__restrict__ offs, u8 *__restrict__ out) {
+    const u32 s = blockIdx.x * 4 + (threadIdx.x >> 5);   // one warp per stream
+    if (s >= ns) return;
+    frame_write(fs[s], out + offs[s]);
 }
 
 // ------------------------------------------------------------------ fill helper

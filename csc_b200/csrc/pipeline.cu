@@ -89,8 +89,8 @@ struct Ctx {
     DevBuf packdesc, lz, tmp, mfs, P6, L6, Z2, Z6, D6, ht, plit, ap, rc, bc, ev, segout, status, blkdesc,
         segdesc, binfo, bbpb, taildlt, dictok, planscratch, runs, counters, streams, segsize, segblk0, sbits, sgoff, sK,
         dwnd, dout, doffs, druns, dmeta, doutptr, P3, L3, P2, L2, D23, nolz, rstiles, rsH, rsB, trace,
-        flip, replan, subdesc, subscratch, rcev, bcev, dec, B6, E6, adl, swnd;
-    PinBuf h_segout, h_status, h_rcev, h_bcev, h_rc, h_bc, h_meta, h_adler, h_replan;
+        flip, replan, subdesc, subscratch, rcev, bcev, dec, B6, E6, adl, fdesc, fsz, foff, swnd;
+    PinBuf h_segout, h_status, h_rcev, h_bcev, h_rc, h_bc, h_meta, h_adler, h_fsz, h_replan;
     Timer tm;
     CSCB200_Stats stats;
 };
@@ -190,7 +190,15 @@ struct EncJob {
     const u8 *rc, *bc;
     const u32 *rc_ev, *bc_ev;   // block-completion time stamps (SegOut::rev_off / bev_off index these)
     u32 adler = 1;              // Adler-32 of the raw input (when the wave is asked for it)
+    // framing on the device (batched calls): the finished stream in pinned staging memory
+    bool frame_dev = false; bool with_props = false;
+    const u8 *framed = nullptr; size_t framed_size = 0;
 };
+
+// framing of the batched calls' streams on the device (frame.cuh); 0: host replay (host_common.h: Framer), A/B only
+#ifndef CSC_FRAME_ON_DEVICE
+#define CSC_FRAME_ON_DEVICE 1
+#endif
 
 // ----------------------------------------------------------------------------- Adler-32
 // adler32() (archiver/csa_adler32.cpp:63-128) of n byte ranges of one device buffer, results into pinned host memory
@@ -542,6 +550,65 @@ int encode_wave(Ctx &C, std::vector<EncJob *> &jobs, bool want_adler = false) {
     T.mark(st);                                                                   // 10
     launches += 2;
     CK(cudaGetLastError());
+    bool frame_dev = true;
+    for (u32 s = 0; s < ns; s++) frame_dev = frame_dev && jobs[s]->frame_dev && !jobs[s]->no_payload;
+    if (frame_dev) {
+        // ---- framing on the device (frame.cuh): sizes -> dense offsets -> the finished streams in ONE download
+        std::vector<FrameStream> fs(ns);
+        for (u32 s = 0; s < ns; s++) {
+            FrameStream &F = fs[s];
+            memset(&F, 0, sizeof(F));
+            F.rc = C.rc.as<u8>() + rcoff[s]; F.bc = C.bc.as<u8>() + bcoff[s];
+            F.rc_ev = C.rcev.as<u32>() + evoff[s]; F.bc_ev = C.bcev.as<u32>() + evoff[s];
+            F.so = C.segout.as<SegOut>() + seg0[s]; F.nseg = (u32)jobs[s]->segs.size();
+            F.bsize = jobs[s]->props.csc_blocksize; F.with_props = jobs[s]->with_props ? 1 : 0;
+            write_props(&jobs[s]->props, F.props);
+            F.status = C.status.as<i32>() + s;
+        }
+        if (C.fdesc.ensure((size_t)ns * sizeof(FrameStream)) || C.fsz.ensure((size_t)ns * 4 + 16) || C.foff.ensure((size_t)ns * 8 + 16) ||
+            C.h_fsz.ensure((size_t)ns * 4 + 16) || C.h_status.ensure((size_t)ns * 4) || C.h_replan.ensure((size_t)ns * 8))
+            return kErrCuda;
+        CK(cudaMemcpyAsync(C.fdesc.p, fs.data(), (size_t)ns * sizeof(FrameStream), cudaMemcpyHostToDevice, st));
+        k_frame_sizes<<<(ns + 127) / 128, 128, 0, st>>>(C.fdesc.as<FrameStream>(), ns, C.fsz.as<u32>());
+        CK(cudaMemcpyAsync(C.h_fsz.p, C.fsz.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(C.h_status.p, C.status.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(C.h_replan.p, C.replan.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const u32 *hsz = C.h_fsz.as<u32>();
+        const i32 *hst = C.h_status.as<i32>();
+        if (h_adl) for (u32 s = 0; s < ns; s++) jobs[s]->adler = h_adl[s];
+        std::vector<u64> foff(ns);
+        u64 ftot = 0;
+        for (u32 s = 0; s < ns; s++) { foff[s] = ftot; ftot += align_up(hsz[s], 16); }
+        if (ftot + 64 > C.mfs.cap || C.h_rc.ensure(ftot + 64)) return kErrCuda;   // (the scratch area holds 2 x the sub-stream capacity)
+        CK(cudaMemcpyAsync(C.foff.p, foff.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, st));
+        k_frame<<<(ns + 3) / 4, 128, 0, st>>>(C.fdesc.as<FrameStream>(), ns, C.foff.as<u64>(), C.mfs.as<u8>());
+        if (ftot) CK(cudaMemcpyAsync(C.h_rc.p, C.mfs.p, ftot, cudaMemcpyDeviceToHost, st));
+        launches += 2;
+        T.mark(st);                                                               // 11
+        CK(cudaStreamSynchronize(st));
+        int ret = 0;
+        for (u32 s = 0; s < ns; s++) {
+            EncJob &J = *jobs[s];
+            J.status = hst[s];
+            if (J.status == kErrReplan) {
+                const u32 *rp = C.h_replan.as<u32>() + 2 * (size_t)s;
+                if (J.flip.empty()) J.flip.assign((s + 1 < ns ? sblk0[s + 1] : nblk) - sblk0[s], 0);
+                if (rp[0] >= sblk0[s] && rp[0] - sblk0[s] < J.flip.size()) J.flip[rp[0] - sblk0[s]] = (u8)rp[1];
+                else { J.status = kErrUnsupported; ret = kErrUnsupported; }
+                C.stats.replans += 1;
+                continue;
+            }
+            if (J.status < 0) { ret = J.status; continue; }
+            J.framed = C.h_rc.as<u8>() + foff[s]; J.framed_size = hsz[s];
+        }
+        CSCB200_Stats &S = C.stats;
+        S.ms_h2d += T.ms(0, 1); S.ms_analyze += T.ms(1, 2); S.ms_filters += T.ms(2, 3); S.ms_mf_hash += T.ms(3, 4);
+        S.ms_mf_sort += T.ms(4, 5); S.ms_mf_rows += T.ms(5, 6); S.ms_mf_extend += T.ms(6, 7); S.ms_mf_chains += T.ms(7, 8);
+        S.ms_encode += T.ms(8, 9); S.ms_rc += T.ms(9, 10); S.ms_d2h += T.ms(10, 11); S.ms_total_gpu += T.ms(0, 11);
+        S.kernel_launches += launches; S.streams += ns; S.waves += 1;
+        return ret;
+    }
     // ---- results
     if (C.h_segout.ensure((size_t)nseg * sizeof(SegOut)) || C.h_status.ensure((size_t)ns * 4) || C.h_rcev.ensure(evtot * 4 + 16) ||
         C.h_bcev.ensure(evtot * 4 + 16) ||
@@ -889,6 +956,7 @@ int encode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_s
         if (in_size[i] >= 0xF0000000ull) return kErrUnsupported;
         J.in = in[i]; J.n = (u32)in_size[i]; J.status = 0; J.rc = J.bc = nullptr; J.rc_ev = J.bc_ev = nullptr;
         J.in_dev = device; J.no_payload = device;
+        J.frame_dev = !device && CSC_FRAME_ON_DEVICE; J.with_props = with_props != 0;
         uint32_t d = (uint64_t)dict_size > in_size[i] ? (uint32_t)in_size[i] : dict_size;   // csa_worker.cpp:35
         props_init(&J.props, d, level);
         J.props.DLTFilter = flt_mask & 1; J.props.TXTFilter = (flt_mask >> 1) & 1; J.props.EXEFilter = (flt_mask >> 2) & 1;
@@ -930,6 +998,13 @@ int encode_chunks_on(Ctx &C, int n, const uint8_t *const *in, const size_t *in_s
                 size_t i = J - jobs.data();
                 if (J->status == kErrReplan) continue;   // goes round again below
                 if (device) { out_size[i] = framed_size(*J, with_props != 0); bytes_out += out_size[i]; continue; }
+                if (J->framed) {   // framed on the device: the stream is final, copy it out
+                    out_size[i] = J->framed_size;
+                    if (J->framed_size > out_cap[i]) { overflow = 1; continue; }
+                    memcpy(out[i], J->framed, J->framed_size);
+                    bytes_out += J->framed_size;
+                    continue;
+                }
                 MemSink sink{out[i], out_cap[i], 0, false};
                 if (with_props) { u8 hdr[CSC_PROP_SIZE]; write_props(&J->props, hdr); sink(hdr, CSC_PROP_SIZE); }
                 Framer fr(J->props.csc_blocksize);

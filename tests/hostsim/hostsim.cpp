@@ -18,6 +18,7 @@
 #include "../../csc_b200/csrc/enc_engine.cuh"
 #include "../../csc_b200/csrc/rc_engine.cuh"
 #include "../../csc_b200/csrc/dec_engine.cuh"
+#include "../../csc_b200/csrc/frame.cuh"
 
 using namespace cscb;
 
@@ -129,6 +130,7 @@ void build_chain23_cpu(const u8 *lz, u32 n, const std::vector<SubBlock> &subs, u
 
 }  // namespace
 
+static std::vector<u8> g_frame_dev;   // the stream as frame.cuh writes it (checked against Framer in hs_encode)
 static int g_replans = 0;   // how often hs_encode had to plan again (tests look at it)
 struct StageDump { u32 *binfo, *bbpb; u8 *lz; u32 *P6; u16 *L6; u32 *Z2, *Z6; u8 *dict_ok; u32 *tail_dlt; bool on; };
 static StageDump g_dump = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false};
@@ -283,6 +285,16 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         if (status < 0) return status;
         break;
         }
+        // the device-side framing statement (frame.cuh, k_frame) on the same sub-streams: must give the bytes Framer gives
+        FrameStream FS;
+        memset(&FS, 0, sizeof(FS));
+        FS.rc = rc.data(); FS.bc = bc.data(); FS.rc_ev = rc_ev.data(); FS.bc_ev = bc_ev.data(); FS.so = so.data();
+        FS.nseg = (u32)seg.size(); FS.bsize = p.csc_blocksize; FS.with_props = with_props ? 1 : 0;
+        const i32 frame_status = 0;
+        FS.status = &frame_status;
+        write_props(&p, FS.props);
+        g_frame_dev.assign(frame_size(FS), 0);
+        frame_write(FS, g_frame_dev.data());
         std::vector<u8> ev;
         for (u32 s = 0; s < seg.size(); s++) {
             merge_events(rc_ev.data() + so[s].rev_off, so[s].rev_len, bc_ev.data() + so[s].bev_off, so[s].bev_len, ev);
@@ -290,6 +302,7 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
         }
     }
     fr.eof(sink);
+    if (n && (g_frame_dev.size() != res.size() || memcmp(g_frame_dev.data(), res.data(), res.size()))) return -77;   // frame.cuh disagrees with Framer
     *out_n = res.size();
     if (res.size() > cap) return kErrOverflow;
     memcpy(out, res.data(), res.size());
