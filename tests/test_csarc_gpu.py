@@ -76,6 +76,24 @@ def test_archive_format_against_stock_csarc(ref, tmp_path):
     assert r.returncode != 0
 
 
+def test_large_file_is_cut_into_at_most_127_fragments(ref, tmp_path):
+    """the packed index keeps a file's fragment count in one signed byte (csa_indexpack.cpp:86,107): a file larger than
+    127 chunks gets larger pieces instead of more of them"""
+    tool, stock = _tools(ref, "csarc_gpu_refshim", "csarc_ref")
+    d = synth.mixed(20 << 20, 31)
+    os.makedirs(tmp_path / "src")
+    d.tofile(tmp_path / "src" / "big.bin")
+    out = _run(tmp_path, tool, "a", "-m1", "-c64k", "-f", "big.csa", "src").stdout
+    assert "127 tasks" in out, out
+    listing = _run(tmp_path, stock, "l", "-v", "big.csa").stdout
+    assert "Fragment 126" in listing and "Fragment 127" not in listing
+    _run(tmp_path, stock, "t", "big.csa")
+    os.mkdir(tmp_path / "o")
+    _run(tmp_path, stock, "x", "-o", "o/", "big.csa")
+    got = np.fromfile(tmp_path / "o" / "src" / "big.bin", dtype=np.uint8)
+    assert got.size == d.size and bool((got == d).all())
+
+
 @pytest.mark.gpu
 def test_csarc_gpu_on_the_gpu(gpu_lib, ref, tmp_path):
     tool, shim, stock = _tools(ref, "csarc_gpu", "csarc_gpu_refshim", "csarc_ref")
