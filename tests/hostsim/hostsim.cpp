@@ -311,6 +311,53 @@ int hs_encode(const uint8_t *in, size_t n_, uint32_t dict_size, int level, uint3
 
 int hs_replans(void) { int r = g_replans; g_replans = 0; return r; }
 
+// frame.cuh against Framer on synthetic sub-streams: `nseg` segments with random RC / BC lengths around multiples of the
+// block size (so that segments with and without full blocks, long and short remainders follow each other: every
+// branch of the stale-byte search), random interleaving of the block completions.  Returns 0 when the bytes agree.
+int hs_frame_selftest(uint32_t seed, uint32_t nseg, uint32_t bsize) {
+    u32 x = seed * 2654435761u + 12345u;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; };
+    std::vector<u8> rc, bc;
+    std::vector<u32> rc_ev, bc_ev;
+    std::vector<SegOut> so(nseg);
+    for (u32 s = 0; s < nseg; s++) {
+        SegOut &o = so[s];
+        memset(&o, 0, sizeof(o));
+        const u32 nr = rnd() % 4, nb = rnd() % 3;                    // full blocks
+        const u32 rrem = 1 + (rnd() % 3 == 0 ? rnd() % 8 : rnd() % bsize);   // remainder incl. the skipped byte (1 .. bsize)
+        const u32 brem = 2 + rnd() % (bsize - 1);
+        o.rc_off = (u32)rc.size(); o.rc_len = nr * bsize + rrem;
+        o.bc_off = (u32)bc.size(); o.bc_len = nb * bsize + brem;
+        for (u32 i = 0; i < o.rc_len; i++) rc.push_back((u8)rnd());
+        for (u32 i = 0; i < o.bc_len; i++) bc.push_back((u8)rnd());
+        o.rev_off = (u32)rc_ev.size(); o.rev_len = nr;
+        o.bev_off = (u32)bc_ev.size(); o.bev_len = nb;
+        u32 t = 0;
+        for (u32 i = 0; i < nr; i++) { t += 1 + rnd() % 50; rc_ev.push_back(2 * t + 1); }   // RC stamps odd, increasing
+        t = 0;
+        for (u32 i = 0; i < nb; i++) { t += 1 + rnd() % 50; bc_ev.push_back(2 * t); }       // BC stamps even, increasing
+    }
+    const i32 status = 0;
+    FrameStream FS;
+    memset(&FS, 0, sizeof(FS));
+    FS.rc = rc.data(); FS.bc = bc.data(); FS.rc_ev = rc_ev.data(); FS.bc_ev = bc_ev.data(); FS.so = so.data();
+    FS.nseg = nseg; FS.bsize = bsize; FS.with_props = 1; FS.status = &status;
+    for (int i = 0; i < 10; i++) FS.props[i] = (u8)(i + 1);
+    std::vector<u8> dev(frame_size(FS), 0xEE);
+    frame_write(FS, dev.data());
+    std::vector<u8> res(FS.props, FS.props + 10);
+    Sink sink{&res};
+    Framer fr(bsize);
+    std::vector<u8> ev;
+    for (u32 s = 0; s < nseg; s++) {
+        merge_events(rc_ev.data() + so[s].rev_off, so[s].rev_len, bc_ev.data() + so[s].bev_off, so[s].bev_len, ev);
+        fr.segment(sink, rc.data() + so[s].rc_off, so[s].rc_len, bc.data() + so[s].bc_off, so[s].bc_len, ev.data(), (u32)ev.size());
+    }
+    fr.eof(sink);
+    if (dev.size() != res.size()) return 1;
+    return memcmp(dev.data(), res.data(), res.size()) ? 2 : 0;
+}
+
 // Whole stream (with 10-byte props header) through the host-simulated decoder engine.
 int hs_decode(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_n) {
     if (n < 10) return -1;

@@ -341,3 +341,16 @@ def test_window_wrap_replans_on_duplicate_block_flips(ref, hs):
     hs.lib().hs_replans()
     assert same(hs.encode(d, 20000, 2), ref.encode(d, 20000, 2))
     assert hs.lib().hs_replans() >= 1
+
+
+def test_device_framing_statement_equals_framer(hs):
+    """frame.cuh (k_frame on the device) against host_common.h: Framer on synthetic sub-streams: segments with and without
+    full RC blocks, remainders longer and shorter than the ones before (every branch of the stale-byte search),
+    random interleaving of RC / BC block completions (H4), small and default block sizes"""
+    l = hs.lib()
+    l.hs_frame_selftest.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+    for seed in range(300):
+        for nseg, bsize in ((1, 64), (2, 64), (5, 64), (9, 256), (3, 65536)):
+            if bsize == 65536 and seed >= 12:
+                continue
+            assert l.hs_frame_selftest(seed, nseg, bsize) == 0, (seed, nseg, bsize)
