@@ -29,7 +29,7 @@
 #ifndef CSC_TMA_STAGE
 #define CSC_TMA_STAGE 0
 #endif
-// A/B switches of the record path (all on in the product build)
+// A/B switches of the record path (compile-time, for same-box comparisons: profiles/r02_ab_*.log); the values below are the product build
 #ifndef CSC_OPT_TREC
 #define CSC_OPT_TREC 1
 #endif
@@ -50,9 +50,6 @@
 #endif
 #ifndef CSC_OPT_BESTOF_OUT
 #define CSC_OPT_BESTOF_OUT 1
-#endif
-#ifndef CSC_OPT_FM_OUT
-#define CSC_OPT_FM_OUT 1
 #endif
 
 namespace cscb {
